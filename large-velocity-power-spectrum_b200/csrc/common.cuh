@@ -1,0 +1,133 @@
+// Internal helpers shared by the kernels of libvpower_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vpower_b200.h"
+
+void vp_set_error(const char* fmt, ...);
+
+#define VP_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      vp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return VP_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define VP_CHECK_LAUNCH() VP_CUDA(cudaGetLastError())
+
+#define VP_REQUIRE(cond, ...)      \
+  do {                             \
+    if (!(cond)) {                 \
+      vp_set_error(__VA_ARGS__);   \
+      return VP_ERR_ARG;           \
+    }                              \
+  } while (0)
+
+#define VP_TRY(expr)           \
+  do {                         \
+    int r__ = (expr);          \
+    if (r__ != VP_OK) return r__; \
+  } while (0)
+
+// Grow-only bump arena.  alloc() never frees; reset() rewinds.  If a request does not fit the arena
+// is re-allocated (after a device sync) -- callers take all their pointers after the last grow by
+// following the pattern  reserve(total) ; alloc() ; alloc() ...
+struct vp_arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+};
+
+struct vp_nn_stats_dev {
+  unsigned long long n_wide;        // nodes sent to the ring>=2 search
+  unsigned long long n_unresolved;  // nodes still unproven afterwards
+  unsigned long long n_kept;        // particles that survived the x filter
+  unsigned long long pad;
+};
+
+// optional per-stage timing with CUDA events on the launching stream (vp_profile_enable / vp_profile_report)
+struct vp_prof_rec {
+  const char* name;
+  cudaEvent_t a, b;
+  int launches;
+  double bytes;  // algorithmic bytes of the stage (0 if not stated)
+};
+
+struct vp_pk_plan;
+struct vp_ctx {
+  bool prof_on = false;
+  std::vector<vp_prof_rec> prof;
+  unsigned long long n_launch = 0;        // kernels launched by this ctx since creation
+  int device = 0;
+  vp_pk_plan* cached_plan = nullptr;      // last plan built by the host-buffer entry point
+  double* cached_plan_key = nullptr;      // host copy of (N, nbins, k table, edges) it was built for
+  size_t cached_plan_key_len = 0;
+  int sm_count = 148;
+  vp_arena arena;
+  vp_nn_stats_dev* nn_stats_d = nullptr;  // persistent small device block
+  double* small_d = nullptr;              // persistent device block for lattice tables etc. (grown on demand)
+  size_t small_cap = 0;
+  void* pinned_h = nullptr;               // pinned staging for small host->device tables
+  size_t pinned_cap = 0;
+};
+
+// Stack discipline: every entry point opens a vp_arena_scope (restores the offset on exit), calls
+// vp_arena_reserve(extra) once for everything it will carve, then vp_arena_alloc().  The block can only
+// be re-allocated while nothing is carved from it (offset 0); an outer caller that holds buffers across
+// inner calls therefore reserves the inner calls' needs up front (see pipeline.cu).
+int vp_arena_reserve(vp_ctx* ctx, size_t extra_bytes);
+void* vp_arena_alloc(vp_ctx* ctx, size_t bytes);  // 256-byte aligned; nullptr if it does not fit
+static inline size_t vp_align256(size_t b) { return (b + 255) & ~size_t(255); }
+struct vp_arena_scope {
+  vp_ctx* c;
+  size_t mark;
+  explicit vp_arena_scope(vp_ctx* ctx) : c(ctx), mark(ctx->arena.off) {}
+  ~vp_arena_scope() { c->arena.off = mark; }
+};
+
+// radix sort (radix_sort.cu).  Sorts in place (result ends in keys/vals); tmp must hold the scratch
+// reported by vp_sort_scratch_bytes(n).
+size_t vp_sort_scratch_bytes(int64_t n);
+int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
+                       cudaStream_t st);
+
+// internal forms used by pipeline.cu (typed device pointers, arena already reserved by the caller)
+size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* qx, int nx, const double* qy, int ny,
+                                       const double* qz, int nz, const vp_nn_opts* opts);
+size_t vp_pk_fields_scratch_bytes(const vp_pk_plan* plan);
+
+// stage timer: records an event pair around the launches between construction and destruction
+struct vp_stage {
+  vp_ctx* c;
+  cudaStream_t st;
+  int idx = -1;
+  vp_stage(vp_ctx* ctx, const char* name, cudaStream_t s, int launches, double bytes = 0.0) : c(ctx), st(s) {
+    c->n_launch += launches;
+    if (!c->prof_on) return;
+    vp_prof_rec r;
+    r.name = name;
+    r.launches = launches;
+    r.bytes = bytes;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    c->prof.push_back(r);
+    idx = int(c->prof.size()) - 1;
+  }
+  ~vp_stage() {
+    if (idx >= 0) cudaEventRecord(c->prof[idx].b, st);
+  }
+};
+
+static inline int vp_ceil_log2(uint64_t v) {
+  int b = 0;
+  while ((uint64_t(1) << b) < v) ++b;
+  return b;
+}

@@ -1,0 +1,634 @@
+// K4 + K5: in-place 3-D r2c FFT (z, y, x line passes) with |F|^2 and k-shell binning fused into the x pass.
+// See include/vpower_b200.h (vp_pk_plan_create / vp_pk_fields) and DESIGN.md for the data layout.
+//
+// Half-spectrum layout ("packed"): the real cube [N][N][N] f32 is overwritten by [N][N][N/2] complex64.
+// After the z pass entry kz=0 of every line holds (Re X[0], Re X[N/2]) -- both are real for a real line --
+// so the whole transform is in place with a power-of-two pitch.  The kz=0 column therefore carries two real
+// planes a+ib through the y and x passes; they are separated at the end by Hermitian symmetry
+// (k_plane_bin), all other columns are ordinary half-spectrum modes with weight 2.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+
+struct vp_pk_plan {
+  vp_ctx* ctx = nullptr;
+  int N = 0, nbins = 0;
+  bool pow2 = false;
+  float2* tw_full = nullptr;  // W_N^m
+  float2* tw_half = nullptr;  // W_{N/2}^m
+  double* kk2 = nullptr;      // k[i]^2, f64
+  double* thr = nullptr;      // nbins+1 thresholds on the squared magnitude
+  float2* plane0 = nullptr;   // [3][N][N] x-pass output of the kz=0 column
+  float inv_kf = 0.f;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ z pass: N reals -> N/2 packed complex
+template <int R2, int R3>
+__global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const float2* __restrict__ tw_half,
+                                               const float2* __restrict__ tw_full) {
+  using F = LineFFT<R2, R3, 1>;
+  constexpr int L = F::L, T = F::T, LINES = 256 / T, XS = xsize<L, 1>();
+  extern __shared__ float2 sm[];
+  const int tid = threadIdx.x, ll = tid / T, t = tid % T;
+  float2* g = reinterpret_cast<float2*>(data) + (size_t(blockIdx.x) * LINES + ll) * L;
+  float2* s = sm + ll * XS;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = g[j * T + t];
+  F::run(v, t, s, tw_half);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s[F::kout(j, t)] = v[j];
+  __syncthreads();
+  for (int k = t; k <= L / 2; k += T) {
+    if (k == 0) {
+      float2 z0 = s[0];
+      g[0] = make_float2(z0.x + z0.y, z0.x - z0.y);  // (X[0], X[N/2]) packed
+    } else if (k == L / 2) {
+      g[k] = cconj(s[k]);
+    } else {
+      float2 zk = s[k], zc = cconj(s[L - k]);
+      float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+      float2 d = cmul_mi(csub(zk, zc));
+      float2 o = make_float2(0.5f * d.x, 0.5f * d.y);
+      float2 wo = cmul(__ldg(tw_full + k), o);
+      g[k] = cadd(e, wo);
+      g[L - k] = cconj(csub(e, wo));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ y pass: lines strided by NZ, C columns per CTA
+template <int R2, int R3, int C>
+__global__ void __launch_bounds__(R2* R3* C) k_fft_y(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
+  using F = LineFFT<R2, R3, C>;
+  constexpr int L = F::L, T = F::T;
+  extern __shared__ float2 sm[];
+  const int tid = threadIdx.x, c = tid % C, t = tid / C;
+  const int tiles = NZ / C;
+  const int x = blockIdx.x / tiles, zt = blockIdx.x % tiles;
+  float2* base = data + size_t(x) * L * NZ + zt * C + c;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * NZ];
+  F::run(v, t, sm + c, tw);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) base[size_t(F::kout(j, t)) * NZ] = v[j];
+}
+
+// ------------------------------------------------------------------ x pass fused with |F|^2 and shell binning
+struct FieldSet {
+  float2* f[3];
+  int n;
+};
+
+constexpr int kBinSlots = 4;  // bins per thread (nbins <= kBinSlots * blockDim)
+
+// smallest row r in [0, nr] with  wrow[r] + zc >= thr  (nr = number of rows when none qualifies)
+__device__ __forceinline__ int first_row_at_or_above(const double* wrow, int nr, double zc, double thr, double base2,
+                                                     float inv_kf) {
+  double d = thr - zc - base2;
+  int r = 0;
+  if (d > 0.0) {
+    float rf = sqrtf(float(d)) * inv_kf;
+    r = rf >= float(nr) ? nr : int(rf);
+  }
+  while (r > 0 && __dadd_rn(wrow[r - 1], zc) >= thr) --r;
+  while (r < nr && __dadd_rn(wrow[r], zc) < thr) ++r;
+  return r;
+}
+
+template <int R2, int R3, int C>
+__global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, const float2* __restrict__ tw,
+                                                         const double* __restrict__ kk2, const double* __restrict__ thr_g,
+                                                         int nbins, float inv_kf, float2* __restrict__ plane0,
+                                                         double* __restrict__ psum_g, unsigned long long* __restrict__ cnt_g) {
+  using F = LineFFT<R2, R3, C>;
+  constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1;
+  extern __shared__ float2 sm[];                                   // exchange area, later the |F|^2 tile
+  float* pt = reinterpret_cast<float*>(sm);                        // [C][PP]
+  double* wrow = reinterpret_cast<double*>(sm + XS);               // [NR]   kx^2 + ky^2
+  double* kz2 = wrow + NR;                                         // [C]
+  double* thr = kz2 + C;                                           // [nbins+1]
+  static_assert(size_t(C) * PP * 4 <= size_t(XS) * 8, "P tile must fit in the exchange area");
+
+  const int tid = threadIdx.x, c = tid % C, t = tid / C;
+  const int tiles_z = NZ / C;
+  const int ntiles = L * tiles_z;
+  const size_t xstride = size_t(L) * NZ;
+
+  for (int i = tid; i <= nbins; i += NT) thr[i] = thr_g[i];
+  double acc[kBinSlots];
+  unsigned long long cnt[kBinSlots];
+#pragma unroll
+  for (int s = 0; s < kBinSlots; ++s) { acc[s] = 0.0; cnt[s] = 0ull; }
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ky = tile / tiles_z, zt = tile % tiles_z;
+    float p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = 0.f;
+    for (int comp = 0; comp < fs.n; ++comp) {
+      const float2* base = fs.f[comp] + size_t(ky) * NZ + zt * C + c;
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+      __syncthreads();  // previous user of the exchange area is done
+      F::run(v, t, sm + c, tw);
+      if (zt == 0 && c == 0) {
+        float2* pl = plane0 + (size_t(comp) * L + ky) * L;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pl[F::kout(j, t)] = v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p[j] += v[j].x * v[j].x + v[j].y * v[j].y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pt[c * PP + F::kout(j, t)] = p[j];
+    const double ky2 = kk2[ky];
+    for (int r = tid; r < NR; r += NT) wrow[r] = __dadd_rn(kk2[r], ky2);
+    if (tid < C) kz2[tid] = kk2[zt * C + tid];
+    __syncthreads();
+
+    // every thread owns bins tid, tid+NT, ... and sums the rows of each column that fall into them
+    const int c0 = (zt == 0) ? 1 : 0;
+#pragma unroll
+    for (int s = 0; s < kBinSlots; ++s) {
+      const int b = tid + s * NT;
+      if (b < nbins) {
+        const double tlo = thr[b], thi = thr[b + 1];
+        float a = 0.f;
+        unsigned n = 0;
+        for (int cc = c0; cc < C; ++cc) {
+          const double zc = kz2[cc];
+          if (__dadd_rn(wrow[0], zc) >= thi || __dadd_rn(wrow[NR - 1], zc) < tlo) continue;
+          const int r0 = first_row_at_or_above(wrow, NR, zc, tlo, ky2, inv_kf);
+          const int r1 = first_row_at_or_above(wrow, NR, zc, thi, ky2, inv_kf);
+          const float* col = pt + cc * PP;
+          for (int r = r0; r < r1; ++r) {
+            float q = col[r];
+            if (r > 0 && r < L / 2) { q += col[L - r]; n += 2; } else n += 1;
+            a += q;
+          }
+        }
+        acc[s] += double(a);
+        cnt[s] += n;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kBinSlots; ++s) {
+    const int b = tid + s * NT;
+    if (b < nbins && cnt[s]) {
+      atomicAdd(psum_g + b, 2.0 * acc[s]);   // Hermitian partner of every kz in [1, N/2-1]
+      atomicAdd(cnt_g + b, 2ull * cnt[s]);
+    }
+  }
+}
+
+__device__ __forceinline__ int bin_of(double s, const double* __restrict__ thr, int nbins) {
+  // number of thresholds <= s, minus one
+  int lo = 0, hi = nbins + 1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (thr[mid] <= s) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;  // -1: below first edge; nbins: beyond last
+}
+
+// kz = 0 and kz = N/2 planes from the packed column:  A = (Z(k) + conj Z(-k))/2,  B = (Z(k) - conj Z(-k))/(2i)
+__global__ void __launch_bounds__(256) k_plane_bin(const float2* __restrict__ plane0, int ncomp, int N,
+                                                   const double* __restrict__ kk2, const double* __restrict__ thr, int nbins,
+                                                   double* __restrict__ psum_g, unsigned long long* __restrict__ cnt_g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  int ky = i / N, kx = i % N;
+  int my = (N - ky) % N, mx = (N - kx) % N;
+  float pa = 0.f, pb = 0.f;
+  for (int comp = 0; comp < ncomp; ++comp) {
+    const float2* pl = plane0 + size_t(comp) * N * N;
+    float2 zp = pl[size_t(ky) * N + kx], zm = cconj(pl[size_t(my) * N + mx]);
+    float2 a = make_float2(0.5f * (zp.x + zm.x), 0.5f * (zp.y + zm.y));
+    float2 d = csub(zp, zm);
+    pa += a.x * a.x + a.y * a.y;
+    pb += 0.25f * (d.x * d.x + d.y * d.y);
+  }
+  double w = __dadd_rn(kk2[kx], kk2[ky]);
+  int ba = bin_of(__dadd_rn(w, kk2[0]), thr, nbins), bb = bin_of(__dadd_rn(w, kk2[N / 2]), thr, nbins);
+  if (ba >= 0 && ba < nbins) { atomicAdd(psum_g + ba, double(pa)); atomicAdd(cnt_g + ba, 1ull); }
+  if (bb >= 0 && bb < nbins) { atomicAdd(psum_g + bb, double(pb)); atomicAdd(cnt_g + bb, 1ull); }
+}
+
+// ------------------------------------------------------------------ standalone binning of a full power cube
+__global__ void __launch_bounds__(256) k_bin_full(const double* __restrict__ P, int N, const double* __restrict__ kk2,
+                                                  const double* __restrict__ thr, int nbins, double* __restrict__ psum_g,
+                                                  unsigned long long* __restrict__ cnt_g) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= size_t(N) * N * N) return;
+  int kz = int(i % N);
+  size_t t = i / N;
+  int ky = int(t % N), kx = int(t / N);
+  double s = __dadd_rn(__dadd_rn(kk2[kx], kk2[ky]), kk2[kz]);
+  int b = bin_of(s, thr, nbins);
+  if (b >= 0 && b < nbins) { atomicAdd(psum_g + b, P[i]); atomicAdd(cnt_g + b, 1ull); }
+}
+
+// ------------------------------------------------------------------ any-N fallback (direct DFT per axis)
+__global__ void k_real_to_complex(const float* __restrict__ f, float2* __restrict__ z, size_t n) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = make_float2(f[i], 0.f);
+}
+// one CTA per line; line element n at base + n*stride
+__global__ void __launch_bounds__(128) k_dft_axis(float2* __restrict__ z, int N, size_t stride, int n_inner, size_t outer_stride,
+                                                  size_t inner_stride, const double2* __restrict__ tw) {
+  extern __shared__ float2 line[];
+  size_t base = size_t(blockIdx.x / n_inner) * outer_stride + size_t(blockIdx.x % n_inner) * inner_stride;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) line[n] = z[base + n * stride];
+  __syncthreads();
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    double re = 0, im = 0;
+    int m = 0;
+    for (int n = 0; n < N; ++n) {
+      double2 w = tw[m];
+      re += double(line[n].x) * w.x - double(line[n].y) * w.y;
+      im += double(line[n].x) * w.y + double(line[n].y) * w.x;
+      m += k;
+      if (m >= N) m -= N;
+    }
+    z[base + k * stride] = make_float2(float(re), float(im));
+  }
+}
+__global__ void k_accum_power(const float2* __restrict__ z, double* __restrict__ P, size_t n, int first) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = double(z[i].x) * z[i].x + double(z[i].y) * z[i].y;
+  P[i] = first ? v : P[i] + v;
+}
+
+__global__ void k_unpack_half(const float2* __restrict__ packed, int N, float2* __restrict__ half) {
+  // half[x][y][kz], kz in [0, N/2]
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int NZ = N / 2, NH = NZ + 1;
+  if (i >= size_t(N) * N * NH) return;
+  int kz = int(i % NH);
+  size_t t = i / NH;
+  int y = int(t % N), x = int(t / N);
+  if (kz > 0 && kz < NZ) { half[i] = packed[(size_t(x) * N + y) * NZ + kz]; return; }
+  int my = (N - y) % N, mx = (N - x) % N;
+  float2 zp = packed[(size_t(x) * N + y) * NZ], zm = cconj(packed[(size_t(mx) * N + my) * NZ]);
+  if (kz == 0) half[i] = make_float2(0.5f * (zp.x + zm.x), 0.5f * (zp.y + zm.y));
+  else {
+    float2 d = cmul_mi(csub(zp, zm));
+    half[i] = make_float2(0.5f * d.x, 0.5f * d.y);
+  }
+}
+
+// full-cube power from the packed half spectrum: every (x,y,kz<=N/2) writes itself and its Hermitian partner
+__global__ void k_expand_power(const float2* __restrict__ packed, int N, double* __restrict__ P, int first) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int NZ = N / 2, NH = NZ + 1;
+  if (i >= size_t(N) * N * NH) return;
+  int kz = int(i % NH);
+  size_t t = i / NH;
+  int y = int(t % N), x = int(t / N);
+  int my = (N - y) % N, mx = (N - x) % N;
+  float2 f;
+  if (kz > 0 && kz < NZ) f = packed[(size_t(x) * N + y) * NZ + kz];
+  else {
+    float2 zp = packed[(size_t(x) * N + y) * NZ], zm = cconj(packed[(size_t(mx) * N + my) * NZ]);
+    if (kz == 0) f = make_float2(0.5f * (zp.x + zm.x), 0.5f * (zp.y + zm.y));
+    else { float2 d = cmul_mi(csub(zp, zm)); f = make_float2(0.5f * d.x, 0.5f * d.y); }
+  }
+  double p = double(f.x) * f.x + double(f.y) * f.y;
+  size_t o = (size_t(x) * N + y) * N + kz;
+  P[o] = first ? p : P[o] + p;
+  if (kz > 0 && kz < NZ) {
+    size_t o2 = (size_t(mx) * N + my) * N + (N - kz);
+    P[o2] = first ? p : P[o2] + p;
+  }
+}
+
+// ------------------------------------------------------------------ launch helpers
+template <int R2, int R3>
+int launch_z(float* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
+  using F = LineFFT<R2, R3, 1>;
+  constexpr int LINES = 256 / F::T;
+  size_t smem = size_t(LINES) * xsize<F::L, 1>() * sizeof(float2);
+  static bool attr = false;
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_z<R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  size_t nlines = size_t(N) * N;
+  vp_stage stage(pl->ctx, "k4a_fft_z", st, 1, 8.0 * double(N) * N * N);   // 4 B/real read + 4 B/real written in place
+  k_fft_z<R2, R3><<<unsigned(nlines / LINES), 256, smem, st>>>(data, pl->tw_half, pl->tw_full);
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+template <int R2, int R3, int C>
+int launch_y(float2* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
+  using F = LineFFT<R2, R3, C>;
+  size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2);
+  static bool attr = false;
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_y<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  const int NZ = N / 2;
+  vp_stage stage(pl->ctx, "k4b_fft_y", st, 1, 8.0 * double(N) * N * N);   // 8 B/mode read + written, N^3/2 modes
+  k_fft_y<R2, R3, C><<<unsigned(N * (NZ / C)), F::T * C, smem, st>>>(data, NZ, pl->tw_full);
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+template <int R2, int R3, int C>
+int launch_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+  using F = LineFFT<R2, R3, C>;
+  constexpr int NT = F::T * C;
+  VP_REQUIRE(pl->nbins <= kBinSlots * NT, "vp_pk_fields: nbins=%d exceeds %d for N=%d", pl->nbins, kBinSlots * NT, N);
+  size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2) + (size_t(F::L / 2 + 1) + C + pl->nbins + 1) * sizeof(double);
+  VP_CUDA(cudaFuncSetAttribute(k_fft_x_bin<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int occ = 1;
+  VP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fft_x_bin<R2, R3, C>, NT, smem));
+  if (occ < 1) occ = 1;
+  const int NZ = N / 2;
+  int ntiles = N * (NZ / C);
+  int grid = pl->ctx->sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  vp_stage stage(pl->ctx, "k4c_fft_x_bin", st, 1, 4.0 * double(N) * N * N * fs.n);   // 8 B/mode read, nothing written
+  k_fft_x_bin<R2, R3, C><<<grid, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->kk2, pl->thr, pl->nbins, pl->inv_kf, pl->plane0, psum, cnt);
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+int run_z(float* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
+  switch (N) {
+    case 64: return launch_z<2, 1>(d, N, pl, st);
+    case 128: return launch_z<4, 1>(d, N, pl, st);
+    case 256: return launch_z<8, 1>(d, N, pl, st);
+    case 512: return launch_z<16, 1>(d, N, pl, st);
+    case 1024: return launch_z<16, 2>(d, N, pl, st);
+    case 2048: return launch_z<16, 4>(d, N, pl, st);
+  }
+  vp_set_error("fft z pass: unsupported N=%d", N);
+  return VP_ERR_UNSUPPORTED;
+}
+int run_y(float2* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
+  switch (N) {
+    case 64: return launch_y<4, 1, 32>(d, N, pl, st);
+    case 128: return launch_y<8, 1, 32>(d, N, pl, st);
+    case 256: return launch_y<16, 1, 16>(d, N, pl, st);
+    case 512: return launch_y<16, 2, 8>(d, N, pl, st);
+    case 1024: return launch_y<16, 4, 8>(d, N, pl, st);
+    case 2048: return launch_y<16, 8, 8>(d, N, pl, st);
+  }
+  vp_set_error("fft y pass: unsupported N=%d", N);
+  return VP_ERR_UNSUPPORTED;
+}
+int run_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+  switch (N) {
+    case 64: return launch_x_bin<4, 1, 32>(fs, N, pl, psum, cnt, st);
+    case 128: return launch_x_bin<8, 1, 32>(fs, N, pl, psum, cnt, st);
+    case 256: return launch_x_bin<16, 1, 16>(fs, N, pl, psum, cnt, st);
+    case 512: return launch_x_bin<16, 2, 8>(fs, N, pl, psum, cnt, st);
+    case 1024: return launch_x_bin<16, 4, 8>(fs, N, pl, psum, cnt, st);
+    case 2048: return launch_x_bin<16, 8, 8>(fs, N, pl, psum, cnt, st);
+  }
+  vp_set_error("fft x pass: unsupported N=%d", N);
+  return VP_ERR_UNSUPPORTED;
+}
+
+// the x pass without binning (diagnostic transform): reuse the y kernel on a transposed view is not possible
+// in place, so the diagnostic transform runs the x lines with the generic strided kernel below.
+template <int R2, int R3, int C>
+__global__ void __launch_bounds__(R2* R3* C) k_fft_x(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
+  using F = LineFFT<R2, R3, C>;
+  constexpr int L = F::L, T = F::T;
+  extern __shared__ float2 sm[];
+  const int tid = threadIdx.x, c = tid % C, t = tid / C;
+  const int tiles = NZ / C;
+  const int y = blockIdx.x / tiles, zt = blockIdx.x % tiles;
+  const size_t xstride = size_t(L) * NZ;
+  float2* base = data + size_t(y) * NZ + zt * C + c;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+  F::run(v, t, sm + c, tw);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) base[size_t(F::kout(j, t)) * xstride] = v[j];
+}
+template <int R2, int R3, int C>
+int launch_x(float2* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
+  using F = LineFFT<R2, R3, C>;
+  size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2);
+  static bool attr = false;
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  const int NZ = N / 2;
+  vp_stage stage(pl->ctx, "k4c_fft_x", st, 1, 8.0 * double(N) * N * N);
+  k_fft_x<R2, R3, C><<<unsigned(N * (NZ / C)), F::T * C, smem, st>>>(data, NZ, pl->tw_full);
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+int run_x(float2* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
+  switch (N) {
+    case 64: return launch_x<4, 1, 32>(d, N, pl, st);
+    case 128: return launch_x<8, 1, 32>(d, N, pl, st);
+    case 256: return launch_x<16, 1, 16>(d, N, pl, st);
+    case 512: return launch_x<16, 2, 8>(d, N, pl, st);
+    case 1024: return launch_x<16, 4, 8>(d, N, pl, st);
+    case 2048: return launch_x<16, 8, 8>(d, N, pl, st);
+  }
+  vp_set_error("fft x pass: unsupported N=%d", N);
+  return VP_ERR_UNSUPPORTED;
+}
+
+// threshold on s = |k|^2 equivalent to the comparison  sqrt(s) >= e  (strict = false) or  sqrt(s) > e  (strict = true)
+double sq_threshold(double e, bool strict) {
+  if (!(e > 0.0)) {
+    if (!strict || e < 0.0) return 0.0;       // every s >= 0 qualifies
+    return nextafter(0.0, 1.0);               // sqrt(s) > 0
+  }
+  double s = e * e;
+  auto ok = [&](double v) { double r = sqrt(v); return strict ? r > e : r >= e; };
+  while (ok(s)) { double p = nextafter(s, -INFINITY); if (p < 0.0) break; if (!ok(p)) break; s = p; }
+  while (!ok(s)) s = nextafter(s, INFINITY);
+  return s;
+}
+
+}  // namespace
+
+extern "C" int vp_pk_plan_create(vp_ctx* ctx, int N, const double* k_h, const double* edges_h, int nbins, vp_pk_plan** out) {
+  VP_REQUIRE(ctx && k_h && edges_h && out, "vp_pk_plan_create: null argument");
+  VP_REQUIRE(N >= 2 && nbins >= 1, "vp_pk_plan_create: bad sizes");
+  for (int j = 0; j < nbins; ++j)
+    VP_REQUIRE(edges_h[j + 1] > edges_h[j], "vp_pk_plan_create: edges must increase");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  vp_pk_plan* p = new vp_pk_plan();
+  p->ctx = ctx;
+  p->N = N;
+  p->nbins = nbins;
+  bool is_pow2 = (N & (N - 1)) == 0 && N >= 64 && N <= 2048;
+  // the fused binning folds kx <-> -kx: needs a symmetric k table (true for fftfreq; false with a fold shift)
+  bool symmetric = true;
+  for (int r = 1; r < N / 2; ++r)
+    if (k_h[r] * k_h[r] != k_h[N - r] * k_h[N - r]) symmetric = false;
+  for (int r = 1; r <= N / 2; ++r)
+    if (!(k_h[r] * k_h[r] >= k_h[r - 1] * k_h[r - 1])) symmetric = false;  // rows must be ordered in |kx|
+  p->pow2 = is_pow2 && symmetric && (N % 2 == 0);
+  std::vector<double> kk2(N), thr(nbins + 1);
+  for (int i = 0; i < N; ++i) kk2[i] = k_h[i] * k_h[i];
+  for (int j = 0; j < nbins; ++j) thr[j] = sq_threshold(edges_h[j], false);
+  thr[nbins] = sq_threshold(edges_h[nbins], true);
+  p->inv_kf = (N > 1 && fabs(k_h[1]) > 0) ? float(1.0 / fabs(k_h[1])) : 1.f;
+  std::vector<float2> twf(N), twh(N / 2 > 0 ? N / 2 : 1);
+  for (int m = 0; m < N; ++m) twf[m] = make_float2(float(cos(2.0 * M_PI * m / N)), float(-sin(2.0 * M_PI * m / N)));
+  for (int m = 0; m < N / 2; ++m)
+    twh[m] = make_float2(float(cos(2.0 * M_PI * m / (N / 2))), float(-sin(2.0 * M_PI * m / (N / 2))));
+  auto fail = [&](const char* what) { vp_set_error("vp_pk_plan_create: %s", what); vp_pk_plan_destroy(p); return VP_ERR_NOMEM; };
+  if (cudaMalloc(&p->tw_full, sizeof(float2) * N) != cudaSuccess) return fail("cudaMalloc tw_full");
+  if (cudaMalloc(&p->tw_half, sizeof(float2) * twh.size()) != cudaSuccess) return fail("cudaMalloc tw_half");
+  if (cudaMalloc(&p->kk2, sizeof(double) * N) != cudaSuccess) return fail("cudaMalloc kk2");
+  if (cudaMalloc(&p->thr, sizeof(double) * (nbins + 1)) != cudaSuccess) return fail("cudaMalloc thr");
+  if (p->pow2 && cudaMalloc(&p->plane0, sizeof(float2) * 3 * size_t(N) * N) != cudaSuccess) return fail("cudaMalloc plane0");
+  VP_CUDA(cudaMemcpy(p->tw_full, twf.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+  VP_CUDA(cudaMemcpy(p->tw_half, twh.data(), sizeof(float2) * twh.size(), cudaMemcpyHostToDevice));
+  VP_CUDA(cudaMemcpy(p->kk2, kk2.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  VP_CUDA(cudaMemcpy(p->thr, thr.data(), sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice));
+  *out = p;
+  return VP_OK;
+}
+
+extern "C" int vp_pk_plan_destroy(vp_pk_plan* p) {
+  if (!p) return VP_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaDeviceSynchronize();
+  if (p->tw_full) cudaFree(p->tw_full);
+  if (p->tw_half) cudaFree(p->tw_half);
+  if (p->kk2) cudaFree(p->kk2);
+  if (p->thr) cudaFree(p->thr);
+  if (p->plane0) cudaFree(p->plane0);
+  delete p;
+  return VP_OK;
+}
+
+size_t vp_pk_fields_scratch_bytes(const vp_pk_plan* pl) {
+  if (pl->pow2) return 0;
+  const size_t n3 = size_t(pl->N) * pl->N * pl->N;
+  return vp_align256(n3 * sizeof(float2)) + vp_align256(n3 * sizeof(double)) + vp_align256(sizeof(double2) * pl->N) + 16384;
+}
+
+// any-N path: full complex transform by direct DFT along each axis -> P = sum_c |F_c|^2 (f64 cube)
+static int power_cube_generic(vp_pk_plan* pl, float* const* field_d, int ncomp, double* P, cudaStream_t st) {
+  const int N = pl->N;
+  const size_t n3 = size_t(N) * N * N;
+  vp_ctx* ctx = pl->ctx;
+  size_t need = vp_align256(n3 * sizeof(float2)) + vp_align256(sizeof(double2) * N);
+  vp_arena_scope scope(ctx);
+  VP_TRY(vp_arena_reserve(ctx, need));
+  float2* z = static_cast<float2*>(vp_arena_alloc(ctx, n3 * sizeof(float2)));
+  double2* tw = static_cast<double2*>(vp_arena_alloc(ctx, sizeof(double2) * N));
+  VP_REQUIRE(z && tw, "power_cube_generic: arena carve failed");
+  std::vector<double2> twh(N);
+  for (int m = 0; m < N; ++m) twh[m] = make_double2(cos(2.0 * M_PI * m / N), -sin(2.0 * M_PI * m / N));
+  VP_CUDA(cudaMemcpyAsync(tw, twh.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, st));
+  VP_CUDA(cudaStreamSynchronize(st));
+  const unsigned nb = unsigned((n3 + 255) / 256);
+  const size_t smem = sizeof(float2) * N;
+  vp_stage stage(ctx, "generic_dft", st, 5 * ncomp);
+  for (int c = 0; c < ncomp; ++c) {
+    k_real_to_complex<<<nb, 256, 0, st>>>(field_d[c], z, n3);
+    k_dft_axis<<<unsigned(N * N), 128, smem, st>>>(z, N, 1, N, size_t(N) * N, size_t(N), tw);   // z lines
+    k_dft_axis<<<unsigned(N * N), 128, smem, st>>>(z, N, size_t(N), N, size_t(N) * N, 1, tw);   // y lines
+    k_dft_axis<<<unsigned(N * N), 128, smem, st>>>(z, N, size_t(N) * N, N, size_t(N), 1, tw);   // x lines
+    k_accum_power<<<nb, 256, 0, st>>>(z, P, n3, c == 0);
+    VP_CHECK_LAUNCH();
+  }
+  return VP_OK;
+}
+
+static int pk_fields_generic(vp_pk_plan* pl, float* const* field_d, int ncomp, double* psum_d, uint64_t* nsample_d, cudaStream_t st) {
+  const size_t n3 = size_t(pl->N) * pl->N * pl->N;
+  vp_arena_scope scope(pl->ctx);
+  VP_TRY(vp_arena_reserve(pl->ctx, vp_pk_fields_scratch_bytes(pl)));
+  double* P = static_cast<double*>(vp_arena_alloc(pl->ctx, n3 * sizeof(double)));
+  VP_REQUIRE(P, "pk_fields_generic: arena carve failed");
+  VP_TRY(power_cube_generic(pl, field_d, ncomp, P, st));
+  return vp_power_bin_full(pl, P, psum_d, nsample_d, st);
+}
+
+extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
+  VP_REQUIRE(pl && field_d && psum_d && nsample_d, "vp_pk_fields: null argument");
+  VP_REQUIRE(ncomp >= 1 && ncomp <= 3, "vp_pk_fields: ncomp must be 1..3");
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!pl->pow2) return pk_fields_generic(pl, field_d, ncomp, psum_d, nsample_d, st);
+  const int N = pl->N;
+  VP_CUDA(cudaMemsetAsync(psum_d, 0, sizeof(double) * pl->nbins, st));
+  VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
+  FieldSet fs;
+  fs.n = ncomp;
+  for (int c = 0; c < 3; ++c) fs.f[c] = nullptr;
+  for (int c = 0; c < ncomp; ++c) {
+    VP_REQUIRE(field_d[c], "vp_pk_fields: null field %d", c);
+    VP_TRY(run_z(field_d[c], N, pl, st));
+    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), N, pl, st));
+    fs.f[c] = reinterpret_cast<float2*>(field_d[c]);
+  }
+  VP_TRY(run_x_bin(fs, N, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
+  vp_stage stage(pl->ctx, "k5_plane_bin", st, 1, 8.0 * double(N) * N * ncomp);
+  k_plane_bin<<<unsigned((size_t(N) * N + 255) / 256), 256, 0, st>>>(pl->plane0, ncomp, N, pl->kk2, pl->thr, pl->nbins, psum_d,
+                                                                  reinterpret_cast<unsigned long long*>(nsample_d));
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) {
+  VP_REQUIRE(pl && field_d, "vp_fft_r2c_inplace: null argument");
+  if (!pl->pow2) { vp_set_error("vp_fft_r2c_inplace: N=%d has no packed fast path", pl->N); return VP_ERR_UNSUPPORTED; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VP_TRY(run_z(field_d, pl->N, pl, st));
+  VP_TRY(run_y(reinterpret_cast<float2*>(field_d), pl->N, pl, st));
+  return run_x(reinterpret_cast<float2*>(field_d), pl->N, pl, st);
+}
+
+extern "C" int vp_power_cube(vp_pk_plan* pl, float* const* field_d, int ncomp, double* P_d, void* stream) {
+  VP_REQUIRE(pl && field_d && P_d && ncomp >= 1 && ncomp <= 3, "vp_power_cube: bad argument");
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!pl->pow2) return power_cube_generic(pl, field_d, ncomp, P_d, st);
+  const int N = pl->N;
+  size_t n = size_t(N) * N * (N / 2 + 1);
+  for (int c = 0; c < ncomp; ++c) {
+    VP_TRY(vp_fft_r2c_inplace(pl, field_d[c], stream));
+    vp_stage stage(pl->ctx, "expand_power", st, 1);
+    k_expand_power<<<unsigned((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(field_d[c]), N, P_d, c == 0);
+    VP_CHECK_LAUNCH();
+  }
+  return VP_OK;
+}
+
+extern "C" int vp_fft_unpack_half(vp_pk_plan* pl, const float* packed_d, float* half_d, void* stream) {
+  VP_REQUIRE(pl && packed_d && half_d, "vp_fft_unpack_half: null argument");
+  const int N = pl->N;
+  size_t n = size_t(N) * N * (N / 2 + 1);
+  vp_stage stage(pl->ctx, "unpack_half", static_cast<cudaStream_t>(stream), 1);
+  k_unpack_half<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(packed_d), N, reinterpret_cast<float2*>(half_d));
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+extern "C" int vp_power_bin_full(vp_pk_plan* pl, const double* P_d, double* psum_d, uint64_t* nsample_d, void* stream) {
+  VP_REQUIRE(pl && P_d && psum_d && nsample_d, "vp_power_bin_full: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = pl->N;
+  VP_CUDA(cudaMemsetAsync(psum_d, 0, sizeof(double) * pl->nbins, st));
+  VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
+  size_t n3 = size_t(N) * N * N;
+  vp_stage stage(pl->ctx, "k5_bin_full", st, 1, 8.0 * double(n3));
+  k_bin_full<<<unsigned((n3 + 255) / 256), 256, 0, st>>>(P_d, N, pl->kk2, pl->thr, pl->nbins, psum_d,
+                                                       reinterpret_cast<unsigned long long*>(nsample_d));
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}

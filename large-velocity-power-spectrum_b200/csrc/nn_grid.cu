@@ -1,0 +1,566 @@
+// K1: exact nearest-particle gridding on a sorted cell list.  See include/vpower_b200.h (vp_nn_grid).
+//
+// Pipeline:  keygen (cell key per particle, optional x filter)  ->  radix sort of (key, index)
+//            ->  reorder to sorted {x,y,z,index}  ->  cell starts  ->  ring-1 search per lattice node
+//            ->  wide (ring >= 2, warp per node) search for the nodes ring 1 could not prove.
+//
+// Exactness: a candidate is accepted only if its distance is strictly below the distance from the
+// node to every face of the searched cell block behind which unexamined particles can exist.  All
+// distance arithmetic is f64 with the reference's association ((dx*dx+dy*dy)+dz*dz) and no FMA
+// contraction (explicit __dmul_rn/__dadd_rn); ties go to the lowest particle index.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+struct Grid {
+  double ox, oy, oz;     // origin of cell (0,0,0)
+  double hx, hy, hz;     // cell size
+  double ihx, ihy, ihz;  // 1/cell size
+  int gx, gy, gz;
+  int use_keep;
+  double keep_lo, keep_hi;
+  int closed_xlo, closed_xhi;  // 1: particles beyond that x face were dropped (face constrains the proof)
+};
+
+template <typename T>
+struct Sorted;  // sorted particle record
+template <>
+struct Sorted<float> {
+  using rec = float4;  // x,y,z, index bits
+  __device__ static rec make(float x, float y, float z, int i) { return make_float4(x, y, z, __int_as_float(i)); }
+  __device__ static void get(const rec* __restrict__ a, int64_t p, double& x, double& y, double& z, int& i) {
+    float4 r = __ldg(a + p);
+    x = r.x; y = r.y; z = r.z; i = __float_as_int(r.w);
+  }
+};
+template <>
+struct Sorted<double> {
+  struct __align__(16) rec { double x, y, z; long long i; };
+  __device__ static rec make(double x, double y, double z, int i) { rec r; r.x = x; r.y = y; r.z = z; r.i = i; return r; }
+  __device__ static void get(const rec* __restrict__ a, int64_t p, double& x, double& y, double& z, int& i) {
+    const double2* q = reinterpret_cast<const double2*>(a + p);
+    double2 u = __ldg(q), v = __ldg(q + 1);
+    x = u.x; y = u.y; z = v.x; i = int(__double_as_longlong(v.y));
+  }
+};
+
+__device__ __forceinline__ int cell_of(double x, double o, double ih, int g) {
+  double f = (x - o) * ih;
+  if (!(f > 0.0)) return 0;
+  if (f >= double(g)) return g - 1;
+  return int(f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_keygen(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ keys,
+                                                 uint32_t* __restrict__ vals, unsigned long long* __restrict__ kept) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  bool ok = i < np;
+  double x = 0, y = 0, z = 0;
+  if (ok) {
+    x = pos[3 * i];
+    y = pos[3 * i + 1];
+    z = pos[3 * i + 2];
+    if (g.use_keep && !(x >= g.keep_lo && x <= g.keep_hi)) ok = false;
+  }
+  uint32_t key = 0;
+  if (ok) {
+    int cx = cell_of(x, g.ox, g.ihx, g.gx), cy = cell_of(y, g.oy, g.ihy, g.gy), cz = cell_of(z, g.oz, g.ihz, g.gz);
+    key = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+  }
+  if (!g.use_keep) {
+    if (ok) { keys[i] = key; vals[i] = uint32_t(i); }
+    return;
+  }
+  // compaction (order is irrelevant: the sort follows and ties are decided by index)
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0 && m) base = atomicAdd(kept, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (ok) {
+    unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+    keys[o] = key;
+    vals[o] = uint32_t(i);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_reorder(const T* __restrict__ pos, const uint32_t* __restrict__ vals, int64_t n,
+                                                  typename Sorted<T>::rec* __restrict__ out) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t j = vals[i];
+  out[i] = Sorted<T>::make(pos[3 * size_t(j)], pos[3 * size_t(j) + 1], pos[3 * size_t(j) + 2], int(j));
+}
+
+// start[c] = first sorted position whose key >= c, for c in [0, ncells]; start[ncells] = n
+__global__ void __launch_bounds__(256) k_cell_starts(const uint32_t* __restrict__ keys, int64_t n, uint32_t ncells,
+                                                      uint32_t* __restrict__ start) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  int64_t lo = 1, hi = 0;  // empty range
+  uint32_t v = 0;
+  if (i < n) {
+    uint32_t k = keys[i];
+    int64_t kp = (i == 0) ? -1 : int64_t(keys[i - 1]);
+    if (int64_t(k) != kp) { lo = kp + 1; hi = k; v = uint32_t(i); }
+    if (i == n - 1) {
+      // tail: cells after the last key (done by this thread after its own range)
+      for (int64_t c = lo; c <= hi; ++c) start[c] = v;
+      lo = int64_t(k) + 1; hi = ncells; v = uint32_t(n);
+    }
+  }
+  // long gaps are filled by the whole warp
+  const int lane = threadIdx.x & 31;
+  unsigned big = __ballot_sync(0xffffffffu, hi - lo >= 32);
+  while (big) {
+    int src = __ffs(big) - 1;
+    big &= big - 1;
+    int64_t l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
+    uint32_t vv = __shfl_sync(0xffffffffu, v, src);
+    for (int64_t c = l + lane; c <= h; c += 32) start[c] = vv;
+    if (lane == src) { lo = 1; hi = 0; }
+  }
+  for (int64_t c = lo; c <= hi; ++c) start[c] = v;
+}
+
+__global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+struct Best {
+  double d2;
+  int idx;
+};
+
+__device__ __forceinline__ void consider(Best& b, double qx, double qy, double qz, double x, double y, double z, int i) {
+  double dx = qx - x, dy = qy - y, dz = qz - z;
+  double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  if (d2 < b.d2 || (d2 == b.d2 && i < b.idx)) { b.d2 = d2; b.idx = i; }
+}
+
+// Distance from coordinate q to the nearest face of the cell block [c0,c1] (inclusive) along one axis
+// behind which unexamined particles may exist; +inf when both sides are open ends of the grid.
+__device__ __forceinline__ double axis_margin(double q, double o, double h, int c0, int c1, int g, bool closed_lo,
+                                              bool closed_hi) {
+  double m = INFINITY;
+  if (c0 > 0) m = fmin(m, q - (o + double(c0) * h));
+  else if (closed_lo) m = fmin(m, q - o);
+  if (c1 < g - 1) m = fmin(m, (o + double(c1 + 1) * h) - q);
+  else if (closed_hi) m = fmin(m, (o + double(g) * h) - q);
+  return m;
+}
+
+__device__ __forceinline__ bool proven(const Best& b, double margin) {
+  if (margin == INFINITY) return true;
+  if (!(margin > 0.0)) return false;
+  double ms = margin * (1.0 - 1.0 / 1048576.0);  // slack for the rounding of the cell assignment
+  return b.d2 < ms * ms;
+}
+
+struct Lattice {
+  const double *qx, *qy, *qz;  // node coordinates
+  const int *cx, *cy, *cz;     // cell of each node coordinate (clamped)
+  int nx, ny, nz;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_search_ring1(const typename Sorted<T>::rec* __restrict__ part,
+                                                       const uint32_t* __restrict__ start, Grid g, Lattice L,
+                                                       int32_t* __restrict__ nn, uint32_t* __restrict__ wide_list,
+                                                       vp_nn_stats_dev* __restrict__ stats) {
+  const int64_t nnodes = int64_t(L.nx) * L.ny * L.nz;
+  int64_t node = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (node >= nnodes) return;
+  int k = int(node % L.nz);
+  int64_t t = node / L.nz;
+  int j = int(t % L.ny), i = int(t / L.ny);
+  const double qx = L.qx[i], qy = L.qy[j], qz = L.qz[k];
+  const int cx = L.cx[i], cy = L.cy[j], cz = L.cz[k];
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
+  const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gy - 1);
+  const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+  Best b;
+  b.d2 = INFINITY;
+  b.idx = 0x7fffffff;
+  for (int X = x0; X <= x1; ++X)
+    for (int Y = y0; Y <= y1; ++Y) {
+      size_t row = (size_t(X) * g.gy + Y) * g.gz;
+      uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
+      for (uint32_t p = s; p < e; ++p) {
+        double x, y, z;
+        int id;
+        Sorted<T>::get(part, p, x, y, z, id);
+        consider(b, qx, qy, qz, x, y, z, id);
+      }
+    }
+  double m = fmin(axis_margin(qx, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
+                  fmin(axis_margin(qy, g.oy, g.hy, y0, y1, g.gy, false, false),
+                       axis_margin(qz, g.oz, g.hz, z0, z1, g.gz, false, false)));
+  if (proven(b, m)) {
+    nn[node] = b.idx;
+  } else {
+    nn[node] = -1;
+    unsigned long long slot = atomicAdd(&stats->n_wide, 1ull);
+    wide_list[slot] = uint32_t(node);
+  }
+}
+
+// one warp per unproven node; the searched block doubles its ring until the proof holds
+template <typename T>
+__global__ void __launch_bounds__(256) k_search_wide(const typename Sorted<T>::rec* __restrict__ part,
+                                                      const uint32_t* __restrict__ start, Grid g, Lattice L,
+                                                      int32_t* __restrict__ nn, const uint32_t* __restrict__ wide_list,
+                                                      vp_nn_stats_dev* __restrict__ stats) {
+  const unsigned long long nw = stats->n_wide;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp0 = (unsigned long long)(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned long long nwarps = (unsigned long long)(gridDim.x) * (blockDim.x >> 5);
+  for (unsigned long long w = warp0; w < nw; w += nwarps) {
+    const int64_t node = wide_list[w];
+    int k = int(node % L.nz);
+    int64_t t = node / L.nz;
+    int j = int(t % L.ny), i = int(t / L.ny);
+    const double qx = L.qx[i], qy = L.qy[j], qz = L.qz[k];
+    const int cx = L.cx[i], cy = L.cy[j], cz = L.cz[k];
+    Best b;
+    bool done = false;
+    for (int r = 2; !done; r *= 2) {
+      const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
+      const int y0 = max(cy - r, 0), y1 = min(cy + r, g.gy - 1);
+      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.gz - 1);
+      b.d2 = INFINITY;
+      b.idx = 0x7fffffff;
+      const int nyb = y1 - y0 + 1;
+      const int nrows = (x1 - x0 + 1) * nyb;
+      for (int rr = lane; rr < nrows; rr += 32) {
+        int X = x0 + rr / nyb, Y = y0 + rr % nyb;
+        size_t row = (size_t(X) * g.gy + Y) * g.gz;
+        uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
+        for (uint32_t p = s; p < e; ++p) {
+          double x, y, z;
+          int id;
+          Sorted<T>::get(part, p, x, y, z, id);
+          consider(b, qx, qy, qz, x, y, z, id);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, b.d2, o);
+        int oi = __shfl_xor_sync(0xffffffffu, b.idx, o);
+        if (od < b.d2 || (od == b.d2 && oi < b.idx)) { b.d2 = od; b.idx = oi; }
+      }
+      double m = fmin(axis_margin(qx, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
+                      fmin(axis_margin(qy, g.oy, g.hy, y0, y1, g.gy, false, false),
+                           axis_margin(qz, g.oz, g.hz, z0, z1, g.gz, false, false)));
+      if (proven(b, m)) {
+        done = true;
+      } else if (x0 == 0 && x1 == g.gx - 1 && y0 == 0 && y1 == g.gy - 1 && z0 == 0 && z1 == g.gz - 1) {
+        // every kept particle was examined and a closed x face is still nearer than the best one
+        if (lane == 0) atomicAdd(&stats->n_unresolved, 1ull);
+        done = true;
+      }
+    }
+    if (lane == 0) nn[node] = (b.idx == 0x7fffffff) ? -1 : b.idx;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_words(const int32_t* __restrict__ idx, int64_t n, const uint32_t* __restrict__ src,
+                                                       int rw, uint32_t* __restrict__ dst) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * rw) return;
+  int64_t i = t / rw;
+  int w = int(t - i * rw);
+  dst[t] = src[size_t(idx[i]) * rw + w];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_build_fields(const int32_t* __restrict__ nn, int64_t n, const T* __restrict__ vel,
+                                                       const T* __restrict__ rho, T lcell3, float* vx, float* vy, float* vz,
+                                                       float* px, float* py, float* pz, float* e, float* mo) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  size_t i = size_t(nn[t]);
+  T a = vel[3 * i], b = vel[3 * i + 1], c = vel[3 * i + 2];
+  T m = lcell3;
+  if (rho) {
+    // reference: payload [rho*v, rho] is gathered, then v = (rho*v)/rho, m = rho*Lcell^3 (interp.py:199-213,272-273)
+    T r = rho[i];
+    a = (a * r) / r;
+    b = (b * r) / r;
+    c = (c * r) / r;
+    m = r * lcell3;
+  }
+  if (vx) vx[t] = float(a);
+  if (vy) vy[t] = float(b);
+  if (vz) vz[t] = float(c);
+  if (px) px[t] = float(a * m);
+  if (py) py[t] = float(b * m);
+  if (pz) pz[t] = float(c * m);
+  if (e) e[t] = float(m * (a * a + b * b + c * c));   // interp.py:546 (no 1/2)
+  if (mo) mo[t] = float(m);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct AxisPlan {
+  double o, h;
+  int g;
+};
+
+// cell lattice for one axis: `g` cells of size h covering the node range widened by half a node
+// spacing on each side (so that for g == n uniform nodes every node sits at a cell centre)
+AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, bool use_ext) {
+  double qmin = q[0], qmax = q[0];
+  for (int i = 1; i < n; ++i) { qmin = fmin(qmin, q[i]); qmax = fmax(qmax, q[i]); }
+  double sp = n > 1 ? (qmax - qmin) / (n - 1) : 1.0;
+  if (!(sp > 0)) sp = 1.0;
+  double lo = qmin - 0.5 * sp, hi = qmax + 0.5 * sp;
+  if (use_ext) { lo = lo_ext; hi = hi_ext; }
+  AxisPlan a;
+  a.g = g;
+  a.o = lo;
+  a.h = (hi - lo) / g;
+  return a;
+}
+
+Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, const double* qz, int nz,
+               const vp_nn_opts& o) {
+  int gx = o.cells_x, gy = o.cells_y, gz = o.cells_z;
+  if (gx <= 0 || gy <= 0 || gz <= 0) {
+    // about one particle per cell inside the lattice volume; when the particle count is comparable to the
+    // node count the lattice itself is the natural resolution (nodes then sit at cell centres)
+    double per_axis = cbrt(double(np > 0 ? np : 1) / (double(nx) * ny * nz));  // cells per node along an axis
+    auto pick = [&](int n) {
+      double g = n * per_axis;
+      if (g > 0.7 * n && g < 1.5 * n) return n;  // snap to the lattice
+      int gi = int(g + 0.5);
+      return gi < 1 ? 1 : gi;
+    };
+    gx = pick(nx); gy = pick(ny); gz = pick(nz);
+    if (o.use_x_keep) {
+      // the x extent is the kept range; keep the same cell size as along y
+      AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false);
+      int g = int((o.x_keep_hi - o.x_keep_lo) / ay.h + 0.999);
+      gx = g < 1 ? 1 : g;
+    }
+  }
+  while (double(gx) * gy * gz >= 4294967295.0) {  // 32-bit keys
+    gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
+  }
+  AxisPlan ax = plan_axis(qx, nx, gx, o.x_keep_lo, o.x_keep_hi, o.use_x_keep != 0);
+  AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false);
+  AxisPlan az = plan_axis(qz, nz, gz, 0, 0, false);
+  Grid g;
+  g.ox = ax.o; g.oy = ay.o; g.oz = az.o;
+  g.hx = ax.h; g.hy = ay.h; g.hz = az.h;
+  g.ihx = 1.0 / ax.h; g.ihy = 1.0 / ay.h; g.ihz = 1.0 / az.h;
+  g.gx = gx; g.gy = gy; g.gz = gz;
+  g.use_keep = o.use_x_keep;
+  g.keep_lo = o.x_keep_lo; g.keep_hi = o.x_keep_hi;
+  g.closed_xlo = o.use_x_keep && !o.x_lo_is_domain_edge;
+  g.closed_xhi = o.use_x_keep && !o.x_hi_is_domain_edge;
+  return g;
+}
+
+struct NNScratch {
+  size_t keys, sorted, start, tail, total;
+};
+NNScratch nn_scratch(int64_t np, size_t rec_bytes, uint64_t ncells, int64_t nnodes) {
+  NNScratch s;
+  s.keys = vp_align256(size_t(np) * 4);
+  s.sorted = vp_align256(size_t(np) * rec_bytes);
+  s.start = vp_align256((ncells + 1) * 4);
+  size_t b_wide = vp_align256(size_t(nnodes) * 4), b_sort = vp_sort_scratch_bytes(np);
+  s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are reordered; the wide list reuses it
+  s.total = 2 * s.keys + s.sorted + s.start + s.tail + 1024;
+  return s;
+}
+
+template <typename T>
+int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int nx, const double* qy, int ny,
+                  const double* qz, int nz, int32_t* nn, const vp_nn_opts* opts, cudaStream_t st) {
+  const int64_t nnodes = int64_t(nx) * ny * nz;
+  VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
+  VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
+  vp_nn_opts o;
+  memset(&o, 0, sizeof o);
+  if (opts) o = *opts;
+  const Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
+  const int gx = g.gx, gy = g.gy, gz = g.gz;
+  const uint64_t ncells = uint64_t(gx) * gy * gz;
+  const int bits = vp_ceil_log2(ncells);
+
+  // ---- lattice tables (host -> pinned -> device)
+  const size_t tab_doubles = size_t(nx) + ny + nz;
+  const size_t tab_bytes = vp_align256(tab_doubles * 8) + vp_align256(tab_doubles * 4);
+  if (ctx->pinned_cap < tab_bytes) {
+    if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
+    VP_CUDA(cudaMallocHost(&ctx->pinned_h, tab_bytes));
+    ctx->pinned_cap = tab_bytes;
+  }
+  if (ctx->small_cap < tab_bytes) {
+    VP_CUDA(cudaStreamSynchronize(st));
+    if (ctx->small_d) cudaFree(ctx->small_d);
+    VP_CUDA(cudaMalloc(&ctx->small_d, tab_bytes));
+    ctx->small_cap = tab_bytes;
+  }
+  VP_CUDA(cudaStreamSynchronize(st));  // the pinned block may still be in flight from a previous call
+  double* hq = static_cast<double*>(ctx->pinned_h);
+  int* hc = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned_h) + vp_align256(tab_doubles * 8));
+  auto host_cell = [](double x, double o_, double ih, int gg) {
+    double f = (x - o_) * ih;
+    if (!(f > 0.0)) return 0;
+    if (f >= double(gg)) return gg - 1;
+    return int(f);
+  };
+  for (int i = 0; i < nx; ++i) { hq[i] = qx[i]; hc[i] = host_cell(qx[i], g.ox, g.ihx, gx); }
+  for (int i = 0; i < ny; ++i) { hq[nx + i] = qy[i]; hc[nx + i] = host_cell(qy[i], g.oy, g.ihy, gy); }
+  for (int i = 0; i < nz; ++i) { hq[nx + ny + i] = qz[i]; hc[nx + ny + i] = host_cell(qz[i], g.oz, g.ihz, gz); }
+  VP_CUDA(cudaMemcpyAsync(ctx->small_d, ctx->pinned_h, tab_bytes, cudaMemcpyHostToDevice, st));
+  Lattice L;
+  L.qx = ctx->small_d; L.qy = L.qx + nx; L.qz = L.qy + ny;
+  L.cx = reinterpret_cast<const int*>(reinterpret_cast<const char*>(ctx->small_d) + vp_align256(tab_doubles * 8));
+  L.cy = L.cx + nx; L.cz = L.cy + ny;
+  L.nx = nx; L.ny = ny; L.nz = nz;
+
+  // ---- scratch
+  using rec = typename Sorted<T>::rec;
+  const NNScratch sc = nn_scratch(np, sizeof(rec), ncells, nnodes);
+  vp_arena_scope scope(ctx);
+  VP_TRY(vp_arena_reserve(ctx, sc.total));
+  uint32_t* keys = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
+  uint32_t* vals = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
+  rec* sorted = static_cast<rec*>(vp_arena_alloc(ctx, sc.sorted));
+  uint32_t* start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.start));
+  void* scratch = vp_arena_alloc(ctx, sc.tail);
+  VP_REQUIRE(keys && vals && sorted && start && scratch, "vp_nn_grid: arena carve failed");
+  uint32_t* wide_list = static_cast<uint32_t*>(scratch);
+
+  VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
+  int64_t n = np;
+  if (np > 0) {
+    vp_stage stage(ctx, "k1a_keygen", st, 1, double(np) * (3.0 * sizeof(T) + 8.0));
+    k_keygen<T><<<unsigned((np + 255) / 256), 256, 0, st>>>(pos, np, g, keys, vals, &ctx->nn_stats_d->n_kept);
+    VP_CHECK_LAUNCH();
+  }
+  if (o.use_x_keep) {
+    unsigned long long kept = 0;
+    VP_CUDA(cudaMemcpyAsync(&kept, &ctx->nn_stats_d->n_kept, 8, cudaMemcpyDeviceToHost, st));
+    VP_CUDA(cudaStreamSynchronize(st));  // documented: the filtered form syncs once
+    n = int64_t(kept);
+  } else {
+    unsigned long long kept = (unsigned long long)np;
+    VP_CUDA(cudaMemcpyAsync(&ctx->nn_stats_d->n_kept, &kept, 8, cudaMemcpyHostToDevice, st));
+  }
+  VP_TRY(vp_sort_pairs_impl(ctx, keys, vals, n, bits, scratch, st));
+  if (n > 0) {
+    {
+      vp_stage stage(ctx, "k1c_reorder", st, 1, double(n) * (4.0 + 3.0 * sizeof(T) + sizeof(rec)));
+      k_reorder<T><<<unsigned((n + 255) / 256), 256, 0, st>>>(pos, vals, n, sorted);
+    }
+    {
+      vp_stage stage(ctx, "k1d_cell_starts", st, 1, double(n) * 4.0 + double(ncells) * 4.0);
+      k_cell_starts<<<unsigned((n + 255) / 256), 256, 0, st>>>(keys, n, uint32_t(ncells), start);
+    }
+  } else {
+    k_fill_u32<<<unsigned((ncells + 1 + 255) / 256), 256, 0, st>>>(start, int64_t(ncells + 1), 0u);
+  }
+  VP_CHECK_LAUNCH();
+  {
+    // sorted records read once + cell starts read once + one index written per node
+    vp_stage stage(ctx, "k1e_search_ring1", st, 1, double(n) * sizeof(rec) + double(ncells) * 4.0 + double(nnodes) * 4.0);
+    k_search_ring1<T><<<unsigned((nnodes + 255) / 256), 256, 0, st>>>(sorted, start, g, L, nn, wide_list, ctx->nn_stats_d);
+  }
+  {
+    vp_stage stage(ctx, "k1f_search_wide", st, 1);
+    k_search_wide<T><<<ctx->sm_count * 4, 256, 0, st>>>(sorted, start, g, L, nn, wide_list, ctx->nn_stats_d);
+  }
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+}  // namespace
+
+size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* qx, int nx, const double* qy, int ny,
+                                       const double* qz, int nz, const vp_nn_opts* opts) {
+  vp_nn_opts o;
+  memset(&o, 0, sizeof o);
+  if (opts) o = *opts;
+  Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
+  size_t rb = pos_dtype == VP_F64 ? sizeof(Sorted<double>::rec) : sizeof(Sorted<float>::rec);
+  return nn_scratch(np, rb, uint64_t(g.gx) * g.gy * g.gz, int64_t(nx) * ny * nz).total + 4096;
+}
+
+extern "C" int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const double* qx_h, int nx,
+                          const double* qy_h, int ny, const double* qz_h, int nz, int32_t* nn_idx_d,
+                          const vp_nn_opts* opts, void* stream) {
+  VP_REQUIRE(ctx && pos_d && qx_h && qy_h && qz_h && nn_idx_d, "vp_nn_grid: null argument");
+  VP_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vp_nn_grid: bad sizes");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pos_dtype == VP_F32)
+    return nn_grid_typed<float>(ctx, static_cast<const float*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, opts, st);
+  if (pos_dtype == VP_F64)
+    return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, opts, st);
+  vp_set_error("vp_nn_grid: unknown dtype %d", pos_dtype);
+  return VP_ERR_ARG;
+}
+
+extern "C" int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_t* n_kept, void* stream) {
+  VP_REQUIRE(ctx, "vp_nn_grid_stats: null ctx");
+  vp_nn_stats_dev h;
+  VP_CUDA(cudaMemcpyAsync(&h, ctx->nn_stats_d, sizeof h, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  VP_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (n_wide) *n_wide = int64_t(h.n_wide);
+  if (n_unresolved) *n_unresolved = int64_t(h.n_unresolved);
+  if (n_kept) *n_kept = int64_t(h.n_kept);
+  return VP_OK;
+}
+
+extern "C" int vp_gather_rows(vp_ctx* ctx, const int32_t* idx_d, int64_t n, const void* src_d, int row_bytes, void* dst_d,
+                              void* stream) {
+  VP_REQUIRE(ctx && idx_d && src_d && dst_d, "vp_gather_rows: null argument");
+  VP_REQUIRE(row_bytes > 0 && row_bytes % 4 == 0, "vp_gather_rows: row_bytes must be a multiple of 4");
+  if (n == 0) return VP_OK;
+  int rw = row_bytes / 4;
+  int64_t tot = n * rw;
+  vp_stage stage(ctx, "gather_rows", static_cast<cudaStream_t>(stream), 1, double(n) * (4.0 + 2.0 * row_bytes));
+  k_gather_words<<<unsigned((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      idx_d, n, static_cast<const uint32_t*>(src_d), rw, static_cast<uint32_t*>(dst_d));
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
+extern "C" int vp_build_fields(vp_ctx* ctx, const int32_t* nn_idx_d, int64_t n_nodes, const void* vel_d, const void* rho_d,
+                               int dtype, double lcell3, float* const v_d[3], float* const p_d[3], float* e_d, float* m_d,
+                               void* stream) {
+  VP_REQUIRE(ctx && nn_idx_d && vel_d, "vp_build_fields: null argument");
+  if (n_nodes == 0) return VP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* v[3] = {v_d ? v_d[0] : nullptr, v_d ? v_d[1] : nullptr, v_d ? v_d[2] : nullptr};
+  float* p[3] = {p_d ? p_d[0] : nullptr, p_d ? p_d[1] : nullptr, p_d ? p_d[2] : nullptr};
+  unsigned nb = unsigned((n_nodes + 255) / 256);
+  int nplanes = 0;
+  for (int c = 0; c < 3; ++c) nplanes += (v[c] != nullptr) + (p[c] != nullptr);
+  nplanes += (e_d != nullptr) + (m_d != nullptr);
+  const double es = dtype == VP_F64 ? 8.0 : 4.0;
+  // per node: index read, (v, rho) gathered, 4 B written per plane
+  vp_stage stage(ctx, "k3_build_fields", st, 1, double(n_nodes) * (4.0 + (rho_d ? 4.0 : 3.0) * es + 4.0 * nplanes));
+  if (dtype == VP_F32)
+    k_build_fields<float><<<nb, 256, 0, st>>>(nn_idx_d, n_nodes, static_cast<const float*>(vel_d),
+                                              static_cast<const float*>(rho_d), float(lcell3), v[0], v[1], v[2], p[0], p[1],
+                                              p[2], e_d, m_d);
+  else if (dtype == VP_F64)
+    k_build_fields<double><<<nb, 256, 0, st>>>(nn_idx_d, n_nodes, static_cast<const double*>(vel_d),
+                                               static_cast<const double*>(rho_d), lcell3, v[0], v[1], v[2], p[0], p[1], p[2],
+                                               e_d, m_d);
+  else {
+    vp_set_error("vp_build_fields: unknown dtype %d", dtype);
+    return VP_ERR_ARG;
+  }
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}

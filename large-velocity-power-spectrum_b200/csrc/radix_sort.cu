@@ -1,0 +1,245 @@
+// LSD radix sort of (key,value) u32 pairs, 8 bits per pass -- builds the cell list of K1.
+//
+// Per pass:  (1) tile digit histograms  (2) exclusive scan, digit-major  (3) stable scatter with
+// warp-level match ranking and a shared-memory staged, digit-run coalesced write.
+// Algorithmic traffic per pass: 4 B (histogram read) + 16 B (pair read + write) per element.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;  // 4096 keys per CTA
+constexpr int kRadix = 256;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan across a 256-thread block; returns the exclusive prefix, *total gets the block sum
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* warp_sums /*[8]*/, uint32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = warp_incl_scan(v, lane);
+  if (lane == 31) warp_sums[w] = incl;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) {
+    uint32_t s = warp_sums[i];
+    if (i < w) woff += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + incl - v;
+}
+
+// (1) per-tile digit histogram, written digit-major: hist[d * nblocks + b]
+__global__ void __launch_bounds__(kThreads) k_tile_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
+                                                         uint32_t* __restrict__ hist, int nblocks) {
+  __shared__ uint32_t sh[kRadix];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = int64_t(blockIdx.x) * kTile;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int64_t i = base + r * kThreads + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// (2) exclusive scan of m u32 values in three kernels (chunk sums, scan of sums, apply)
+constexpr int kScanChunk = kThreads * 16;
+
+__global__ void __launch_bounds__(kThreads) k_scan_sums(const uint32_t* __restrict__ a, int64_t m,
+                                                         uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[kWarps];
+  const int64_t base = int64_t(blockIdx.x) * kScanChunk;
+  uint32_t s = 0;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    int64_t i = base + r * kThreads + threadIdx.x;
+    if (i < m) s += a[i];
+  }
+  uint32_t tot;
+  block_excl_scan_256(s, ws, &tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_top(uint32_t* __restrict__ sums, int nchunks) {
+  __shared__ uint32_t ws[kWarps];
+  uint32_t carry = 0;
+  for (int base = 0; base < nchunks; base += kThreads) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nchunks ? sums[i] : 0u, tot;
+    uint32_t ex = block_excl_scan_256(v, ws, &tot);
+    if (i < nchunks) sums[i] = carry + ex;
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t* __restrict__ a, int64_t m,
+                                                          const uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[kWarps];
+  const int64_t base = int64_t(blockIdx.x) * kScanChunk + int64_t(threadIdx.x) * 16;
+  uint32_t v[16], s = 0;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    v[r] = (base + r < m) ? a[base + r] : 0u;
+    s += v[r];
+  }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan_256(s, ws, &tot) + sums[blockIdx.x];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    if (base + r < m) a[base + r] = ex;
+    ex += v[r];
+  }
+}
+
+// (3) stable scatter
+__global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                       uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                       int64_t n, int shift, const uint32_t* __restrict__ hist,
+                                                       int nblocks) {
+  __shared__ uint32_t wcnt[kWarps][kRadix];
+  __shared__ uint32_t dbase[kRadix];   // exclusive prefix of digit totals inside this tile
+  __shared__ uint32_t gbase[kRadix];   // global output offset of the digit run minus dbase
+  __shared__ uint32_t skey[kTile];
+  __shared__ uint32_t sval[kTile];
+  __shared__ uint32_t ws[kWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t tile0 = int64_t(blockIdx.x) * kTile;
+  const int64_t rem = n - tile0;
+  const int count = rem < kTile ? int(rem) : kTile;
+
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) wcnt[i][tid] = 0;
+  __syncthreads();
+
+  uint32_t key[kItems], val[kItems], rank[kItems];
+  const int wbase = w * (kItems * 32);
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int li = wbase + r * 32 + lane;
+    bool ok = li < count;
+    key[r] = ok ? kin[tile0 + li] : 0u;
+    val[r] = ok ? vin[tile0 + li] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int li = wbase + r * 32 + lane;
+    bool ok = li < count;
+    uint32_t d = ok ? ((key[r] >> shift) & 0xff) : 256u;
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(peers) - 1;
+    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    uint32_t old = 0;
+    if (ok && lane == leader) {
+      old = wcnt[w][d];
+      wcnt[w][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + before;
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // digit `tid`: exclusive offsets across warps, then across digits
+  uint32_t tot = 0;
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) {
+    uint32_t c = wcnt[i][tid];
+    wcnt[i][tid] = tot;
+    tot += c;
+  }
+  uint32_t blocktot;
+  uint32_t ex = block_excl_scan_256(tot, ws, &blocktot);
+  dbase[tid] = ex;
+  gbase[tid] = hist[size_t(tid) * nblocks + blockIdx.x] - ex;
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int li = wbase + r * 32 + lane;
+    if (li < count) {
+      uint32_t d = (key[r] >> shift) & 0xff;
+      uint32_t p = dbase[d] + wcnt[w][d] + rank[r];
+      skey[p] = key[r];
+      sval[p] = val[r];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int i = r * kThreads + tid;
+    if (i < count) {
+      uint32_t k = skey[i];
+      uint32_t d = (k >> shift) & 0xff;
+      size_t o = size_t(gbase[d]) + i;
+      kout[o] = k;
+      vout[o] = sval[i];
+    }
+  }
+}
+
+}  // namespace
+
+static inline int64_t sort_nblocks(int64_t n) { return (n + kTile - 1) / kTile; }
+
+size_t vp_sort_scratch_bytes(int64_t n) {
+  int64_t nb = sort_nblocks(n < 1 ? 1 : n);
+  int64_t m = nb * kRadix;
+  int64_t nchunks = (m + kScanChunk - 1) / kScanChunk;
+  return vp_align256(size_t(n) * 4) * 2      // alternate key / value buffers
+         + vp_align256(size_t(m) * 4)         // tile histograms
+         + vp_align256(size_t(nchunks) * 4);  // scan partials
+}
+
+int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
+                       cudaStream_t st) {
+  if (n <= 1 || bits <= 0) return VP_OK;
+  VP_REQUIRE(n < (int64_t(1) << 32), "vp_sort_pairs: n=%lld exceeds 2^32", (long long)n);
+  const int nb = int(sort_nblocks(n));
+  const int64_t m = int64_t(nb) * kRadix;
+  const int nchunks = int((m + kScanChunk - 1) / kScanChunk);
+  char* p = static_cast<char*>(scratch);
+  uint32_t* k2 = reinterpret_cast<uint32_t*>(p);
+  p += vp_align256(size_t(n) * 4);
+  uint32_t* v2 = reinterpret_cast<uint32_t*>(p);
+  p += vp_align256(size_t(n) * 4);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(p);
+  p += vp_align256(size_t(m) * 4);
+  uint32_t* sums = reinterpret_cast<uint32_t*>(p);
+
+  uint32_t *ka = keys, *va = vals, *kb = k2, *vb = v2;
+  const int passes = (bits + 7) / 8;
+  // algorithmic bytes: 4 (histogram read) + 16 (pair read + write) per element per pass
+  vp_stage stage(ctx, "k1b_radix_sort", st, 5 * passes, double(n) * 20.0 * passes);
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * 8;
+    k_tile_hist<<<nb, kThreads, 0, st>>>(ka, n, shift, hist, nb);
+    k_scan_sums<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
+    k_scan_top<<<1, kThreads, 0, st>>>(sums, nchunks);
+    k_scan_apply<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
+    k_scatter<<<nb, kThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nb);
+    VP_CHECK_LAUNCH();
+    uint32_t* t;
+    t = ka; ka = kb; kb = t;
+    t = va; va = vb; vb = t;
+  }
+  if (ka != keys) {
+    VP_CUDA(cudaMemcpyAsync(keys, ka, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
+    VP_CUDA(cudaMemcpyAsync(vals, va, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return VP_OK;
+}

@@ -1,0 +1,346 @@
+"""ctypes binding of libvpower_b200.so (include/vpower_b200.h) + thin torch plumbing.
+
+PyTorch is used only for device memory and streams.  There is no CPU fallback: importing this
+module succeeds anywhere (so that the host-side logic can be tested), but every compute call
+raises `VPowerError` when the shared library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvpower_b200.so")
+
+VP_F32, VP_F64 = 0, 1
+
+
+class VPowerError(RuntimeError):
+    pass
+
+
+class NNOpts(C.Structure):
+    _fields_ = [("cells_x", C.c_int), ("cells_y", C.c_int), ("cells_z", C.c_int), ("use_x_keep", C.c_int),
+                ("x_keep_lo", C.c_double), ("x_keep_hi", C.c_double), ("x_lo_is_domain_edge", C.c_int),
+                ("x_hi_is_domain_edge", C.c_int)]
+
+
+_P, _D, _I, _L = C.c_void_p, C.c_double, C.c_int, C.c_int64
+_dp = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes): every symbol declared in include/vpower_b200.h
+SIGNATURES = {
+    "vp_version": (_I, []),
+    "vp_last_error": (C.c_char_p, []),
+    "vp_ctx_create": (_I, [_I, C.POINTER(_P)]),
+    "vp_ctx_destroy": (_I, [_P]),
+    "vp_ctx_arena_bytes": (C.c_size_t, [_P]),
+    "vp_ctx_trim": (_I, [_P]),
+    "vp_profile_enable": (_I, [_P, _I]),
+    "vp_profile_report": (_I, [_P, C.c_char_p, C.c_size_t]),
+    "vp_launch_count": (C.c_ulonglong, [_P]),
+    "vp_nn_grid": (_I, [_P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _P, C.POINTER(NNOpts), _P]),
+    "vp_nn_grid_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _P]),
+    "vp_gather_rows": (_I, [_P, _P, _L, _P, _I, _P, _P]),
+    "vp_build_fields": (_I, [_P, _P, _L, _P, _P, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
+    "vp_deposit_ngp": (_I, [_P, _P, _I, _L, _P, _I, _I, _D, _P, _P]),
+    "vp_pk_plan_create": (_I, [_P, _I, _dp, _dp, _I, C.POINTER(_P)]),
+    "vp_pk_plan_destroy": (_I, [_P]),
+    "vp_pk_fields": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
+    "vp_fft_r2c_inplace": (_I, [_P, _P, _P]),
+    "vp_fft_unpack_half": (_I, [_P, _P, _P, _P]),
+    "vp_power_bin_full": (_I, [_P, _P, _P, _P, _P]),
+    "vp_power_cube": (_I, [_P, C.POINTER(_P), _I, _P, _P]),
+    "vp_k_magnitude": (_I, [_P, _dp, _dp, _dp, _I, _P, _P]),
+    "vp_hist_weighted": (_I, [_P, _P, _P, _L, _dp, _I, _P, _P, _P]),
+    "vp_sort_pairs": (_I, [_P, _P, _P, _L, _I, _P]),
+    "vp_host_particles_to_pk": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _dp, _I, _D, _D, _dp, _dp, _I, _I, _I, _P, _P, _P]),
+    "vp_dev_particles_to_pk": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _dp, _I, _D, _D, _dp, _dp, _I, _I, _I, _P, _P, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}
+
+
+def load_library():
+    """dlopen the shared object and declare every prototype.  No GPU needed for this step."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise VPowerError(f"{LIB_PATH} not found -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                                  "vpower_b200 has no CPU fallback")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise VPowerError(f"libvpower_b200 error {rc}: {load_library().vp_last_error().decode()}")
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise VPowerError("no CUDA device: vpower_b200 runs on B200 (sm_100a) only and has no CPU fallback")
+    return torch
+
+
+def ctx(device=None):
+    torch = _torch()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _ctx:
+        h = _P()
+        _check(load_library().vp_ctx_create(dev, C.byref(h)))
+        _ctx[dev] = h
+    return _ctx[dev]
+
+
+def profile_enable(on=True):
+    _check(load_library().vp_profile_enable(ctx(), 1 if on else 0))
+
+
+def profile_report():
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    _check(load_library().vp_profile_report(ctx(), buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
+def launch_count():
+    return int(load_library().vp_launch_count(ctx()))
+
+
+def stream_ptr():
+    return _P(_torch().cuda.current_stream().cuda_stream)
+
+
+def _dtype_code(t):
+    torch = _torch()
+    if t.dtype == torch.float32:
+        return VP_F32
+    if t.dtype == torch.float64:
+        return VP_F64
+    raise VPowerError(f"unsupported dtype {t.dtype}; use float32 or float64")
+
+
+def _as_dp(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def to_device(a, dtype=None):
+    """numpy / torch -> contiguous CUDA tensor (plumbing)."""
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        arr = np.ascontiguousarray(a)
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("="))
+        t = torch.from_numpy(arr)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to("cuda", non_blocking=False).contiguous()
+
+
+# --------------------------------------------------------------------------- K1
+def nn_grid(pos_t, qx, qy, qz, opts: NNOpts | None = None):
+    """pos_t: CUDA tensor [Np,3] f32/f64 -> CUDA int32 tensor [nx,ny,nz] (0-based nearest particle)."""
+    torch = _torch()
+    assert pos_t.is_cuda and pos_t.dim() == 2 and pos_t.shape[1] == 3 and pos_t.is_contiguous()
+    qx_a, qx_p = _as_dp(qx)
+    qy_a, qy_p = _as_dp(qy)
+    qz_a, qz_p = _as_dp(qz)
+    out = torch.empty((len(qx_a), len(qy_a), len(qz_a)), dtype=torch.int32, device=pos_t.device)
+    _check(load_library().vp_nn_grid(ctx(), _P(pos_t.data_ptr()), _dtype_code(pos_t), pos_t.shape[0], qx_p, len(qx_a),
+                                     qy_p, len(qy_a), qz_p, len(qz_a), _P(out.data_ptr()),
+                                     C.byref(opts) if opts is not None else None, stream_ptr()))
+    return out
+
+
+def nn_grid_stats():
+    a, b, c = _L(), _L(), _L()
+    _check(load_library().vp_nn_grid_stats(ctx(), C.byref(a), C.byref(b), C.byref(c), stream_ptr()))
+    return {"n_wide": a.value, "n_unresolved": b.value, "n_kept": c.value}
+
+
+def gather_rows(idx_t, src_t):
+    torch = _torch()
+    src_t = src_t.contiguous()
+    row = src_t[0].numel() * src_t.element_size() if src_t.dim() > 1 else src_t.element_size()
+    n = idx_t.numel()
+    out = torch.empty((n,) + tuple(src_t.shape[1:]), dtype=src_t.dtype, device=src_t.device)
+    _check(load_library().vp_gather_rows(ctx(), _P(idx_t.data_ptr()), n, _P(src_t.data_ptr()), row, _P(out.data_ptr()),
+                                         stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------- K3
+def build_fields(nn_t, vel_t, rho_t, lcell3, want_v=True, want_p=(False, False, False), want_e=False, want_m=False):
+    """-> dict of float32 CUDA cubes with the shape of nn_t: vx,vy,vz,px,py,pz,e,m (only the requested ones)."""
+    torch = _torch()
+    shape = tuple(nn_t.shape)
+    n = nn_t.numel()
+    out = {}
+
+    def cube(name, on):
+        if on:
+            out[name] = torch.empty(shape, dtype=torch.float32, device=nn_t.device)
+            return out[name].data_ptr()
+        return None
+
+    v = (_P * 3)(*[cube(nm, want_v) for nm in ("vx", "vy", "vz")])
+    p = (_P * 3)(*[cube(nm, on) for nm, on in zip(("px", "py", "pz"), want_p)])
+    e = cube("e", want_e)
+    m = cube("m", want_m)
+    if rho_t is not None:
+        assert rho_t.dtype == vel_t.dtype
+    _check(load_library().vp_build_fields(ctx(), _P(nn_t.data_ptr()), n, _P(vel_t.data_ptr()),
+                                          _P(rho_t.data_ptr()) if rho_t is not None else None, _dtype_code(vel_t),
+                                          float(lcell3), v, p, _P(e) if e else None, _P(m) if m else None, stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------- K2
+def deposit_ngp(pos_t, w_t, N, Lbox):
+    torch = _torch()
+    w2 = w_t.to(torch.float64).contiguous()
+    ncomp = 1 if w2.dim() == 1 else w2.shape[1]
+    shape = (N, N, N) if w2.dim() == 1 else (N, N, N, ncomp)
+    grid = torch.empty(shape, dtype=torch.float64, device=pos_t.device)
+    _check(load_library().vp_deposit_ngp(ctx(), _P(pos_t.data_ptr()), _dtype_code(pos_t), pos_t.shape[0],
+                                         _P(w2.data_ptr()), ncomp, N, float(Lbox), _P(grid.data_ptr()), stream_ptr()))
+    return grid
+
+
+# --------------------------------------------------------------------------- K4/K5
+class PkPlan:
+    """Geometry of one transform+binning: N, k axis table (2 pi fftfreq), bin edges."""
+
+    def __init__(self, N, k_axis, edges):
+        self.N = int(N)
+        self.k_axis, kp = _as_dp(k_axis)
+        self.edges, ep = _as_dp(edges)
+        self.nbins = len(self.edges) - 1
+        assert len(self.k_axis) == self.N
+        self._h = _P()
+        _check(load_library().vp_pk_plan_create(ctx(), self.N, kp, ep, self.nbins, C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().vp_pk_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def fields(self, cubes):
+        """cubes: list of 1..3 float32 CUDA tensors [N,N,N]; they are OVERWRITTEN.
+        -> (sum_c |FFT(f_c)|^2 per shell as numpy f64 [nbins], Nsample numpy int64 [nbins])."""
+        torch = _torch()
+        for c in cubes:
+            assert c.is_cuda and c.dtype == torch.float32 and c.is_contiguous() and tuple(c.shape) == (self.N,) * 3
+        ptrs = (_P * len(cubes))(*[c.data_ptr() for c in cubes])
+        psum = torch.empty(self.nbins, dtype=torch.float64, device=cubes[0].device)
+        ns = torch.empty(self.nbins, dtype=torch.int64, device=cubes[0].device)
+        _check(load_library().vp_pk_fields(self._h, ptrs, len(cubes), _P(psum.data_ptr()), _P(ns.data_ptr()), stream_ptr()))
+        return psum.cpu().numpy(), ns.cpu().numpy()
+
+    def power_cube(self, cubes):
+        """-> CUDA f64 tensor [N,N,N] = sum_c |FFT(f_c)|^2 over the FULL spectrum (cubes are overwritten)."""
+        torch = _torch()
+        ptrs = (_P * len(cubes))(*[c.data_ptr() for c in cubes])
+        P = torch.empty((self.N,) * 3, dtype=torch.float64, device=cubes[0].device)
+        _check(load_library().vp_power_cube(self._h, ptrs, len(cubes), _P(P.data_ptr()), stream_ptr()))
+        return P
+
+    def bin_full(self, P_t):
+        torch = _torch()
+        P_t = P_t.to(torch.float64).contiguous()
+        psum = torch.empty(self.nbins, dtype=torch.float64, device=P_t.device)
+        ns = torch.empty(self.nbins, dtype=torch.int64, device=P_t.device)
+        _check(load_library().vp_power_bin_full(self._h, _P(P_t.data_ptr()), _P(psum.data_ptr()), _P(ns.data_ptr()), stream_ptr()))
+        return psum.cpu().numpy(), ns.cpu().numpy()
+
+    def fft_half(self, cube):
+        """Diagnostic: in-place r2c of one cube, returned as complex64 CUDA tensor [N,N,N/2+1]."""
+        torch = _torch()
+        _check(load_library().vp_fft_r2c_inplace(self._h, _P(cube.data_ptr()), stream_ptr()))
+        half = torch.empty((self.N, self.N, self.N // 2 + 1, 2), dtype=torch.float32, device=cube.device)
+        _check(load_library().vp_fft_unpack_half(self._h, _P(cube.data_ptr()), _P(half.data_ptr()), stream_ptr()))
+        return torch.view_as_complex(half)
+
+
+def k_magnitude(kx, ky, kz):
+    """|k| = sqrt((kx*kx + ky*ky) + kz*kz) for the separable table, flattened C order (CUDA f64 tensor)."""
+    torch = _torch()
+    kx_a, kxp = _as_dp(kx)
+    ky_a, kyp = _as_dp(ky)
+    kz_a, kzp = _as_dp(kz)
+    assert len(kx_a) == len(ky_a) == len(kz_a)
+    n = len(kx_a)
+    out = torch.empty(n ** 3, dtype=torch.float64, device="cuda")
+    _check(load_library().vp_k_magnitude(ctx(), kxp, kyp, kzp, n, _P(out.data_ptr()), stream_ptr()))
+    return out
+
+
+def hist_weighted(k_t, w_t, edges):
+    """numpy.histogram(k, bins=edges, weights=w) and the unweighted counts, on the device."""
+    torch = _torch()
+    k_t = k_t.to(torch.float64).contiguous()
+    w_t = w_t.to(torch.float64).contiguous()
+    e_a, ep = _as_dp(edges)
+    nb = len(e_a) - 1
+    psum = torch.empty(nb, dtype=torch.float64, device=k_t.device)
+    ns = torch.empty(nb, dtype=torch.int64, device=k_t.device)
+    _check(load_library().vp_hist_weighted(ctx(), _P(k_t.data_ptr()), _P(w_t.data_ptr()), k_t.numel(), ep, nb,
+                                           _P(psum.data_ptr()), _P(ns.data_ptr()), stream_ptr()))
+    return psum.cpu().numpy(), ns.cpu().numpy()
+
+
+def sort_pairs(keys_t, vals_t, bits=32):
+    _check(load_library().vp_sort_pairs(ctx(), _P(keys_t.data_ptr()), _P(vals_t.data_ptr()), keys_t.numel(), bits, stream_ptr()))
+
+
+# --------------------------------------------------------------------------- whole path
+def particles_to_pk(pos, vel, rho, qx, qy, qz, N, lcell3, norm, k_axis, edges, quantities=("velocity",),
+                    momentum_strict=True):
+    """Whole path in one C call.  pos/vel/rho: numpy arrays (HOST buffers; copied inside the call) or CUDA
+    tensors (device resident).  -> dict quantity -> Psum[nbins] (normalised by `norm`), and Nsample."""
+    lib = load_library()
+    mask = sum({"velocity": 1, "momentum": 2, "energy": 4}[q] for q in quantities)
+    qx_a, qxp = _as_dp(qx)
+    qy_a, qyp = _as_dp(qy)
+    qz_a, qzp = _as_dp(qz)
+    k_a, kp = _as_dp(k_axis)
+    e_a, ep = _as_dp(edges)
+    nb = len(e_a) - 1
+    psum = np.zeros((3, nb), dtype=np.float64)
+    ns = np.zeros(nb, dtype=np.uint64)
+    on_host = isinstance(pos, np.ndarray)
+    if on_host:
+        _torch()
+        dt = VP_F64 if pos.dtype == np.float64 else VP_F32
+        want = np.float64 if dt == VP_F64 else np.float32
+        pos = np.ascontiguousarray(pos, dtype=want)
+        vel = np.ascontiguousarray(vel, dtype=want)
+        rho = None if rho is None else np.ascontiguousarray(rho, dtype=want)
+        ptr = lambda a: _P(a.ctypes.data) if a is not None else None  # noqa: E731
+        fn = lib.vp_host_particles_to_pk
+    else:
+        dt = _dtype_code(pos)
+        ptr = lambda a: _P(a.data_ptr()) if a is not None else None  # noqa: E731
+        fn = lib.vp_dev_particles_to_pk
+    _check(fn(ctx(), ptr(pos), ptr(vel), ptr(rho), dt, pos.shape[0], qxp, qyp, qzp, int(N), float(lcell3), float(norm),
+              kp, ep, nb, mask, 1 if momentum_strict else 0, _P(psum.ctypes.data), _P(ns.ctypes.data), stream_ptr()))
+    out = {q: psum[i] for i, q in enumerate(("velocity", "momentum", "energy")) if q in quantities}
+    return out, ns.astype(np.int64)

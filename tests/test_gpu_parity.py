@@ -1,0 +1,341 @@
+"""Parity of the CUDA path (through the C ABI / the vpower mirror) against the CPU oracle and the golden
+vectors of the unmodified reference.  All tests need a B200: `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): nearest-particle indices and per-bin mode counts bit-exact; binned P(k)
+within 1e-5 relative where the oracle is f64 (library flavour), 1e-3 where the reference itself is f32
+(script flavour).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vp():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    import vpower
+    from vpower import _lib
+    _lib.load_library()
+    return vpower
+
+
+@pytest.fixture(scope="module")
+def lib(vp):
+    from vpower import _lib
+    return _lib
+
+
+def _pos_seen_by_ann(g, name):
+    return g[f"{name}/pos_parsed"] if bool(g[f"{name}/pos_parsed_differs"]) else g[f"{name}/pos"]
+
+
+# ------------------------------------------------------------------------------------------ radix sort
+@pytest.mark.parametrize("n,bits", [(1, 8), (1000, 8), (4096, 16), (100003, 24), (1 << 20, 30), ((1 << 21) + 17, 32)])
+def test_sort_pairs(lib, n, bits):
+    import torch
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(np.uint32)
+    vals = np.arange(n, dtype=np.uint32)
+    kt = torch.from_numpy(keys.view(np.int32)).cuda()
+    vt = torch.from_numpy(vals.view(np.int32)).cuda()
+    lib.sort_pairs(kt, vt, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(kt.cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(vt.cpu().numpy().view(np.uint32), vals[order])          # stable
+
+
+# ------------------------------------------------------------------------------------------ K1 nearest particle
+@pytest.mark.parametrize("name,N", [("lib16", 16), ("lib24", 24), ("lib32c", 32)])
+def test_nn_vs_ann_golden(lib, golden, name, N):
+    """Same inputs the reference's ANN 1.1.2 engine saw; bit-exact on every non-tied query."""
+    pos = _pos_seen_by_ann(golden, name)
+    ax = [golden[f"{name}/axis_parsed{c}"] for c in range(3)]
+    nn = lib.nn_grid(lib.to_device(pos), *ax).cpu().numpy()
+    ties = np.unpackbits(golden[f"{name}/nn_ties"])[: N ** 3].astype(bool).reshape(N, N, N)
+    assert np.array_equal(nn[~ties], golden[f"{name}/nn_ann"][~ties])
+    st = lib.nn_grid_stats()
+    assert st["n_unresolved"] == 0 and st["n_kept"] == len(pos)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("Np,N,clustered", [(1 << 15, 32, False), (1 << 18, 64, False), (40 ** 3, 40, True), (5000, 48, False),
+                                            (300000, 24, False)])
+def test_nn_vs_oracle(lib, orc, dtype, Np, N, clustered):
+    pos, _, _, _ = orc.synth_particles(3, Np, 1.0, clustered=clustered, lattice_n=40 if clustered else None)
+    pos = pos.astype(dtype)
+    if dtype == np.float64:
+        pos = pos + 1e-9 * np.random.default_rng(0).random(pos.shape)             # genuinely 64-bit coordinates
+    ax = orc.lattice_axis_lib(1.0, N)
+    ref, ties = orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax, return_ties=True)
+    nn = lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy()
+    assert np.array_equal(nn, ref)                       # ties included: both sides pick the lowest index
+    assert lib.nn_grid_stats()["n_unresolved"] == 0
+
+
+def test_nn_script_lattice_and_ties(lib, orc):
+    """f32 node coordinates i*LCELL (parallel_optimized.py:343-346) and constructed exact ties."""
+    N = 32
+    ax = orc.lattice_axis_script(N, 1)
+    rng = np.random.default_rng(5)
+    pos = rng.integers(0, 64, size=(4000, 3)).astype(np.float32) / 64.0           # coarse lattice -> many exact ties
+    ref, ties = orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax, return_ties=True)
+    assert ties.sum() > 100
+    nn = lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy()
+    assert np.array_equal(nn, ref)
+
+
+def test_nn_edge_cases(lib, orc):
+    ax = orc.lattice_axis_lib(1.0, 8)
+    # one particle, far outside the lattice
+    pos = np.array([[5.0, -3.0, 0.5]], dtype=np.float64)
+    assert (lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy() == 0).all()
+    # all particles in one corner: every node needs the wide search
+    pos = (np.random.default_rng(1).random((500, 3)) * 0.05).astype(np.float32)
+    ref = orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax)
+    assert np.array_equal(lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy(), ref)
+    assert lib.nn_grid_stats()["n_wide"] > 0
+    # rectangular lattice with different tables per axis
+    qx, qy, qz = np.linspace(0.1, 0.9, 5), np.linspace(0.0, 1.0, 17), np.linspace(0.3, 0.4, 9)
+    pos = np.random.default_rng(2).random((3000, 3))
+    ref = orc.nn_exact_lattice(pos, qx, qy, qz)
+    assert np.array_equal(lib.nn_grid(lib.to_device(pos), qx, qy, qz).cpu().numpy(), ref)
+
+
+def test_nn_slab_matches_full(lib, orc):
+    """Multi-GPU building block: a slab of the lattice with only nearby particles kept gives the same answer."""
+    N, Np = 64, 1 << 17
+    pos, _, _, _ = orc.synth_particles(9, Np, 1.0)
+    ax = orc.lattice_axis_lib(1.0, N)
+    full = lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy()
+    h = ax[1] - ax[0]
+    for r in range(4):
+        sl = slice(r * N // 4, (r + 1) * N // 4)
+        o = lib.NNOpts()
+        o.use_x_keep = 1
+        o.x_keep_lo = ax[sl][0] - 4.5 * h
+        o.x_keep_hi = ax[sl][-1] + 4.5 * h
+        o.x_lo_is_domain_edge = 0
+        o.x_hi_is_domain_edge = 0
+        part = lib.nn_grid(lib.to_device(pos), ax[sl], ax, ax, o).cpu().numpy()
+        st = lib.nn_grid_stats()
+        assert st["n_unresolved"] == 0 and st["n_kept"] < Np
+        assert np.array_equal(part, full[sl])
+
+
+def test_ann_interpolate_api(vp, orc, golden):
+    """vpower.interp.ann_interpolate keeps the reference's signature and gather semantics (interp.py:1018-1049)."""
+    name, N, L = "lib16", 16, 1.0
+    pos = golden[f"{name}/pos"]
+    f = orc.density_velocity_vector(golden[f"{name}/vel"].astype(np.float64), golden[f"{name}/dens"].astype(np.float64))
+    got = vp.interp.ann_interpolate(pos, vp.interp.make_grid_coords(L, N), f, N, 0.0)
+    ref = f[golden[f"{name}/nn_ann"].astype(np.int64).ravel()].reshape(N, N, N, 4)
+    assert got.dtype == f.dtype and np.array_equal(got, ref)
+    got1 = vp.interp.ann_interpolate(pos, vp.interp.make_grid_coords(L, N), f[:, 3].copy(), N, 0.0)
+    assert np.array_equal(got1, ref[..., 3])
+    assert np.array_equal(vp.interp.make_grid_coords(L, N), orc.make_grid_coords(L, N))
+
+
+# ------------------------------------------------------------------------------------------ K2 deposit
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_deposit_golden(vp, golden, tag):
+    pos, w1, w4 = golden[f"deposit_{tag}/pos"], golden[f"deposit_{tag}/w1"], golden[f"deposit_{tag}/w4"]
+    g1 = vp.interp.deposit_to_grid(w1, pos, 12, 1.5)
+    assert g1.dtype == np.float64 and np.array_equal(g1, golden[f"deposit_{tag}/grid1"])       # integer weights: exact
+    g4 = vp.interp.deposit_to_grid(w4, pos, 12, 1.5)
+    assert np.allclose(g4, golden[f"deposit_{tag}/grid4"], rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ K4 FFT
+@pytest.mark.parametrize("N", [64, 128, 256])
+def test_fft_half_spectrum(lib, N):
+    import torch
+    rng = np.random.default_rng(N)
+    f = rng.normal(size=(N, N, N)).astype(np.float32)
+    ks = 2 * np.pi * np.fft.fftfreq(N, 1.0 / N)
+    plan = lib.PkPlan(N, ks, np.array([0.0, 1.0]))
+    got = plan.fft_half(torch.from_numpy(f.copy()).cuda()).cpu().numpy()
+    ref = np.fft.rfftn(f.astype(np.float64))
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
+
+
+# ------------------------------------------------------------------------------------------ K4+K5 fused
+@pytest.mark.parametrize("N,L", [(64, 1.0), (128, 2.5), (256, 1.0), (48, 0.7), (16, 1.0)])
+def test_pk_fields_vs_oracle(lib, orc, N, L):
+    import torch
+    rng = np.random.default_rng(100 + N)
+    f = [rng.normal(size=(N, N, N)).astype(np.float32) for _ in range(3)]
+    # give the spectrum some dynamic range
+    x = (np.arange(N) + 0.5) / N
+    f[0] += 3 * np.sin(2 * np.pi * 2 * x)[:, None, None].astype(np.float32)
+    f[1] += 2 * np.cos(2 * np.pi * 3 * x)[None, :, None].astype(np.float32)
+    kmin, kmax = 2 * np.pi / L, np.pi / (L / N)
+    for maker in (orc.edges_lib, orc.edges_script):
+        centres, edges = maker(kmin, kmax, kmin)
+        plan = lib.PkPlan(N, orc.k_axis(L, N), edges)
+        k = orc.k_magnitude(L, N)
+        for comps in ([0, 1, 2], [1]):
+            P = sum(np.abs(np.fft.fftn(f[c].astype(np.float64))) ** 2 for c in comps)
+            ref = orc.hist_sample(k, P, centres, edges, empty_to_zero=True)
+            psum, ns = plan.fields([torch.from_numpy(f[c].copy()).cuda() for c in comps])
+            assert np.array_equal(ns, ref[:, 3].astype(np.int64))                 # mode counts bit-exact
+            ok = ref[:, 3] > 0
+            rel = np.abs(psum[ok] - ref[ok, 2]) / ref[ok, 2]
+            assert rel.max() < 1e-5, (N, comps, rel.max())
+
+
+def test_shell_counts_match_reference(lib, orc, golden):
+    import torch
+    for N, L in ((16, 1.0), (32, 2.5), (64, 1.0), (48, 0.7)):
+        kmin, kmax = 2 * np.pi / L, np.pi / (L / N)
+        c, e = orc.edges_lib(kmin, kmax, kmin)
+        plan = lib.PkPlan(N, orc.k_axis(L, N), e)
+        _, ns = plan.fields([torch.ones((N, N, N), dtype=torch.float32, device="cuda")])
+        assert np.array_equal(ns, golden[f"shells_lib_{N}_{L}/Nsample"].astype(np.int64))
+    # full-size property: every mode lands in exactly one shell or outside [first,last] edge
+    for N in (256, 512):
+        kmin, kmax = 2 * np.pi, np.pi * N
+        c, e = orc.edges_lib(kmin, kmax, kmin)
+        plan = lib.PkPlan(N, orc.k_axis(1.0, N), e)
+        _, ns = plan.fields([torch.ones((N, N, N), dtype=torch.float32, device="cuda")])
+        if N == 256:
+            assert ns.sum() == 8886577
+        j = np.arange(N // 2) + 1
+        # integer-shell closed form: modes with floor(|n|+1/2) == j
+        n1 = np.fft.fftfreq(N, 1.0 / N)
+        n2 = (n1[:, None, None] ** 2 + n1[None, :, None] ** 2 + n1[None, None, :] ** 2).ravel()
+        shell = np.floor(np.sqrt(n2) + 0.5).astype(np.int64)
+        ref = np.bincount(shell, minlength=N)[1:N // 2 + 1]
+        assert np.array_equal(ns, ref)
+
+
+def test_power_cube_and_pairs_api(vp, orc, golden):
+    """_vector_power / _scalar_power / _pair_power / _hist_sample keep the reference's return conventions."""
+    v, m = golden["lib16/v_grid"], golden["lib16/m_grid"]
+    P = vp.interp._vector_power(v[..., 0], v[..., 1], v[..., 2], 1.0, 16)
+    assert P.shape == (16, 16, 16)
+    assert np.allclose(P, golden["lib16/Pgrid_velocity"], rtol=2e-4, atol=1e-6 * golden["lib16/Pgrid_velocity"].max())
+    E = m * (v[..., 0] ** 2 + v[..., 1] ** 2 + v[..., 2] ** 2)
+    Pe = vp.interp._scalar_power(E, 1.0, 16)
+    assert np.allclose(Pe, golden["lib16/Pgrid_energy"], rtol=2e-4, atol=1e-6 * golden["lib16/Pgrid_energy"].max())
+    pairs = vp.interp._pair_power(golden["lib16/Pgrid_velocity"], 1.0, 16)
+    assert pairs.shape == (4096, 2) and np.array_equal(pairs[:, 0], golden["lib16/pairs_k"])   # |k| bit-exact
+    h = vp.interp._hist_sample(pairs, 2 * np.pi, np.pi * 16, 2 * np.pi)
+    ref = golden["lib16/spctrm_velocity"]
+    assert np.array_equal(h[:, 0], ref[:, 0]) and np.array_equal(h[:, 3], ref[:, 3])
+    assert np.allclose(h[:, 2], ref[:, 2], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ whole path, library flavour
+@pytest.mark.parametrize("name,N,L", [("lib16", 16, 1.0), ("lib24", 24, 2.5), ("lib32c", 32, 1.0)])
+def test_library_path_vs_reference_golden(vp, golden, name, N, L):
+    """GasParticles(...).ann_interp_to_field(N).spctrm(q) against the unmodified reference (true ANN engine)."""
+    pos = _pos_seen_by_ann(golden, name)
+    gp = vp.interp.GasParticles(pos.copy(), golden[f"{name}/mass"].astype(np.float64),
+                                golden[f"{name}/dens"].astype(np.float64), golden[f"{name}/vel"].astype(np.float64), L)
+    bf = gp.ann_interp_to_field(N)
+    if name == "lib16":     # the lattice the reference used is the un-parsed one only when positions round trip
+        assert np.array_equal(np.stack([bf.vx, bf.vy, bf.vz], -1), golden[f"{name}/v_grid"])
+        assert np.array_equal(bf.mass, golden[f"{name}/m_grid"])
+    for q in ("velocity", "momentum", "energy"):
+        sp = bf.spctrm(q)
+        ref = golden[f"{name}/spctrm_{q}"]
+        assert np.array_equal(sp.k, ref[:, 0])
+        assert np.array_equal(sp.Nsample, ref[:, 3])
+        if name == "lib16":
+            assert np.allclose(sp.Psum, ref[:, 2], rtol=1e-5, atol=0)
+            assert np.allclose(sp.P, ref[:, 1], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("N,Np", [(64, 1 << 18), (128, 1 << 19)])
+def test_library_path_vs_oracle(vp, orc, N, Np):
+    """cfg1-sized run of the object API against the oracle (64^3 / 2^18 = BASELINE configs[0])."""
+    L = 1.0
+    pos, vel, dens, mass = orc.synth_particles(0, Np, L)
+    p64, v64, d64 = pos.astype(np.float64), vel.astype(np.float64), dens.astype(np.float64)
+    gp = vp.interp.GasParticles(p64, mass.astype(np.float64), d64, v64, L)
+    bf = gp.ann_interp_to_field(N)
+    v_ref, m_ref, Lcell = orc.ann_interp_to_field(p64, d64, v64, L, N)
+    assert np.array_equal(bf.get_v(), v_ref) and np.array_equal(bf.mass, m_ref)
+    for q in ("velocity", "momentum", "energy"):
+        sp = bf.spctrm(q)
+        ref = orc.spctrm(v_ref, m_ref, Lcell, q)
+        assert np.array_equal(sp.Nsample, ref[:, 3])
+        assert np.allclose(sp.P, ref[:, 1], rtol=1e-5, atol=0), np.max(np.abs(sp.P / ref[:, 1] - 1))
+    bf.strict_reference = False
+    sp = bf.spctrm("momentum")
+    ref = orc.spctrm(v_ref, m_ref, Lcell, "momentum", strict_reference=False)
+    assert np.allclose(sp.P, ref[:, 1], rtol=1e-5, atol=0)
+    # Parseval (interp.py:1377-1378): sum(P) (2pi/L)^3 == 1/2 mean(v^2)
+    Pg = bf.velocity_power()
+    assert np.isclose(Pg.sum() * (2 * np.pi / L) ** 3, 0.5 * np.mean((v_ref ** 2).sum(-1)), rtol=1e-5)
+
+
+def test_boxfield_from_arrays(vp, orc, golden):
+    """BoxField(v, mass, Lcell) built from host arrays, as a reference user would (interp.py:456-471)."""
+    v, m = golden["lib32c/v_grid"], golden["lib32c/m_grid"]
+    bf = vp.interp.BoxField(v, m, 1.0 / 32)
+    for q in ("velocity", "momentum", "energy"):
+        sp = bf.spctrm(q)
+        ref = golden[f"lib32c/spctrm_{q}"]
+        assert np.array_equal(sp.Nsample, ref[:, 3])
+        assert np.allclose(sp.P, ref[:, 1], rtol=2e-5, atol=0)
+    with pytest.raises(Exception):
+        bf.spctrm("vorticity")
+    # custom k range / resolution (interp.py:560-570)
+    sp = bf.spctrm("velocity", kmin=4 * np.pi, kmax=40 * np.pi, kres=np.pi)
+    ref = orc.spctrm(v, m, 1.0 / 32, "velocity", kmin=4 * np.pi, kmax=40 * np.pi, kres=np.pi)
+    assert np.array_equal(sp.Nsample, ref[:, 3]) and np.allclose(sp.Psum, ref[:, 2], rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ whole path, one C call
+@pytest.mark.parametrize("host", [True, False])
+def test_one_call_path(lib, orc, host):
+    N, Np, L = 64, 1 << 18, 1.0
+    pos, vel, dens, _ = orc.synth_particles(0, Np, L)
+    ax = orc.lattice_axis_lib(L, N)
+    Lcell = L / N
+    centres, edges = orc.edges_lib(2 * np.pi / L, np.pi / Lcell, 2 * np.pi / L)
+    a = (L / (2 * np.pi)) ** 1.5 / N ** 3
+    args = (pos, vel, dens) if host else tuple(lib.to_device(x) for x in (pos, vel, dens))
+    out, ns = lib.particles_to_pk(*args, ax, ax, ax, N, Lcell ** 3, 0.5 * a * a, orc.k_axis(L, N), edges,
+                                  quantities=("velocity", "momentum", "energy"))
+    v_ref, m_ref, _ = orc.ann_interp_to_field(pos.astype(np.float64), dens.astype(np.float64), vel.astype(np.float64), L, N)
+    for q in ("velocity", "momentum", "energy"):
+        ref = orc.spctrm(v_ref, m_ref, Lcell, q)
+        assert np.array_equal(ns, ref[:, 3].astype(np.int64))
+        # f32 particle arithmetic (rho*v)/rho differs from the f64 oracle by ulps of f32
+        assert np.allclose(out[q], ref[:, 2], rtol=1e-4, atol=0), (q, np.max(np.abs(out[q] / ref[:, 2] - 1)))
+
+
+@pytest.mark.parametrize("name", ["script16", "script16_fold2"])
+def test_script_flavour_vs_reference_golden(lib, orc, golden, name):
+    """The unfolded full transform equals the script's folded pipeline (verbatim single-rank run, Pk.txt)."""
+    pos, vel, mass = golden[f"{name}/pos"], golden[f"{name}/vel"].copy(), golden[f"{name}/mass"]
+    pos = pos - pos.min(axis=0)
+    M = np.sum(mass)
+    for c in range(3):
+        vel[:, c] -= np.sum(mass * vel[:, c]) / M
+    NTOT, LTOT = 16, 1
+    ax = orc.lattice_axis_script(NTOT, LTOT)
+    LCELL = LTOT / NTOT
+    centres, edges = orc.edges_script(2 * np.pi / LTOT, np.pi / LCELL, 2 * np.pi / LTOT)
+    const = (LTOT / (2 * np.pi)) ** 1.5 / NTOT ** 3
+    out, ns = lib.particles_to_pk(pos.astype(np.float32), vel.astype(np.float32), None, ax, ax, ax, NTOT, LCELL ** 3,
+                                  0.5 * const * const, orc.k_axis(LTOT, NTOT), edges, quantities=("velocity",))
+    ref = golden[f"{name}/Pk"]
+    assert np.array_equal(ns, ref[:, 3].astype(np.int64))
+    assert np.allclose(out["velocity"], ref[:, 2], rtol=1e-3, atol=0)
+
+
+def test_errors_are_loud(lib, vp):
+    import torch
+    with pytest.raises(lib.VPowerError):
+        lib.PkPlan(64, np.arange(64.0), np.array([1.0, 0.5]))          # edges must increase
+    with pytest.raises(Exception):
+        vp.interp.ann_interpolate(np.zeros((4, 3)), np.zeros((7, 3)), np.zeros(4), 2, 0.0)
+    with pytest.raises(Exception):
+        vp.interp.GasParticles(np.zeros((4, 3)), np.ones(4), np.ones(4), np.zeros((4, 3)), 1.0).ann_interp_to_field(8, eps=0.5)

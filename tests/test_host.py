@@ -1,0 +1,186 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/vpower_b200.h, the host-side
+mirror keeps the reference's conventions, and the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import pickle
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from vpower import _lib
+    return _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vpower_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vpower_b200.h but not exported"
+    assert sorted(built.SIGNATURES) == names, "ctypes prototypes out of sync with the header"
+    assert built.load_library().vp_version() >= 100
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import vpower.interp as vi
+    h = ctypes.c_void_p()
+    rc = built.load_library().vp_ctx_create(0, ctypes.byref(h))
+    assert rc != 0 and b"no CUDA device" in built.load_library().vp_last_error()
+    with pytest.raises(built.VPowerError):
+        vi.GasParticles(np.zeros((8, 3)), np.ones(8), np.ones(8), np.zeros((8, 3)), 1.0).ann_interp_to_field(4)
+    with pytest.raises(built.VPowerError):
+        vi.deposit_to_grid(np.ones(8), np.zeros((8, 3)), 4, 1.0)
+    with pytest.raises(built.VPowerError):
+        vi.BoxField(np.zeros((4, 4, 4, 3)), np.ones((4, 4, 4)), 0.25).spctrm("velocity")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "large-velocity-power-spectrum_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "vpower_oracle" not in txt and "refshims" not in txt, f
+
+
+def test_host_expressions_match_oracle(built, orc):
+    import vpower.interp as vi
+    for N, L in ((16, 1.0), (24, 2.5), (1024, 1.0), (500, 0.7)):
+        assert np.array_equal(vi._lattice_axis(L, N), orc.lattice_axis_lib(L, N))
+        assert np.array_equal(vi._k_axis(L, N), orc.k_axis(L, N))
+        kmin, kmax = 2 * np.pi / L, np.pi / (L / N)
+        for a, b in zip(vi._edges_lib(kmin, kmax, kmin), orc.edges_lib(kmin, kmax, kmin)):
+            assert np.array_equal(a, b)
+    assert np.array_equal(vi.make_grid_coords(2.5, 6), orc.make_grid_coords(2.5, 6))
+    # the script's linspace edges give 511 bins at (1024, 1)
+    c, e = orc.edges_script(2 * np.pi, np.pi * 1024, 2 * np.pi)
+    assert len(c) == 511 and len(e) == 512
+
+
+def test_separable_axes_detection(built):
+    import vpower.interp as vi
+    q = vi.make_grid_coords(1.0, 5)
+    ax = vi._separable_axes(q, 5)
+    assert ax is not None and np.array_equal(ax[0], vi._lattice_axis(1.0, 5))
+    q2 = q.copy()
+    q2[7, 1] += 1e-3
+    assert vi._separable_axes(q2, 5) is None
+    assert vi._separable_axes(q[:-1], 5) is None
+
+
+def test_gasparticles_preprocessing(built):
+    """shift_to_origin / remove_bulk_velocity / payload (interp.py:169-213)."""
+    import vpower.interp as vi
+    rng = np.random.default_rng(0)
+    pos, vel = rng.random((100, 3)) + 3.0, rng.normal(size=(100, 3)) + 5.0
+    mass, dens = rng.random(100) + 0.5, rng.random(100) + 1.0
+    gp = vi.GasParticles(pos.copy(), mass, dens, vel.copy(), 1.0)
+    gp.shift_to_origin()
+    gp.remove_bulk_velocity()
+    assert np.allclose(gp.pos.min(axis=0), 0)
+    assert np.allclose((mass[:, None] * gp.v).sum(0), 0, atol=1e-12)
+    pay = gp.density_velocity_vector()
+    assert pay.shape == (100, 4) and np.array_equal(pay[:, 3], dens) and np.array_equal(pay[:, 0], gp.v[:, 0] * dens)
+    assert len(gp) == 100 and len(gp[:10]) == 10
+    assert np.isclose(gp.total_kinetic_energy(), 0.5 * np.sum(mass * (gp.v ** 2).sum(1)))
+
+
+def test_power_spectrum_container(built, tmp_path):
+    """vpower.spctrm keeps the reference semantics (spctrm.py:55-380)."""
+    import vpower.spctrm as vs
+    k = np.arange(1, 6) * 2 * np.pi
+    a = vs.PowerSpectrum(np.column_stack((k, np.ones(5), np.full(5, 2.0), np.full(5, 4.0))))
+    b = vs.PowerSpectrum(np.column_stack((k, np.ones(5), np.full(5, 6.0), np.full(5, 4.0))))
+    assert len(a) == 5 and np.isclose(a.Lbox(), 1.0) and np.isclose(a.kres(), 2 * np.pi)
+    c = a.copy()
+    c.add(b)
+    assert np.allclose(c.Psum, 8) and np.allclose(c.Nsample, 8) and np.allclose(c.P, 4 * np.pi * k ** 2)
+    c.remove(b)
+    assert np.allclose(c.Psum, 2) and np.allclose(c.Nsample, 4)
+    with pytest.raises(ValueError):
+        c.remove(b)
+    with pytest.raises(Exception):
+        a.add(vs.PowerSpectrum(np.ones((3, 4))))
+    assert np.isclose(a.energy(), np.sum(a.P[:-1] * np.diff(k)))
+    e = vs.empty_spectrum_like(a)
+    assert np.all(e.Psum == 0) and e.m == 0
+    a.save(str(tmp_path))
+    assert os.path.isfile(tmp_path / "full_spctrm.pkl")
+    assert np.array_equal(vs.PowerSpectrum.load(str(tmp_path)).Psum, a.Psum)
+    s1 = vs.PowerSpectrum(a.data(), m=2, beta=np.array([0, 1, 1]))
+    s1.save(str(tmp_path))
+    assert os.path.isfile(tmp_path / "sub_spctrm_b011.pkl")
+    sl = vs.SpectrumList.load(str(tmp_path))
+    assert len(sl) == 1 and sl.m == 2 and np.array_equal(sl[np.array([0, 1, 1])].Psum, a.Psum)
+    assert vs.init_beta_space(2).shape == (8, 3)
+    assert np.isclose(vs.relative_diff(a.copy(), b.copy()), 0.0)
+    pw = vs.PowerSpectrum(np.column_stack((k, k ** -2.0, k, k)))
+    assert np.isclose(pw.index(), -2.0)
+    pickle.loads(pickle.dumps(a))
+
+
+def test_fft_index_model():
+    """numpy model of the kernel's stage/thread/register index maps (csrc/fft_core.cuh LineFFT) vs np.fft."""
+    def dft(v):
+        r = len(v)
+        kk = np.arange(r)
+        return np.exp(-2j * np.pi * np.outer(kk, kk) / r) @ v
+
+    def model(x, R2, R3):
+        L = len(x)
+        T = L // 16
+        W = np.exp(-2j * np.pi * np.arange(L) / L)
+        sm = np.zeros(L, complex)
+        for t in range(T):
+            v = dft(np.array([x[j * T + t] for j in range(16)]))
+            for k1 in range(16):
+                sm[k1 * T + t] = v[k1] * W[t * k1]
+        M2 = 16 // R2
+        regs = np.zeros((T, 16), complex)
+        sm2 = np.zeros(L, complex)
+        for t in range(T):
+            for b in range(M2):
+                g = t * M2 + b
+                k1, d3 = g // R3, g % R3
+                u = dft(np.array([sm[k1 * T + a * R3 + d3] for a in range(R2)]))
+                for k2 in range(R2):
+                    val = u[k2] * (W[16 * d3 * k2] if R3 > 1 else 1)
+                    regs[t, k2 + R2 * b] = val
+                    sm2[k1 * T + k2 * R3 + d3] = val
+        X = np.zeros(L, complex)
+        if R3 == 1:
+            for t in range(T):
+                for j in range(16):
+                    X[(t * M2 + j // R2) + 16 * (j % R2)] = regs[t, j]          # kout, two-stage form
+            return X
+        M3 = 16 // R3
+        for t in range(T):
+            for b in range(M3):
+                g = t + T * b
+                u = dft(np.array([sm2[(g % 16) * T + (g // 16) * R3 + a] for a in range(R3)]))
+                for a in range(R3):
+                    X[t + T * (j := b) + 16 * R2 * a] = u[a]                      # kout, three-stage form
+        return X
+
+    rng = np.random.default_rng(0)
+    for R2, R3 in ((2, 1), (4, 1), (8, 1), (16, 1), (16, 2), (16, 4), (16, 8)):
+        L = 16 * R2 * R3
+        x = rng.normal(size=L) + 1j * rng.normal(size=L)
+        assert np.abs(model(x, R2, R3) - np.fft.fft(x)).max() < 1e-11 * L
