@@ -92,6 +92,19 @@ int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const 
  * and the number it could not prove at all (only possible with use_x_keep).  Syncs `stream`. */
 int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_t* n_kept, void* stream);
 
+/* K1 with a payload (whole-path form).  Besides (optionally) nn_idx_d it returns
+ *   spay_d   [np] float4 = (vx', vy', vz', m) in CELL-SORTED particle order, v' = (rho*v)/rho, m = rho*lcell3
+ *            evaluated in the input dtype (interp.py:199-213,272-273), rho_d == NULL -> rho = 1;
+ *   nn_pos_d [nx,ny,nz] int32 = position in that sorted order of every node's nearest particle,
+ * so that vp_fields_sorted reads the payload almost sequentially instead of gathering by particle index. */
+int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                       const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz, double lcell3,
+                       int32_t* nn_idx_d /* may be NULL */, int32_t* nn_pos_d, float* spay_d, const vp_nn_opts* opts,
+                       void* stream);
+/* K3 on the sorted payload: same planes as vp_build_fields (interp.py:501-557). */
+int vp_fields_sorted(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, float* const v_d[3],
+                     float* const p_d[3], float* e_d, float* m_d, void* stream);
+
 /* Row gather: dst[i,:] = src[idx[i],:]  (interp.py:1040-1045 `f[index]`), row_bytes in {4,8,12,16,24,32}. */
 int vp_gather_rows(vp_ctx* ctx, const int32_t* idx_d, int64_t n, const void* src_d, int row_bytes,
                    void* dst_d, void* stream);

@@ -1,8 +1,9 @@
 // K1: exact nearest-particle gridding on a sorted cell list.  See include/vpower_b200.h (vp_nn_grid).
 //
-// Pipeline:  keygen (cell key per particle, optional x filter)  ->  radix sort of (key, index)
-//            ->  reorder to sorted {x,y,z,index}  ->  cell starts  ->  ring-1 search per lattice node
-//            ->  wide (ring >= 2, warp per node) search for the nodes ring 1 could not prove.
+// Pipeline:  keygen + pack (cell key per particle, optional x filter, one packed record per particle)
+//            ->  radix sort of (key, slot)  ->  permute the packed records into cell order  ->  cell starts
+//            ->  ring-1 search per lattice node (f32 prefilter)  ->  exact f64 search (warp per node, growing ring)
+//                for every node the prefilter could not settle.
 //
 // Exactness: a candidate is accepted only if its distance is strictly below the distance from the
 // node to every face of the searched cell block behind which unexamined particles can exist.  All
@@ -24,27 +25,9 @@ struct Grid {
   int closed_xlo, closed_xhi;  // 1: particles beyond that x face were dropped (face constrains the proof)
 };
 
-template <typename T>
-struct Sorted;  // sorted particle record
-template <>
-struct Sorted<float> {
-  using rec = float4;  // x,y,z, index bits
-  __device__ static rec make(float x, float y, float z, int i) { return make_float4(x, y, z, __int_as_float(i)); }
-  __device__ static void get(const rec* __restrict__ a, int64_t p, double& x, double& y, double& z, int& i) {
-    float4 r = __ldg(a + p);
-    x = r.x; y = r.y; z = r.z; i = __float_as_int(r.w);
-  }
-};
-template <>
-struct Sorted<double> {
-  struct __align__(16) rec { double x, y, z; long long i; };
-  __device__ static rec make(double x, double y, double z, int i) { rec r; r.x = x; r.y = y; r.z = z; r.i = i; return r; }
-  __device__ static void get(const rec* __restrict__ a, int64_t p, double& x, double& y, double& z, int& i) {
-    const double2* q = reinterpret_cast<const double2*>(a + p);
-    double2 u = __ldg(q), v = __ldg(q + 1);
-    x = u.x; y = u.y; z = v.x; i = int(__double_as_longlong(v.y));
-  }
-};
+// Sorted particle record: position relative to the grid origin rounded to f32 (used only by the f32
+// prefilter; every close call is re-decided in f64 from the caller's array) and the particle index.
+typedef float4 rec_t;
 
 __device__ __forceinline__ int cell_of(double x, double o, double ih, int g) {
   double f = (x - o) * ih;
@@ -53,9 +36,23 @@ __device__ __forceinline__ int cell_of(double x, double o, double ih, int g) {
   return int(f);
 }
 
+// Packed particle record written once, in input order, so that the permutation after the sort is ONE random
+// 64-byte access per particle (separate pos/vel/rho arrays would cost three).
+//   a = (x-ox, y-oy, z-oz as f32, particle index)        b = (vx', vy', vz', m)  [only with a payload]
+// with v' = (rho*v)/rho and m = rho*Lcell^3 evaluated in the input dtype (interp.py:199-213,272-273).
+struct __align__(32) rec32_t { float4 a, b; };
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_keygen(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ keys,
-                                                 uint32_t* __restrict__ vals, unsigned long long* __restrict__ kept) {
+struct PayloadIn {
+  const T* vel;   // [np,3] or null
+  const T* rho;   // [np] or null (rho = 1)
+  T lcell3;
+};
+
+template <typename T, bool PAY>
+__global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, Grid g,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                      void* __restrict__ packed, unsigned long long* __restrict__ kept) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   bool ok = i < np;
   double x = 0, y = 0, z = 0;
@@ -70,30 +67,52 @@ __global__ void __launch_bounds__(256) k_keygen(const T* __restrict__ pos, int64
     int cx = cell_of(x, g.ox, g.ihx, g.gx), cy = cell_of(y, g.oy, g.ihy, g.gy), cz = cell_of(z, g.oz, g.ihz, g.gz);
     key = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
   }
-  if (!g.use_keep) {
-    if (ok) { keys[i] = key; vals[i] = uint32_t(i); }
-    return;
+  int64_t o = i;
+  if (g.use_keep) {
+    // compaction (order is irrelevant: the sort follows and ties are decided by index)
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0 && m) base = atomicAdd(kept, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    o = int64_t(base + __popc(m & ((1u << lane) - 1u)));
   }
-  // compaction (order is irrelevant: the sort follows and ties are decided by index)
-  unsigned m = __ballot_sync(0xffffffffu, ok);
-  int lane = threadIdx.x & 31;
-  unsigned long long base = 0;
-  if (lane == 0 && m) base = atomicAdd(kept, (unsigned long long)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (ok) {
-    unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
-    keys[o] = key;
-    vals[o] = uint32_t(i);
+  if (!ok) return;
+  keys[o] = key;
+  vals[o] = uint32_t(o);
+  const float4 a = make_float4(float(x - g.ox), float(y - g.oy), float(z - g.oz), __int_as_float(int(i)));
+  if (PAY) {
+    T vx = pin.vel[3 * i], vy = pin.vel[3 * i + 1], vz = pin.vel[3 * i + 2];
+    T m = pin.lcell3;
+    if (pin.rho) {
+      T r = pin.rho[i];
+      vx = (vx * r) / r;
+      vy = (vy * r) / r;
+      vz = (vz * r) / r;
+      m = r * pin.lcell3;
+    }
+    rec32_t* out = static_cast<rec32_t*>(packed) + o;
+    out->a = a;
+    out->b = make_float4(float(vx), float(vy), float(vz), float(m));
+  } else {
+    static_cast<float4*>(packed)[o] = a;
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_reorder(const T* __restrict__ pos, const uint32_t* __restrict__ vals, int64_t n,
-                                                  typename Sorted<T>::rec* __restrict__ out) {
+template <bool PAY>
+__global__ void __launch_bounds__(256) k_permute(const void* __restrict__ packed, const uint32_t* __restrict__ vals, int64_t n,
+                                                  rec_t* __restrict__ spos, float4* __restrict__ spay) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t j = vals[i];
-  out[i] = Sorted<T>::make(pos[3 * size_t(j)], pos[3 * size_t(j) + 1], pos[3 * size_t(j) + 2], int(j));
+  const uint32_t j = vals[i];
+  if (PAY) {
+    const float4* src = reinterpret_cast<const float4*>(static_cast<const rec32_t*>(packed) + j);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    spos[i] = a;
+    spay[i] = b;
+  } else {
+    spos[i] = __ldg(static_cast<const float4*>(packed) + j);
+  }
 }
 
 // start[c] = first sorted position whose key >= c, for c in [0, ncells]; start[ncells] = n
@@ -167,10 +186,18 @@ struct Lattice {
   int nx, ny, nz;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_search_ring1(const typename Sorted<T>::rec* __restrict__ part,
-                                                       const uint32_t* __restrict__ start, Grid g, Lattice L,
-                                                       int32_t* __restrict__ nn, uint32_t* __restrict__ wide_list,
+// Ring-1 search, f32 prefilter.  One thread per lattice node (consecutive lanes = consecutive z nodes).
+// Distances are evaluated in f32 on origin-relative coordinates; the two smallest are tracked.  The node is
+// settled here only if (a) the runner-up is farther than the winner by more than a rigorous bound on the f32
+// error of both and (b) the winner (plus that bound) is strictly inside the proof margin.  Everything else --
+// near ties, exact ties, unproven nodes -- goes to k_search_exact.
+//
+// f32 error bound: stored coordinate c~ = fl(p-o), query q~ = fl(q-o), d~x = fl(q~-c~):
+//   |d~x - dx| <= 2^-24 (|q-o| + |p-o| + |dx|) <= 2^-23 (E + |dx|) =: eps      (E = grid extent)
+//   |d~^2 - d^2| <= 2 sqrt(3) d eps + 3 eps^2 + 2^-22 d^2
+__global__ void __launch_bounds__(256) k_search_ring1(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
+                                                       Lattice L, float extent, int32_t* __restrict__ nn,
+                                                       int32_t* __restrict__ nn_pos, uint32_t* __restrict__ list,
                                                        vp_nn_stats_dev* __restrict__ stats) {
   const int64_t nnodes = int64_t(L.nx) * L.ny * L.nz;
   int64_t node = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -178,62 +205,81 @@ __global__ void __launch_bounds__(256) k_search_ring1(const typename Sorted<T>::
   int k = int(node % L.nz);
   int64_t t = node / L.nz;
   int j = int(t % L.ny), i = int(t / L.ny);
-  const double qx = L.qx[i], qy = L.qy[j], qz = L.qz[k];
+  const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
+  const float qx = float(qxd - g.ox), qy = float(qyd - g.oy), qz = float(qzd - g.oz);
   const int cx = L.cx[i], cy = L.cy[j], cz = L.cz[k];
   const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
   const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gy - 1);
   const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
-  Best b;
-  b.d2 = INFINITY;
-  b.idx = 0x7fffffff;
+  float b1 = INFINITY, b2 = INFINITY;
+  int bi = -1;
   for (int X = x0; X <= x1; ++X)
     for (int Y = y0; Y <= y1; ++Y) {
-      size_t row = (size_t(X) * g.gy + Y) * g.gz;
-      uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
+      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+      const uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
       for (uint32_t p = s; p < e; ++p) {
-        double x, y, z;
-        int id;
-        Sorted<T>::get(part, p, x, y, z, id);
-        consider(b, qx, qy, qz, x, y, z, id);
+        const float4 r = __ldg(part + p);
+        const float dx = qx - r.x, dy = qy - r.y, dz = qz - r.z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool lt = d < b1;
+        b2 = fminf(b2, lt ? b1 : d);
+        bi = lt ? int(p) : bi;
+        b1 = lt ? d : b1;
       }
     }
-  double m = fmin(axis_margin(qx, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
-                  fmin(axis_margin(qy, g.oy, g.hy, y0, y1, g.gy, false, false),
-                       axis_margin(qz, g.oz, g.hz, z0, z1, g.gz, false, false)));
-  if (proven(b, m)) {
-    nn[node] = b.idx;
+  bool settled = false;
+  if (bi >= 0) {
+    const float rb = sqrtf(b2 < INFINITY ? b2 : b1);
+    const float eps = 1.5e-7f * (extent + rb);
+    const float tol = 8.f * rb * eps + 8.f * eps * eps + 1e-6f * rb * rb;   // >= err(b1) + err(b2)
+    if (b2 - b1 > tol) {
+      const double m = fmin(axis_margin(qxd, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
+                            fmin(axis_margin(qyd, g.oy, g.hy, y0, y1, g.gy, false, false),
+                                 axis_margin(qzd, g.oz, g.hz, z0, z1, g.gz, false, false)));
+      if (m == INFINITY) settled = true;
+      else if (m > 0.0) {
+        const float mf = __double2float_rd(m * (1.0 - 1.0 / 1048576.0));
+        settled = b1 + tol < mf * mf;
+      }
+    }
+  }
+  if (settled) {
+    if (nn) nn[node] = __float_as_int(__ldg(&part[bi].w));
+    if (nn_pos) nn_pos[node] = bi;
   } else {
-    nn[node] = -1;
     unsigned long long slot = atomicAdd(&stats->n_wide, 1ull);
-    wide_list[slot] = uint32_t(node);
+    list[slot] = uint32_t(node);
   }
 }
 
-// one warp per unproven node; the searched block doubles its ring until the proof holds
+// Exact search, one warp per listed node, f64 arithmetic on the caller's coordinates.  The searched block
+// starts at ring 1 and doubles until the proof holds (or every kept particle has been examined).
 template <typename T>
-__global__ void __launch_bounds__(256) k_search_wide(const typename Sorted<T>::rec* __restrict__ part,
-                                                      const uint32_t* __restrict__ start, Grid g, Lattice L,
-                                                      int32_t* __restrict__ nn, const uint32_t* __restrict__ wide_list,
-                                                      vp_nn_stats_dev* __restrict__ stats) {
+__global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ part, const uint32_t* __restrict__ start,
+                                                       const T* __restrict__ pos, Grid g, Lattice L, int32_t* __restrict__ nn,
+                                                       int32_t* __restrict__ nn_pos, const uint32_t* __restrict__ list,
+                                                       vp_nn_stats_dev* __restrict__ stats) {
   const unsigned long long nw = stats->n_wide;
   const int lane = threadIdx.x & 31;
   const unsigned long long warp0 = (unsigned long long)(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const unsigned long long nwarps = (unsigned long long)(gridDim.x) * (blockDim.x >> 5);
   for (unsigned long long w = warp0; w < nw; w += nwarps) {
-    const int64_t node = wide_list[w];
+    const int64_t node = list[w];
     int k = int(node % L.nz);
     int64_t t = node / L.nz;
     int j = int(t % L.ny), i = int(t / L.ny);
     const double qx = L.qx[i], qy = L.qy[j], qz = L.qz[k];
     const int cx = L.cx[i], cy = L.cy[j], cz = L.cz[k];
     Best b;
+    int bpos = -1;
     bool done = false;
-    for (int r = 2; !done; r *= 2) {
+    for (int r = 1; !done; r *= 2) {
       const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
       const int y0 = max(cy - r, 0), y1 = min(cy + r, g.gy - 1);
       const int z0 = max(cz - r, 0), z1 = min(cz + r, g.gz - 1);
       b.d2 = INFINITY;
       b.idx = 0x7fffffff;
+      bpos = -1;
       const int nyb = y1 - y0 + 1;
       const int nrows = (x1 - x0 + 1) * nyb;
       for (int rr = lane; rr < nrows; rr += 32) {
@@ -241,17 +287,18 @@ __global__ void __launch_bounds__(256) k_search_wide(const typename Sorted<T>::r
         size_t row = (size_t(X) * g.gy + Y) * g.gz;
         uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
         for (uint32_t p = s; p < e; ++p) {
-          double x, y, z;
-          int id;
-          Sorted<T>::get(part, p, x, y, z, id);
-          consider(b, qx, qy, qz, x, y, z, id);
+          const int id = __float_as_int(__ldg(&part[p].w));
+          const int before = b.idx;
+          consider(b, qx, qy, qz, double(pos[3 * size_t(id)]), double(pos[3 * size_t(id) + 1]), double(pos[3 * size_t(id) + 2]), id);
+          if (b.idx != before) bpos = int(p);
         }
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
         double od = __shfl_xor_sync(0xffffffffu, b.d2, o);
         int oi = __shfl_xor_sync(0xffffffffu, b.idx, o);
-        if (od < b.d2 || (od == b.d2 && oi < b.idx)) { b.d2 = od; b.idx = oi; }
+        int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+        if (od < b.d2 || (od == b.d2 && oi < b.idx)) { b.d2 = od; b.idx = oi; bpos = op; }
       }
       double m = fmin(axis_margin(qx, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
                       fmin(axis_margin(qy, g.oy, g.hy, y0, y1, g.gy, false, false),
@@ -264,8 +311,28 @@ __global__ void __launch_bounds__(256) k_search_wide(const typename Sorted<T>::r
         done = true;
       }
     }
-    if (lane == 0) nn[node] = (b.idx == 0x7fffffff) ? -1 : b.idx;
+    if (lane == 0) {
+      if (nn) nn[node] = (b.idx == 0x7fffffff) ? -1 : b.idx;
+      if (nn_pos) nn_pos[node] = bpos;
+    }
   }
+}
+
+// fields from the SORTED payload: node -> sorted position of its nearest particle -> (v', m)
+__global__ void __launch_bounds__(256) k_fields_sorted(const int32_t* __restrict__ nn_pos, int64_t n, const float4* __restrict__ spay,
+                                                        float* vx, float* vy, float* vz, float* px, float* py, float* pz, float* e,
+                                                        float* mo) {
+  int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float4 w = __ldg(spay + nn_pos[t]);
+  if (vx) vx[t] = w.x;
+  if (vy) vy[t] = w.y;
+  if (vz) vz[t] = w.z;
+  if (px) px[t] = w.x * w.w;
+  if (py) py[t] = w.y * w.w;
+  if (pz) pz[t] = w.z * w.w;
+  if (e) e[t] = w.w * (w.x * w.x + w.y * w.y + w.z * w.z);   // interp.py:546 (no 1/2)
+  if (mo) mo[t] = w.w;
 }
 
 __global__ void __launch_bounds__(256) k_gather_words(const int32_t* __restrict__ idx, int64_t n, const uint32_t* __restrict__ src,
@@ -366,25 +433,39 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
 }
 
 struct NNScratch {
-  size_t keys, sorted, start, tail, total;
+  size_t keys, packed, spos, start, tail, total;
 };
-NNScratch nn_scratch(int64_t np, size_t rec_bytes, uint64_t ncells, int64_t nnodes) {
+NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, int64_t nnodes) {
   NNScratch s;
   s.keys = vp_align256(size_t(np) * 4);
-  s.sorted = vp_align256(size_t(np) * rec_bytes);
+  s.packed = vp_align256(size_t(np) * (pay ? sizeof(rec32_t) : sizeof(float4)));
+  s.spos = vp_align256(size_t(np) * sizeof(rec_t));
   s.start = vp_align256((ncells + 1) * 4);
   size_t b_wide = vp_align256(size_t(nnodes) * 4), b_sort = vp_sort_scratch_bytes(np);
-  s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are reordered; the wide list reuses it
-  s.total = 2 * s.keys + s.sorted + s.start + s.tail + 1024;
+  s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are permuted; the node list reuses it
+  s.total = 2 * s.keys + s.packed + s.spos + s.start + s.tail + 2048;
   return s;
 }
 
+// Optional payload travelling with the particles (whole-path use): sorted (v', m) records and the sorted position
+// of every node's nearest particle, so that the field kernel reads the payload almost sequentially.
+template <typename T>
+struct NNPayload {
+  const T* vel = nullptr;
+  const T* rho = nullptr;
+  double lcell3 = 1.0;
+  float4* spay_out = nullptr;    // [np]
+  int32_t* nn_pos_out = nullptr;  // [nnodes]
+};
+
 template <typename T>
 int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int nx, const double* qy, int ny,
-                  const double* qz, int nz, int32_t* nn, const vp_nn_opts* opts, cudaStream_t st) {
+                  const double* qz, int nz, int32_t* nn, const NNPayload<T>* pay, const vp_nn_opts* opts, cudaStream_t st) {
   const int64_t nnodes = int64_t(nx) * ny * nz;
   VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
   VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
+  const bool has_pay = pay != nullptr;
+  if (has_pay) VP_REQUIRE(pay->vel && pay->spay_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
   vp_nn_opts o;
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
@@ -427,23 +508,31 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   L.nx = nx; L.ny = ny; L.nz = nz;
 
   // ---- scratch
-  using rec = typename Sorted<T>::rec;
-  const NNScratch sc = nn_scratch(np, sizeof(rec), ncells, nnodes);
+  const NNScratch sc = nn_scratch(np, has_pay, ncells, nnodes);
   vp_arena_scope scope(ctx);
   VP_TRY(vp_arena_reserve(ctx, sc.total));
   uint32_t* keys = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
   uint32_t* vals = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
-  rec* sorted = static_cast<rec*>(vp_arena_alloc(ctx, sc.sorted));
+  void* packed = vp_arena_alloc(ctx, sc.packed);
+  rec_t* spos = static_cast<rec_t*>(vp_arena_alloc(ctx, sc.spos));
   uint32_t* start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.start));
   void* scratch = vp_arena_alloc(ctx, sc.tail);
-  VP_REQUIRE(keys && vals && sorted && start && scratch, "vp_nn_grid: arena carve failed");
-  uint32_t* wide_list = static_cast<uint32_t*>(scratch);
+  VP_REQUIRE(keys && vals && packed && spos && start && scratch, "vp_nn_grid: arena carve failed");
+  uint32_t* node_list = static_cast<uint32_t*>(scratch);
 
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
   int64_t n = np;
   if (np > 0) {
-    vp_stage stage(ctx, "k1a_keygen", st, 1, double(np) * (3.0 * sizeof(T) + 8.0));
-    k_keygen<T><<<unsigned((np + 255) / 256), 256, 0, st>>>(pos, np, g, keys, vals, &ctx->nn_stats_d->n_kept);
+    // read pos (+vel, rho), write key, slot and the packed record
+    const double es = sizeof(T);
+    vp_stage stage(ctx, "k1a_keygen_pack", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 8.0 + 32.0 : 3 * es + 8.0 + 16.0));
+    PayloadIn<T> pin;
+    pin.vel = has_pay ? pay->vel : nullptr;
+    pin.rho = has_pay ? pay->rho : nullptr;
+    pin.lcell3 = T(has_pay ? pay->lcell3 : 1.0);
+    const unsigned nb = unsigned((np + 255) / 256);
+    if (has_pay) k_keygen_pack<T, true><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, &ctx->nn_stats_d->n_kept);
+    else k_keygen_pack<T, false><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, &ctx->nn_stats_d->n_kept);
     VP_CHECK_LAUNCH();
   }
   if (o.use_x_keep) {
@@ -458,8 +547,11 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   VP_TRY(vp_sort_pairs_impl(ctx, keys, vals, n, bits, scratch, st));
   if (n > 0) {
     {
-      vp_stage stage(ctx, "k1c_reorder", st, 1, double(n) * (4.0 + 3.0 * sizeof(T) + sizeof(rec)));
-      k_reorder<T><<<unsigned((n + 255) / 256), 256, 0, st>>>(pos, vals, n, sorted);
+      // slot read, one packed record gathered, sorted records written
+      vp_stage stage(ctx, "k1c_permute", st, 1, double(n) * (4.0 + (has_pay ? 64.0 : 32.0)));
+      const unsigned nb = unsigned((n + 255) / 256);
+      if (has_pay) k_permute<true><<<nb, 256, 0, st>>>(packed, vals, n, spos, pay->spay_out);
+      else k_permute<false><<<nb, 256, 0, st>>>(packed, vals, n, spos, nullptr);
     }
     {
       vp_stage stage(ctx, "k1d_cell_starts", st, 1, double(n) * 4.0 + double(ncells) * 4.0);
@@ -469,17 +561,32 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     k_fill_u32<<<unsigned((ncells + 1 + 255) / 256), 256, 0, st>>>(start, int64_t(ncells + 1), 0u);
   }
   VP_CHECK_LAUNCH();
+  int32_t* nn_pos = has_pay ? pay->nn_pos_out : nullptr;
   {
     // sorted records read once + cell starts read once + one index written per node
-    vp_stage stage(ctx, "k1e_search_ring1", st, 1, double(n) * sizeof(rec) + double(ncells) * 4.0 + double(nnodes) * 4.0);
-    k_search_ring1<T><<<unsigned((nnodes + 255) / 256), 256, 0, st>>>(sorted, start, g, L, nn, wide_list, ctx->nn_stats_d);
+    vp_stage stage(ctx, "k1e_search_ring1", st, 1, double(n) * sizeof(rec_t) + double(ncells) * 4.0 + double(nnodes) * 4.0);
+    const float extent = float(fmax(fmax(g.gx * g.hx, g.gy * g.hy), g.gz * g.hz));
+    k_search_ring1<<<unsigned((nnodes + 255) / 256), 256, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, node_list, ctx->nn_stats_d);
   }
   {
-    vp_stage stage(ctx, "k1f_search_wide", st, 1);
-    k_search_wide<T><<<ctx->sm_count * 4, 256, 0, st>>>(sorted, start, g, L, nn, wide_list, ctx->nn_stats_d);
+    vp_stage stage(ctx, "k1f_search_exact", st, 1);
+    k_search_exact<T><<<ctx->sm_count * 8, 256, 0, st>>>(spos, start, pos, g, L, nn, nn_pos, node_list, ctx->nn_stats_d);
   }
   VP_CHECK_LAUNCH();
   return VP_OK;
+}
+
+template <typename T>
+int nn_payload_typed(vp_ctx* ctx, const void* pos, const void* vel, const void* rho, int64_t np, const double* qx, int nx,
+                     const double* qy, int ny, const double* qz, int nz, double lcell3, int32_t* nn_idx, int32_t* nn_pos,
+                     float* spay, const vp_nn_opts* opts, cudaStream_t st) {
+  NNPayload<T> pay;
+  pay.vel = static_cast<const T*>(vel);
+  pay.rho = static_cast<const T*>(rho);
+  pay.lcell3 = lcell3;
+  pay.spay_out = reinterpret_cast<float4*>(spay);
+  pay.nn_pos_out = nn_pos;
+  return nn_grid_typed<T>(ctx, static_cast<const T*>(pos), np, qx, nx, qy, ny, qz, nz, nn_idx, &pay, opts, st);
 }
 
 }  // namespace
@@ -490,8 +597,41 @@ size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* 
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
   Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
-  size_t rb = pos_dtype == VP_F64 ? sizeof(Sorted<double>::rec) : sizeof(Sorted<float>::rec);
-  return nn_scratch(np, rb, uint64_t(g.gx) * g.gy * g.gz, int64_t(nx) * ny * nz).total + 4096;
+  (void)pos_dtype;
+  return nn_scratch(np, true, uint64_t(g.gx) * g.gy * g.gz, int64_t(nx) * ny * nz).total + 4096;
+}
+
+extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                                  const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz,
+                                  double lcell3, int32_t* nn_idx_d, int32_t* nn_pos_d, float* spay_d, const vp_nn_opts* opts,
+                                  void* stream) {
+  VP_REQUIRE(ctx && pos_d && vel_d && qx_h && qy_h && qz_h && nn_pos_d && spay_d, "vp_nn_grid_payload: null argument");
+  VP_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vp_nn_grid_payload: bad sizes");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VP_F32)
+    return nn_payload_typed<float>(ctx, pos_d, vel_d, rho_d, np, qx_h, nx, qy_h, ny, qz_h, nz, lcell3, nn_idx_d, nn_pos_d, spay_d, opts, st);
+  if (dtype == VP_F64)
+    return nn_payload_typed<double>(ctx, pos_d, vel_d, rho_d, np, qx_h, nx, qy_h, ny, qz_h, nz, lcell3, nn_idx_d, nn_pos_d, spay_d, opts, st);
+  vp_set_error("vp_nn_grid_payload: unknown dtype %d", dtype);
+  return VP_ERR_ARG;
+}
+
+extern "C" int vp_fields_sorted(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, float* const v_d[3],
+                                float* const p_d[3], float* e_d, float* m_d, void* stream) {
+  VP_REQUIRE(ctx && nn_pos_d && spay_d, "vp_fields_sorted: null argument");
+  if (n_nodes == 0) return VP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* v[3] = {v_d ? v_d[0] : nullptr, v_d ? v_d[1] : nullptr, v_d ? v_d[2] : nullptr};
+  float* p[3] = {p_d ? p_d[0] : nullptr, p_d ? p_d[1] : nullptr, p_d ? p_d[2] : nullptr};
+  int nplanes = (e_d != nullptr) + (m_d != nullptr);
+  for (int c = 0; c < 3; ++c) nplanes += (v[c] != nullptr) + (p[c] != nullptr);
+  // per node: sorted position read, 16-byte payload record read, 4 B written per plane
+  vp_stage stage(ctx, "k3_fields_sorted", st, 1, double(n_nodes) * (4.0 + 16.0 + 4.0 * nplanes));
+  k_fields_sorted<<<unsigned((n_nodes + 255) / 256), 256, 0, st>>>(nn_pos_d, n_nodes, reinterpret_cast<const float4*>(spay_d), v[0],
+                                                                   v[1], v[2], p[0], p[1], p[2], e_d, m_d);
+  VP_CHECK_LAUNCH();
+  return VP_OK;
 }
 
 extern "C" int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const double* qx_h, int nx,
@@ -502,9 +642,9 @@ extern "C" int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t
   VP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pos_dtype == VP_F32)
-    return nn_grid_typed<float>(ctx, static_cast<const float*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, opts, st);
+    return nn_grid_typed<float>(ctx, static_cast<const float*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, nullptr, opts, st);
   if (pos_dtype == VP_F64)
-    return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, opts, st);
+    return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, nullptr, opts, st);
   vp_set_error("vp_nn_grid: unknown dtype %d", pos_dtype);
   return VP_ERR_ARG;
 }

@@ -49,7 +49,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
 
   size_t own = 0;
   if (on_host) own += vp_align256(size_t(np) * 3 * es) * 2 + (rho ? vp_align256(size_t(np) * es) : 0);
-  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(nbins) * 16) + 8192;
+  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * 16) + vp_align256(size_t(nbins) * 16) + 8192;
   size_t inner = vp_nn_grid_scratch_bytes_tables(np, dtype, qx, N, qy, N, qz, N, nullptr);
   size_t inner2 = vp_pk_fields_scratch_bytes(plan);
   vp_arena_scope scope(ctx);
@@ -66,7 +66,8 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
     if (rho) VP_CUDA(cudaMemcpyAsync(r, rho, size_t(np) * es, cudaMemcpyHostToDevice, st));
     pos_d = p; vel_d = v; rho_d = r;
   }
-  int32_t* nn = static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4));
+  int32_t* nn_pos = static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4));
+  float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * 16));
   float* planes[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < nplanes; ++i) {
     planes[i] = static_cast<float*>(vp_arena_alloc(ctx, n3 * 4));
@@ -74,16 +75,16 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   }
   double* psum_d = static_cast<double*>(vp_arena_alloc(ctx, size_t(nbins) * 8));
   uint64_t* ns_d = static_cast<uint64_t*>(vp_arena_alloc(ctx, size_t(nbins) * 8));
-  VP_REQUIRE(nn && psum_d && ns_d, "particles_to_pk: arena carve failed");
+  VP_REQUIRE(nn_pos && spay && psum_d && ns_d, "particles_to_pk: arena carve failed");
 
-  VP_TRY(vp_nn_grid(ctx, pos_d, dtype, np, qx, N, qy, N, qz, N, nn, nullptr, st));
+  VP_TRY(vp_nn_grid_payload(ctx, pos_d, vel_d, rho_d, dtype, np, qx, N, qy, N, qz, N, lcell3, nullptr, nn_pos, spay, nullptr, st));
 
   int at = 0;
   float *v3[3] = {nullptr, nullptr, nullptr}, *p3[3] = {nullptr, nullptr, nullptr}, *e1 = nullptr;
   if (want_v) { v3[0] = planes[at++]; v3[1] = planes[at++]; v3[2] = planes[at++]; }
   if (want_p) { p3[0] = planes[at++]; if (!strict) { p3[1] = planes[at++]; p3[2] = planes[at++]; } }
   if (want_e) e1 = planes[at++];
-  VP_TRY(vp_build_fields(ctx, nn, int64_t(n3), vel_d, rho_d, dtype, lcell3, v3, p3, e1, nullptr, st));
+  VP_TRY(vp_fields_sorted(ctx, nn_pos, int64_t(n3), spay, v3, p3, e1, nullptr, st));
 
   std::vector<double> hp(nbins);
   auto one = [&](float** f, int nc, double scale, int row) -> int {

@@ -44,6 +44,8 @@ SIGNATURES = {
     "vp_launch_count": (C.c_ulonglong, [_P]),
     "vp_nn_grid": (_I, [_P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _P, C.POINTER(NNOpts), _P]),
     "vp_nn_grid_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _P]),
+    "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
+    "vp_fields_sorted": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_gather_rows": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "vp_build_fields": (_I, [_P, _P, _L, _P, _P, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_deposit_ngp": (_I, [_P, _P, _I, _L, _P, _I, _I, _D, _P, _P]),
@@ -164,6 +166,46 @@ def nn_grid(pos_t, qx, qy, qz, opts: NNOpts | None = None):
     _check(load_library().vp_nn_grid(ctx(), _P(pos_t.data_ptr()), _dtype_code(pos_t), pos_t.shape[0], qx_p, len(qx_a),
                                      qy_p, len(qy_a), qz_p, len(qz_a), _P(out.data_ptr()),
                                      C.byref(opts) if opts is not None else None, stream_ptr()))
+    return out
+
+
+def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):
+    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, spay[np,4] f32 in cell order)."""
+    torch = _torch()
+    assert pos_t.is_cuda and pos_t.is_contiguous() and vel_t.is_contiguous() and vel_t.dtype == pos_t.dtype
+    qx_a, qx_p = _as_dp(qx)
+    qy_a, qy_p = _as_dp(qy)
+    qz_a, qz_p = _as_dp(qz)
+    shape = (len(qx_a), len(qy_a), len(qz_a))
+    nn_idx = torch.empty(shape, dtype=torch.int32, device=pos_t.device) if want_idx else None
+    nn_pos = torch.empty(shape, dtype=torch.int32, device=pos_t.device)
+    spay = torch.empty((pos_t.shape[0], 4), dtype=torch.float32, device=pos_t.device)
+    _check(load_library().vp_nn_grid_payload(
+        ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()), _P(rho_t.data_ptr()) if rho_t is not None else None,
+        _dtype_code(pos_t), pos_t.shape[0], qx_p, shape[0], qy_p, shape[1], qz_p, shape[2], float(lcell3),
+        _P(nn_idx.data_ptr()) if want_idx else None, _P(nn_pos.data_ptr()), _P(spay.data_ptr()),
+        C.byref(opts) if opts is not None else None, stream_ptr()))
+    return nn_idx, nn_pos, spay
+
+
+def fields_sorted(nn_pos_t, spay_t, want_v=True, want_p=(False, False, False), want_e=False, want_m=False):
+    """-> dict of float32 CUDA cubes (vx,vy,vz,px,py,pz,e,m as requested) from the sorted payload."""
+    torch = _torch()
+    shape = tuple(nn_pos_t.shape)
+    out = {}
+
+    def cube(name, on):
+        if on:
+            out[name] = torch.empty(shape, dtype=torch.float32, device=nn_pos_t.device)
+            return out[name].data_ptr()
+        return None
+
+    v = (_P * 3)(*[cube(nm, want_v) for nm in ("vx", "vy", "vz")])
+    p = (_P * 3)(*[cube(nm, on) for nm, on in zip(("px", "py", "pz"), want_p)])
+    e = cube("e", want_e)
+    m = cube("m", want_m)
+    _check(load_library().vp_fields_sorted(ctx(), _P(nn_pos_t.data_ptr()), nn_pos_t.numel(), _P(spay_t.data_ptr()), v, p,
+                                           _P(e) if e else None, _P(m) if m else None, stream_ptr()))
     return out
 
 

@@ -103,11 +103,11 @@ class GasParticles:
         ax = _lattice_axis(self.Lbox, Nsize)
         dt = np.float64 if np.asarray(self.pos).dtype == np.float64 else np.float32
         pos_t = _lib.to_device(np.asarray(self.pos, dtype=dt))
-        nn = _lib.nn_grid(pos_t, ax, ax, ax)
-        del pos_t
         vel_t = _lib.to_device(np.asarray(self.v, dtype=dt))
         rho_t = _lib.to_device(np.asarray(self.density, dtype=dt))
-        return BoxField._from_device(nn, vel_t, rho_t, Lcell)
+        nn, nn_pos, spay = _lib.nn_grid_payload(pos_t, vel_t, rho_t, ax, ax, ax, Lcell ** 3)
+        del pos_t
+        return BoxField._from_device(nn, vel_t, rho_t, Lcell, nn_pos, spay)
 
     # totals used by check_conservation (interp.py:424-450)
     def total_mass(self):
@@ -137,10 +137,10 @@ class BoxField:
         self.Lbox = self.Nsize * self.Lcell
 
     @classmethod
-    def _from_device(cls, nn_t, vel_t, rho_t, Lcell):
+    def _from_device(cls, nn_t, vel_t, rho_t, Lcell, nn_pos_t=None, spay_t=None):
         self = cls.__new__(cls)
         self.Lcell = Lcell
-        self._dev = {"nn": nn_t, "vel": vel_t, "rho": rho_t}
+        self._dev = {"nn": nn_t, "vel": vel_t, "rho": rho_t, "nn_pos": nn_pos_t, "spay": spay_t}
         self._host = {}
         self.Nsize = int(nn_t.shape[0])
         self.Lbox = self.Nsize * self.Lcell
@@ -196,6 +196,19 @@ class BoxField:
         """-> (list of float32 CUDA cubes to transform, multiplicity).  Field algebra interp.py:501-557."""
         torch = _lib._torch()
         strict = self.strict_reference
+        if self._dev is not None and self._dev.get("spay") is not None:
+            d = self._dev          # payload already in cell-sorted order: near-sequential reads
+            if quantity == "velocity":
+                f = _lib.fields_sorted(d["nn_pos"], d["spay"], want_v=True)
+                return [f["vx"], f["vy"], f["vz"]], 1.0
+            if quantity == "momentum":
+                if strict:
+                    f = _lib.fields_sorted(d["nn_pos"], d["spay"], want_v=False, want_p=(True, False, False))
+                    return [f["px"]], 3.0          # three identical components (interp.py:523-525)
+                f = _lib.fields_sorted(d["nn_pos"], d["spay"], want_v=False, want_p=(True, True, True))
+                return [f["px"], f["py"], f["pz"]], 1.0
+            f = _lib.fields_sorted(d["nn_pos"], d["spay"], want_v=False, want_e=True)
+            return [f["e"]], 1.0
         if self._dev is not None:
             d = self._dev
             lc3 = float(self.Lcell) ** 3
