@@ -183,6 +183,11 @@ __device__ __forceinline__ bool proven(const Best& b, double margin) {
 struct Lattice {
   const double *qx, *qy, *qz;  // node coordinates
   const int *cx, *cy, *cz;     // cell of each node coordinate (clamped)
+  // ring-1 tables, precomputed on the host: origin-relative f32 coordinates and, per axis, the distance from the
+  // node to the nearest face of its ring-1 cell block behind which unexamined particles may exist (rounded down,
+  // with the cell-assignment slack already taken off; +inf when the block reaches an open end of the grid)
+  const float *fx, *fy, *fz;
+  const float *mx, *my, *mz;
   int nx, ny, nz;
 };
 
@@ -199,48 +204,50 @@ __global__ void __launch_bounds__(256) k_search_ring1(const rec_t* __restrict__ 
                                                        Lattice L, float extent, int32_t* __restrict__ nn,
                                                        int32_t* __restrict__ nn_pos, uint32_t* __restrict__ list,
                                                        vp_nn_stats_dev* __restrict__ stats) {
-  const int64_t nnodes = int64_t(L.nx) * L.ny * L.nz;
-  int64_t node = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (node >= nnodes) return;
-  int k = int(node % L.nz);
-  int64_t t = node / L.nz;
-  int j = int(t % L.ny), i = int(t / L.ny);
-  const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
-  const float qx = float(qxd - g.ox), qy = float(qyd - g.oy), qz = float(qzd - g.oz);
-  const int cx = L.cx[i], cy = L.cy[j], cz = L.cz[k];
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
-  const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gy - 1);
+  // block = (z nodes, y rows); grid = (z chunks, y chunks, x)
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= L.nz || j >= L.ny) return;
+  const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
+  const float qx = __ldg(L.fx + i), qy = __ldg(L.fy + j), qz = __ldg(L.fz + k);
+  const int cx = __ldg(L.cx + i), cy = __ldg(L.cy + j), cz = __ldg(L.cz + k);
   const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
   float b1 = INFINITY, b2 = INFINITY;
   int bi = -1;
-  for (int X = x0; X <= x1; ++X)
-    for (int Y = y0; Y <= y1; ++Y) {
-      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
-      const uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
-      for (uint32_t p = s; p < e; ++p) {
-        const float4 r = __ldg(part + p);
-        const float dx = qx - r.x, dy = qy - r.y, dz = qz - r.z;
-        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const bool lt = d < b1;
-        b2 = fminf(b2, lt ? b1 : d);
-        bi = lt ? int(p) : bi;
-        b1 = lt ? d : b1;
-      }
+  // all row bounds first (independent loads), then nine short, non-unrolled candidate loops
+  uint32_t rs[9], re[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int X = cx - 1 + a, Y = cy - 1 + b;
+      const bool in = X >= 0 && X < g.gx && Y >= 0 && Y < g.gy;
+      const size_t row = in ? (size_t(X) * g.gy + Y) * g.gz : 0;
+      rs[a * 3 + b] = in ? __ldg(start + row + z0) : 0u;
+      re[a * 3 + b] = in ? __ldg(start + row + z1 + 1) : 0u;
     }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+#pragma unroll 1
+    for (uint32_t p = rs[r]; p < re[r]; ++p) {
+      const float4 q = __ldg(part + p);
+      const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
+      const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      const bool lt = d < b1;
+      b2 = fminf(b2, lt ? b1 : d);
+      bi = lt ? int(p) : bi;
+      b1 = lt ? d : b1;
+    }
+  }
   bool settled = false;
   if (bi >= 0) {
     const float rb = sqrtf(b2 < INFINITY ? b2 : b1);
     const float eps = 1.5e-7f * (extent + rb);
     const float tol = 8.f * rb * eps + 8.f * eps * eps + 1e-6f * rb * rb;   // >= err(b1) + err(b2)
     if (b2 - b1 > tol) {
-      const double m = fmin(axis_margin(qxd, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
-                            fmin(axis_margin(qyd, g.oy, g.hy, y0, y1, g.gy, false, false),
-                                 axis_margin(qzd, g.oz, g.hz, z0, z1, g.gz, false, false)));
-      if (m == INFINITY) settled = true;
-      else if (m > 0.0) {
-        const float mf = __double2float_rd(m * (1.0 - 1.0 / 1048576.0));
-        settled = b1 + tol < mf * mf;
-      }
+      const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
+      settled = (m == INFINITY) || (m > 0.f && b1 + tol < m * m);
     }
   }
   if (settled) {
@@ -475,8 +482,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   const int bits = vp_ceil_log2(ncells);
 
   // ---- lattice tables (host -> pinned -> device)
-  const size_t tab_doubles = size_t(nx) + ny + nz;
-  const size_t tab_bytes = vp_align256(tab_doubles * 8) + vp_align256(tab_doubles * 4);
+  const size_t nt = size_t(nx) + ny + nz;
+  const size_t off_c = vp_align256(nt * 8), off_f = off_c + vp_align256(nt * 4), off_m = off_f + vp_align256(nt * 4);
+  const size_t tab_bytes = off_m + vp_align256(nt * 4);
   if (ctx->pinned_cap < tab_bytes) {
     if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
     VP_CUDA(cudaMallocHost(&ctx->pinned_h, tab_bytes));
@@ -489,22 +497,44 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     ctx->small_cap = tab_bytes;
   }
   VP_CUDA(cudaStreamSynchronize(st));  // the pinned block may still be in flight from a previous call
-  double* hq = static_cast<double*>(ctx->pinned_h);
-  int* hc = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned_h) + vp_align256(tab_doubles * 8));
-  auto host_cell = [](double x, double o_, double ih, int gg) {
-    double f = (x - o_) * ih;
-    if (!(f > 0.0)) return 0;
-    if (f >= double(gg)) return gg - 1;
-    return int(f);
+  char* hb = static_cast<char*>(ctx->pinned_h);
+  double* hq = reinterpret_cast<double*>(hb);
+  int* hc = reinterpret_cast<int*>(hb + off_c);
+  float* hf = reinterpret_cast<float*>(hb + off_f);
+  float* hm = reinterpret_cast<float*>(hb + off_m);
+  auto fill_axis = [&](const double* q, int n, int at, double o_, double h_, double ih, int gg, bool closed_lo, bool closed_hi) {
+    for (int i = 0; i < n; ++i) {
+      double f = (q[i] - o_) * ih;
+      int c = !(f > 0.0) ? 0 : (f >= double(gg) ? gg - 1 : int(f));
+      hq[at + i] = q[i];
+      hc[at + i] = c;
+      hf[at + i] = float(q[i] - o_);
+      // same expression as the device axis_margin() for the ring-1 block [c-1, c+1]
+      const int c0 = c - 1 < 0 ? 0 : c - 1, c1 = c + 1 > gg - 1 ? gg - 1 : c + 1;
+      double m = INFINITY;
+      if (c0 > 0) m = fmin(m, q[i] - (o_ + double(c0) * h_));
+      else if (closed_lo) m = fmin(m, q[i] - o_);
+      if (c1 < gg - 1) m = fmin(m, (o_ + double(c1 + 1) * h_) - q[i]);
+      else if (closed_hi) m = fmin(m, (o_ + double(gg) * h_) - q[i]);
+      float mf = INFINITY;
+      if (m != INFINITY) {
+        double ms = m * (1.0 - 1.0 / 1048576.0);
+        mf = ms > 0.0 ? nextafterf(float(ms), -INFINITY) : 0.f;   // rounded down
+        if (!(mf > 0.f)) mf = 0.f;
+      }
+      hm[at + i] = mf;
+    }
   };
-  for (int i = 0; i < nx; ++i) { hq[i] = qx[i]; hc[i] = host_cell(qx[i], g.ox, g.ihx, gx); }
-  for (int i = 0; i < ny; ++i) { hq[nx + i] = qy[i]; hc[nx + i] = host_cell(qy[i], g.oy, g.ihy, gy); }
-  for (int i = 0; i < nz; ++i) { hq[nx + ny + i] = qz[i]; hc[nx + ny + i] = host_cell(qz[i], g.oz, g.ihz, gz); }
+  fill_axis(qx, nx, 0, g.ox, g.hx, g.ihx, gx, g.closed_xlo != 0, g.closed_xhi != 0);
+  fill_axis(qy, ny, nx, g.oy, g.hy, g.ihy, gy, false, false);
+  fill_axis(qz, nz, nx + ny, g.oz, g.hz, g.ihz, gz, false, false);
   VP_CUDA(cudaMemcpyAsync(ctx->small_d, ctx->pinned_h, tab_bytes, cudaMemcpyHostToDevice, st));
+  const char* db = reinterpret_cast<const char*>(ctx->small_d);
   Lattice L;
-  L.qx = ctx->small_d; L.qy = L.qx + nx; L.qz = L.qy + ny;
-  L.cx = reinterpret_cast<const int*>(reinterpret_cast<const char*>(ctx->small_d) + vp_align256(tab_doubles * 8));
-  L.cy = L.cx + nx; L.cz = L.cy + ny;
+  L.qx = reinterpret_cast<const double*>(db); L.qy = L.qx + nx; L.qz = L.qy + ny;
+  L.cx = reinterpret_cast<const int*>(db + off_c); L.cy = L.cx + nx; L.cz = L.cy + ny;
+  L.fx = reinterpret_cast<const float*>(db + off_f); L.fy = L.fx + nx; L.fz = L.fy + ny;
+  L.mx = reinterpret_cast<const float*>(db + off_m); L.my = L.mx + nx; L.mz = L.my + ny;
   L.nx = nx; L.ny = ny; L.nz = nz;
 
   // ---- scratch
@@ -566,7 +596,12 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     // sorted records read once + cell starts read once + one index written per node
     vp_stage stage(ctx, "k1e_search_ring1", st, 1, double(n) * sizeof(rec_t) + double(ncells) * 4.0 + double(nnodes) * 4.0);
     const float extent = float(fmax(fmax(g.gx * g.hx, g.gy * g.hy), g.gz * g.hz));
-    k_search_ring1<<<unsigned((nnodes + 255) / 256), 256, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, node_list, ctx->nn_stats_d);
+    // block = (z nodes, y rows), one x plane per blockIdx.z: no integer division in the kernel
+    int bx = nz >= 256 ? 256 : ((nz + 31) / 32) * 32;
+    int by = 256 / bx;
+    dim3 block(bx, by, 1), grid((nz + bx - 1) / bx, (ny + by - 1) / by, nx);
+    VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the ring-1 launch");
+    k_search_ring1<<<grid, block, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, node_list, ctx->nn_stats_d);
   }
   {
     vp_stage stage(ctx, "k1f_search_exact", st, 1);
