@@ -27,6 +27,15 @@ struct vp_pk_plan {
 
 namespace {
 
+// 8-byte asynchronous global -> shared copy (LDGSTS); each thread only ever reads back what it copied itself,
+// so its own wait_group is the only synchronisation the prefetch needs.
+__device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* gsrc) {
+  unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // ------------------------------------------------------------------ z pass: N reals -> N/2 packed complex
 template <int R2, int R3>
 __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const float2* __restrict__ tw_half,
@@ -65,7 +74,7 @@ __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const f
 
 // ------------------------------------------------------------------ y pass: lines strided by NZ, C columns per CTA
 template <int R2, int R3, int C>
-__global__ void __launch_bounds__(R2* R3* C) k_fft_y(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
+__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_y(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
   using F = LineFFT<R2, R3, C>;
   constexpr int L = F::L, T = F::T;
   extern __shared__ float2 sm[];
@@ -87,7 +96,12 @@ struct FieldSet {
   int n;
 };
 
-constexpr int kBinSlots = 4;  // bins per thread (nbins <= kBinSlots * blockDim)
+// Binning inside the x pass: the |F|^2 tile [C columns][L rows] sits in shared memory; rows kx and -kx are folded.
+// For a column the shell index is monotone in |kx|, so the rows of shell b form one contiguous segment
+// [r0(b), r0(b+1)).  Work item = (shell b, column c): lanes of a group of C consecutive threads take the C columns
+// of one shell, sum their segments, and reduce across the group with shuffles; the group leader keeps the running
+// f64 sum and the mode count of that shell in registers for the whole kernel.  No atomics until the final flush.
+constexpr int kMaxSlots = 8;  // shells per group leader
 
 // smallest row r in [0, nr] with  wrow[r] + zc >= thr  (nr = number of rows when none qualifies)
 __device__ __forceinline__ int first_row_at_or_above(const double* wrow, int nr, double zc, double thr, double base2,
@@ -103,30 +117,45 @@ __device__ __forceinline__ int first_row_at_or_above(const double* wrow, int nr,
   return r;
 }
 
-template <int R2, int R3, int C>
+template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
 __global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, const float2* __restrict__ tw,
                                                          const double* __restrict__ kk2, const double* __restrict__ thr_g,
                                                          int nbins, float inv_kf, float2* __restrict__ plane0,
                                                          double* __restrict__ psum_g, unsigned long long* __restrict__ cnt_g) {
   using F = LineFFT<R2, R3, C>;
   constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1;
+  constexpr int NG = NT / C;                                       // shell groups per sweep
   extern __shared__ float2 sm[];                                   // exchange area, later the |F|^2 tile
   float* pt = reinterpret_cast<float*>(sm);                        // [C][PP]
   double* wrow = reinterpret_cast<double*>(sm + XS);               // [NR]   kx^2 + ky^2
   double* kz2 = wrow + NR;                                         // [C]
   double* thr = kz2 + C;                                           // [nbins+1]
   static_assert(size_t(C) * PP * 4 <= size_t(XS) * 8, "P tile must fit in the exchange area");
+  static_assert(C <= 32 && (C & (C - 1)) == 0, "a shell group must sit inside one warp");
 
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
   const int tiles_z = NZ / C;
   const int ntiles = L * tiles_z;
   const size_t xstride = size_t(L) * NZ;
+  float2* pre = reinterpret_cast<float2*>(thr + nbins + 1 + ((nbins + 1) & 1));   // [16][NT] prefetch slots (thread private)
 
   for (int i = tid; i <= nbins; i += NT) thr[i] = thr_g[i];
-  double acc[kBinSlots];
-  unsigned long long cnt[kBinSlots];
+  double acc[SLOTS];
+  unsigned cnt[SLOTS];   // per-CTA mode counts stay far below 2^32 (<= tiles per CTA * 2*NR*C)
 #pragma unroll
-  for (int s = 0; s < kBinSlots; ++s) { acc[s] = 0.0; cnt[s] = 0ull; }
+  for (int s = 0; s < SLOTS; ++s) { acc[s] = 0.0; cnt[s] = 0u; }
+
+  // software pipeline over the sequence (tile, component): the next item's 16 strided elements are copied
+  // global -> shared with cp.async while the current item is transformed and binned
+  auto prefetch = [&](int tile, int comp) {
+    if (!PREFETCH) return;
+    const int ky = tile / tiles_z, zt = tile % tiles_z;
+    const float2* base = fs.f[comp] + size_t(ky) * NZ + zt * C + c;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cp_async8(pre + j * NT + tid, base + size_t(j * T + t) * xstride);
+    cp_async_commit();
+  };
+  if (int(blockIdx.x) < ntiles) prefetch(blockIdx.x, 0);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int ky = tile / tiles_z, zt = tile % tiles_z;
@@ -134,10 +163,18 @@ __global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, co
 #pragma unroll
     for (int j = 0; j < 16; ++j) p[j] = 0.f;
     for (int comp = 0; comp < fs.n; ++comp) {
-      const float2* base = fs.f[comp] + size_t(ky) * NZ + zt * C + c;
       float2 v[16];
+      if (PREFETCH) {
+        cp_async_wait_all();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+        for (int j = 0; j < 16; ++j) v[j] = pre[j * NT + tid];
+      } else {
+        const float2* base = fs.f[comp] + size_t(ky) * NZ + zt * C + c;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+      }
+      if (comp + 1 < fs.n) prefetch(tile, comp + 1);
+      else if (tile + int(gridDim.x) < ntiles) prefetch(tile + gridDim.x, 0);
       __syncthreads();  // previous user of the exchange area is done
       F::run(v, t, sm + c, tw);
       if (zt == 0 && c == 0) {
@@ -156,38 +193,44 @@ __global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, co
     if (tid < C) kz2[tid] = kk2[zt * C + tid];
     __syncthreads();
 
-    // every thread owns bins tid, tid+NT, ... and sums the rows of each column that fall into them
-    const int c0 = (zt == 0) ? 1 : 0;
+    const double zc = kz2[c];
+    const double smin = __dadd_rn(wrow[0], zc), smax = __dadd_rn(wrow[NR - 1], zc);
+    const bool col_on = !(zt == 0 && c == 0);     // the packed kz=0 column is binned by k_plane_bin
+    const float* col = pt + c * PP;
 #pragma unroll
-    for (int s = 0; s < kBinSlots; ++s) {
-      const int b = tid + s * NT;
-      if (b < nbins) {
+    for (int s = 0; s < SLOTS; ++s) {
+      const int b = t + s * NG;                   // shell of this group in sweep s (uniform across the group)
+      float a = 0.f;
+      unsigned n = 0;
+      if (b < nbins && col_on) {
         const double tlo = thr[b], thi = thr[b + 1];
-        float a = 0.f;
-        unsigned n = 0;
-        for (int cc = c0; cc < C; ++cc) {
-          const double zc = kz2[cc];
-          if (__dadd_rn(wrow[0], zc) >= thi || __dadd_rn(wrow[NR - 1], zc) < tlo) continue;
+        if (smin < thi && smax >= tlo) {
           const int r0 = first_row_at_or_above(wrow, NR, zc, tlo, ky2, inv_kf);
           const int r1 = first_row_at_or_above(wrow, NR, zc, thi, ky2, inv_kf);
-          const float* col = pt + cc * PP;
           for (int r = r0; r < r1; ++r) {
             float q = col[r];
             if (r > 0 && r < L / 2) { q += col[L - r]; n += 2; } else n += 1;
             a += q;
           }
         }
-        acc[s] += double(a);
-        cnt[s] += n;
       }
+#pragma unroll
+      for (int o = C / 2; o; o >>= 1) {            // all lanes take part (full-warp shuffles)
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+      }
+      acc[s] += double(a);
+      cnt[s] += n;
     }
   }
+  if (c == 0) {
 #pragma unroll
-  for (int s = 0; s < kBinSlots; ++s) {
-    const int b = tid + s * NT;
-    if (b < nbins && cnt[s]) {
-      atomicAdd(psum_g + b, 2.0 * acc[s]);   // Hermitian partner of every kz in [1, N/2-1]
-      atomicAdd(cnt_g + b, 2ull * cnt[s]);
+    for (int s = 0; s < SLOTS; ++s) {
+      const int b = t + s * NG;
+      if (b < nbins && cnt[s]) {
+        atomicAdd(psum_g + b, 2.0 * acc[s]);   // Hermitian partner of every kz in [1, N/2-1]
+        atomicAdd(cnt_g + b, 2ull * (unsigned long long)cnt[s]);
+      }
     }
   }
 }
@@ -342,24 +385,44 @@ int launch_y(float2* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
   return VP_OK;
 }
 
-template <int R2, int R3, int C>
-int launch_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
+int launch_x_bin_sp(FieldSet fs, int N, const vp_pk_plan* pl, size_t smem, double* psum, unsigned long long* cnt, cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
   constexpr int NT = F::T * C;
-  VP_REQUIRE(pl->nbins <= kBinSlots * NT, "vp_pk_fields: nbins=%d exceeds %d for N=%d", pl->nbins, kBinSlots * NT, N);
-  size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2) + (size_t(F::L / 2 + 1) + C + pl->nbins + 1) * sizeof(double);
-  VP_CUDA(cudaFuncSetAttribute(k_fft_x_bin<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  auto kern = k_fft_x_bin<R2, R3, C, SLOTS, PREFETCH>;
+  VP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int occ = 1;
-  VP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fft_x_bin<R2, R3, C>, NT, smem));
+  VP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
   if (occ < 1) occ = 1;
   const int NZ = N / 2;
   int ntiles = N * (NZ / C);
   int grid = pl->ctx->sm_count * occ;
   if (grid > ntiles) grid = ntiles;
   vp_stage stage(pl->ctx, "k4c_fft_x_bin", st, 1, 4.0 * double(N) * N * N * fs.n);   // 8 B/mode read, nothing written
-  k_fft_x_bin<R2, R3, C><<<grid, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->kk2, pl->thr, pl->nbins, pl->inv_kf, pl->plane0, psum, cnt);
+  kern<<<grid, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->kk2, pl->thr, pl->nbins, pl->inv_kf, pl->plane0, psum, cnt);
   VP_CHECK_LAUNCH();
   return VP_OK;
+}
+
+template <int R2, int R3, int C, int SLOTS>
+int launch_x_bin_s(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+  using F = LineFFT<R2, R3, C>;
+  constexpr int NT = F::T * C;
+  const size_t base = size_t(xsize<F::L, C>()) * sizeof(float2) +
+                      (size_t(F::L / 2 + 1) + C + pl->nbins + 1 + ((pl->nbins + 1) & 1)) * sizeof(double);
+  const size_t pre = size_t(16) * NT * sizeof(float2);
+  if (base + pre <= size_t(200) * 1024) return launch_x_bin_sp<R2, R3, C, SLOTS, true>(fs, N, pl, base + pre, psum, cnt, st);
+  return launch_x_bin_sp<R2, R3, C, SLOTS, false>(fs, N, pl, base, psum, cnt, st);
+}
+
+template <int R2, int R3, int C>
+int launch_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+  using F = LineFFT<R2, R3, C>;
+  constexpr int NG = F::T;   // shell groups per sweep
+  const int need = (pl->nbins + NG - 1) / NG;
+  VP_REQUIRE(need <= 4 * kMaxSlots, "vp_pk_fields: nbins=%d exceeds %d for N=%d", pl->nbins, 4 * kMaxSlots * NG, N);
+  if (need <= kMaxSlots) return launch_x_bin_s<R2, R3, C, kMaxSlots>(fs, N, pl, psum, cnt, st);
+  return launch_x_bin_s<R2, R3, C, 4 * kMaxSlots>(fs, N, pl, psum, cnt, st);
 }
 
 int run_z(float* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
@@ -402,7 +465,7 @@ int run_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned l
 // the x pass without binning (diagnostic transform): reuse the y kernel on a transposed view is not possible
 // in place, so the diagnostic transform runs the x lines with the generic strided kernel below.
 template <int R2, int R3, int C>
-__global__ void __launch_bounds__(R2* R3* C) k_fft_x(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
+__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_x(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
   using F = LineFFT<R2, R3, C>;
   constexpr int L = F::L, T = F::T;
   extern __shared__ float2 sm[];

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t* __restrict__ 
 }
 
 // (3) stable scatter
-__global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+__global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                        uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                        int64_t n, int shift, const uint32_t* __restrict__ hist,
                                                        int nblocks) {
@@ -140,7 +140,14 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict
     int li = wbase + r * 32 + lane;
     bool ok = li < count;
     uint32_t d = ok ? ((key[r] >> shift) & 0xff) : 256u;
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    // lanes holding the same digit: eight ballots, one per digit bit (MATCH.ANY serialises over distinct values)
+    uint32_t peers = __ballot_sync(0xffffffffu, ok);
+    if (!ok) peers = ~peers;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+      const uint32_t m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
+      peers &= ((d >> bit) & 1u) ? m : ~m;
+    }
     int leader = __ffs(peers) - 1;
     uint32_t before = __popc(peers & ((1u << lane) - 1u));
     uint32_t old = 0;
