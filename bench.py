@@ -188,7 +188,13 @@ def main():
     pos, vel, rho = synth_on_device(torch, Np, seed=3)
     torch.cuda.synchronize()
 
+    if world > 1:
+        from vpower import dist as vd
+        backend = vd.CudaBackend(N, k, edges, world, rank)
+
     def step_dev():
+        if world > 1:      # x-slab gridding, slab FFT with one all-to-all per field, all-reduce of the shells
+            return vd.particles_to_pk_dist(pos, vel, rho, ax, lc3, norm, k, edges, quantities=quantities, backend=backend)
         return _lib.particles_to_pk(pos, vel, rho, ax, ax, ax, N, lc3, norm, k, edges, quantities=quantities)
 
     def barrier():
@@ -240,7 +246,7 @@ def main():
 
     # end to end through the host-buffer C ABI: pinned host arrays in, spectra out
     e2e = None
-    if not args.no_e2e and rank == 0:
+    if not args.no_e2e and rank == 0 and world == 1:
         try:
             hp = torch.empty(pos.shape, dtype=pos.dtype, pin_memory=True).copy_(pos)
             hv = torch.empty(vel.shape, dtype=vel.dtype, pin_memory=True).copy_(vel)

@@ -156,6 +156,20 @@ int vp_pk_plan_destroy(vp_pk_plan* plan);
 int vp_pk_fields(vp_pk_plan* plan, float* const* field_d, int ncomp, double* psum_d, uint64_t* nsample_d,
                  void* stream);
 
+/* Slab decomposition over `nranks` processes (one per GPU).  Before the exchange rank r owns the x planes
+ * [r*N/nranks, (r+1)*N/nranks) of every real field; after it, the half-spectrum columns kz in
+ * [r*kzc, (r+1)*kzc), kzc = N/2/nranks, for ALL x and ky.  The exchange itself (an all-to-all with equal blocks)
+ * is the caller's: torch.distributed / NCCL in the Python mirror (vpower/dist.py).
+ *   vp_pk_dist_local : z pass in place on field_d[c] ([N/nranks][N][N] f32), then the y pass, whose store is the
+ *                      transpose packing: send_d[c] is [nranks][N/nranks][N][kzc] complex64, block d goes to rank d.
+ *   vp_pk_dist_final : recv_d[c] is [N][N][kzc] complex64 (= the received blocks in rank order); x pass fused with
+ *                      |F|^2 and shell binning -> this rank's PARTIAL psum_d/nsample_d, to be summed over ranks.
+ * Replaces the reference's folded DFT across MPI ranks (scripts/parallel_optimized.py:362-389, 455-456). */
+int vp_pk_plan_create_dist(vp_ctx* ctx, int N, int nranks, int rank, const double* k_h, const double* edges_h, int nbins,
+                           vp_pk_plan** out);
+int vp_pk_dist_local(vp_pk_plan* plan, float* const* field_d, int ncomp, float* const* send_d, void* stream);
+int vp_pk_dist_final(vp_pk_plan* plan, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream);
+
 /* Test/diagnostic entry points */
 /* In-place 3-D r2c transform only.  Output layout: [N][N][N/2] complex64 where entry (x,y,0) packs
  * (Re F(x,y,0), Re F_zNyquist-line ...) -- see DESIGN.md "half-spectrum layout"; use

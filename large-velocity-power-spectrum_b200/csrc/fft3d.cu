@@ -23,6 +23,10 @@ struct vp_pk_plan {
   double* thr = nullptr;      // nbins+1 thresholds on the squared magnitude
   float2* plane0 = nullptr;   // [3][N][N] x-pass output of the kz=0 column
   float inv_kf = 0.f;
+  // slab decomposition (one process per GPU): this rank owns x planes [rank*N/nranks, ...) before the exchange
+  // and half-spectrum columns kz in [rank*kzc, (rank+1)*kzc) after it
+  int nranks = 1, rank = 0;
+  int kzc = 0;                // N/2/nranks
 };
 
 namespace {
@@ -73,21 +77,26 @@ __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const f
 }
 
 // ------------------------------------------------------------------ y pass: lines strided by NZ, C columns per CTA
+// `out` may be the input itself (single GPU, in place) or the all-to-all send buffer laid out
+// [dest rank][x_local][ky][kzc]: the transpose packing is fused into the store of this pass.
 template <int R2, int R3, int C>
-__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_y(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
+__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_y(const float2* __restrict__ data, float2* __restrict__ out,
+                                                                                   int nx, int NZ, int kzc, const float2* __restrict__ tw) {
   using F = LineFFT<R2, R3, C>;
   constexpr int L = F::L, T = F::T;
   extern __shared__ float2 sm[];
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
   const int tiles = NZ / C;
   const int x = blockIdx.x / tiles, zt = blockIdx.x % tiles;
-  float2* base = data + size_t(x) * L * NZ + zt * C + c;
+  const float2* base = data + size_t(x) * L * NZ + zt * C + c;
   float2 v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * NZ];
   F::run(v, t, sm + c, tw);
+  const int kz0 = zt * C, d = kz0 / kzc;
+  float2* ob = out + (size_t(d) * nx + x) * L * kzc + (kz0 - d * kzc) + c;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) base[size_t(F::kout(j, t)) * NZ] = v[j];
+  for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * kzc] = v[j];
 }
 
 // ------------------------------------------------------------------ x pass fused with |F|^2 and shell binning
@@ -120,7 +129,7 @@ __device__ __forceinline__ int first_row_at_or_above(const double* wrow, int nr,
 template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
 __global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, const float2* __restrict__ tw,
                                                          const double* __restrict__ kk2, const double* __restrict__ thr_g,
-                                                         int nbins, float inv_kf, float2* __restrict__ plane0,
+                                                         int nbins, float inv_kf, float2* __restrict__ plane0, int kz_offset,
                                                          double* __restrict__ psum_g, unsigned long long* __restrict__ cnt_g) {
   using F = LineFFT<R2, R3, C>;
   constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1;
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, co
       else if (tile + int(gridDim.x) < ntiles) prefetch(tile + gridDim.x, 0);
       __syncthreads();  // previous user of the exchange area is done
       F::run(v, t, sm + c, tw);
-      if (zt == 0 && c == 0) {
+      if (kz_offset + zt * C + c == 0) {
         float2* pl = plane0 + (size_t(comp) * L + ky) * L;
 #pragma unroll
         for (int j = 0; j < 16; ++j) pl[F::kout(j, t)] = v[j];
@@ -190,12 +199,12 @@ __global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, co
     for (int j = 0; j < 16; ++j) pt[c * PP + F::kout(j, t)] = p[j];
     const double ky2 = kk2[ky];
     for (int r = tid; r < NR; r += NT) wrow[r] = __dadd_rn(kk2[r], ky2);
-    if (tid < C) kz2[tid] = kk2[zt * C + tid];
+    if (tid < C) kz2[tid] = kk2[kz_offset + zt * C + tid];
     __syncthreads();
 
     const double zc = kz2[c];
     const double smin = __dadd_rn(wrow[0], zc), smax = __dadd_rn(wrow[NR - 1], zc);
-    const bool col_on = !(zt == 0 && c == 0);     // the packed kz=0 column is binned by k_plane_bin
+    const bool col_on = (kz_offset + zt * C + c) != 0;   // the packed kz=0 column is binned by k_plane_bin
     const float* col = pt + c * PP;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
@@ -359,34 +368,37 @@ __global__ void k_expand_power(const float2* __restrict__ packed, int N, double*
 
 // ------------------------------------------------------------------ launch helpers
 template <int R2, int R3>
-int launch_z(float* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
+int launch_z(float* data, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
   using F = LineFFT<R2, R3, 1>;
   constexpr int LINES = 256 / F::T;
+  VP_REQUIRE((size_t(nx) * N) % LINES == 0, "fft z pass: %d x %d lines is not a multiple of %d", nx, N, LINES);
   size_t smem = size_t(LINES) * xsize<F::L, 1>() * sizeof(float2);
   static bool attr = false;
   if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_z<R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
-  size_t nlines = size_t(N) * N;
-  vp_stage stage(pl->ctx, "k4a_fft_z", st, 1, 8.0 * double(N) * N * N);   // 4 B/real read + 4 B/real written in place
+  size_t nlines = size_t(nx) * N;
+  vp_stage stage(pl->ctx, "k4a_fft_z", st, 1, 8.0 * double(nx) * N * N);   // 4 B/real read + 4 B/real written in place
   k_fft_z<R2, R3><<<unsigned(nlines / LINES), 256, smem, st>>>(data, pl->tw_half, pl->tw_full);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
 
 template <int R2, int R3, int C>
-int launch_y(float2* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
+int launch_y(const float2* data, float2* out, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
   size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2);
   static bool attr = false;
   if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_y<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
   const int NZ = N / 2;
-  vp_stage stage(pl->ctx, "k4b_fft_y", st, 1, 8.0 * double(N) * N * N);   // 8 B/mode read + written, N^3/2 modes
-  k_fft_y<R2, R3, C><<<unsigned(N * (NZ / C)), F::T * C, smem, st>>>(data, NZ, pl->tw_full);
+  VP_REQUIRE(kzc % C == 0, "fft y pass: %d columns per rank is not a multiple of the tile width %d", kzc, C);
+  vp_stage stage(pl->ctx, "k4b_fft_y", st, 1, 8.0 * double(nx) * N * N);   // 8 B/mode read + written, nx*N*N/2 modes
+  k_fft_y<R2, R3, C><<<unsigned(nx * (NZ / C)), F::T * C, smem, st>>>(data, out, nx, NZ, kzc, pl->tw_full);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
 
 template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
-int launch_x_bin_sp(FieldSet fs, int N, const vp_pk_plan* pl, size_t smem, double* psum, unsigned long long* cnt, cudaStream_t st) {
+int launch_x_bin_sp(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, size_t smem, double* psum, unsigned long long* cnt,
+                    cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
   constexpr int NT = F::T * C;
   auto kern = k_fft_x_bin<R2, R3, C, SLOTS, PREFETCH>;
@@ -394,69 +406,69 @@ int launch_x_bin_sp(FieldSet fs, int N, const vp_pk_plan* pl, size_t smem, doubl
   int occ = 1;
   VP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
   if (occ < 1) occ = 1;
-  const int NZ = N / 2;
+  VP_REQUIRE(NZ % C == 0, "fft x pass: %d columns is not a multiple of the tile width %d", NZ, C);
   int ntiles = N * (NZ / C);
   int grid = pl->ctx->sm_count * occ;
   if (grid > ntiles) grid = ntiles;
-  vp_stage stage(pl->ctx, "k4c_fft_x_bin", st, 1, 4.0 * double(N) * N * N * fs.n);   // 8 B/mode read, nothing written
-  kern<<<grid, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->kk2, pl->thr, pl->nbins, pl->inv_kf, pl->plane0, psum, cnt);
+  vp_stage stage(pl->ctx, "k4c_fft_x_bin", st, 1, 8.0 * double(N) * N * NZ * fs.n);   // 8 B/mode read, nothing written
+  kern<<<grid, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->kk2, pl->thr, pl->nbins, pl->inv_kf, pl->plane0, kz_offset, psum, cnt);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
 
 template <int R2, int R3, int C, int SLOTS>
-int launch_x_bin_s(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+int launch_x_bin_s(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
   constexpr int NT = F::T * C;
   const size_t base = size_t(xsize<F::L, C>()) * sizeof(float2) +
                       (size_t(F::L / 2 + 1) + C + pl->nbins + 1 + ((pl->nbins + 1) & 1)) * sizeof(double);
   const size_t pre = size_t(16) * NT * sizeof(float2);
-  if (base + pre <= size_t(200) * 1024) return launch_x_bin_sp<R2, R3, C, SLOTS, true>(fs, N, pl, base + pre, psum, cnt, st);
-  return launch_x_bin_sp<R2, R3, C, SLOTS, false>(fs, N, pl, base, psum, cnt, st);
+  if (base + pre <= size_t(200) * 1024) return launch_x_bin_sp<R2, R3, C, SLOTS, true>(fs, N, NZ, kz_offset, pl, base + pre, psum, cnt, st);
+  return launch_x_bin_sp<R2, R3, C, SLOTS, false>(fs, N, NZ, kz_offset, pl, base, psum, cnt, st);
 }
 
 template <int R2, int R3, int C>
-int launch_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+int launch_x_bin(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
   constexpr int NG = F::T;   // shell groups per sweep
   const int need = (pl->nbins + NG - 1) / NG;
   VP_REQUIRE(need <= 4 * kMaxSlots, "vp_pk_fields: nbins=%d exceeds %d for N=%d", pl->nbins, 4 * kMaxSlots * NG, N);
-  if (need <= kMaxSlots) return launch_x_bin_s<R2, R3, C, kMaxSlots>(fs, N, pl, psum, cnt, st);
-  return launch_x_bin_s<R2, R3, C, 4 * kMaxSlots>(fs, N, pl, psum, cnt, st);
+  if (need <= kMaxSlots) return launch_x_bin_s<R2, R3, C, kMaxSlots>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+  return launch_x_bin_s<R2, R3, C, 4 * kMaxSlots>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
 }
 
-int run_z(float* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
+int run_z(float* d, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_z<2, 1>(d, N, pl, st);
-    case 128: return launch_z<4, 1>(d, N, pl, st);
-    case 256: return launch_z<8, 1>(d, N, pl, st);
-    case 512: return launch_z<16, 1>(d, N, pl, st);
-    case 1024: return launch_z<16, 2>(d, N, pl, st);
-    case 2048: return launch_z<16, 4>(d, N, pl, st);
+    case 64: return launch_z<2, 1>(d, N, nx, pl, st);
+    case 128: return launch_z<4, 1>(d, N, nx, pl, st);
+    case 256: return launch_z<8, 1>(d, N, nx, pl, st);
+    case 512: return launch_z<16, 1>(d, N, nx, pl, st);
+    case 1024: return launch_z<16, 2>(d, N, nx, pl, st);
+    case 2048: return launch_z<16, 4>(d, N, nx, pl, st);
   }
   vp_set_error("fft z pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
 }
-int run_y(float2* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
+int run_y(const float2* d, float2* out, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_y<4, 1, 32>(d, N, pl, st);
-    case 128: return launch_y<8, 1, 32>(d, N, pl, st);
-    case 256: return launch_y<16, 1, 16>(d, N, pl, st);
-    case 512: return launch_y<16, 2, 8>(d, N, pl, st);
-    case 1024: return launch_y<16, 4, 8>(d, N, pl, st);
-    case 2048: return launch_y<16, 8, 8>(d, N, pl, st);
+    case 64: return launch_y<4, 1, 32>(d, out, N, nx, kzc, pl, st);
+    case 128: return launch_y<8, 1, 32>(d, out, N, nx, kzc, pl, st);
+    case 256: return launch_y<16, 1, 16>(d, out, N, nx, kzc, pl, st);
+    case 512: return launch_y<16, 2, 8>(d, out, N, nx, kzc, pl, st);
+    case 1024: return launch_y<16, 4, 8>(d, out, N, nx, kzc, pl, st);
+    case 2048: return launch_y<16, 8, 8>(d, out, N, nx, kzc, pl, st);
   }
   vp_set_error("fft y pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
 }
-int run_x_bin(FieldSet fs, int N, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+int run_x_bin(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_x_bin<4, 1, 32>(fs, N, pl, psum, cnt, st);
-    case 128: return launch_x_bin<8, 1, 32>(fs, N, pl, psum, cnt, st);
-    case 256: return launch_x_bin<16, 1, 16>(fs, N, pl, psum, cnt, st);
-    case 512: return launch_x_bin<16, 2, 8>(fs, N, pl, psum, cnt, st);
-    case 1024: return launch_x_bin<16, 4, 8>(fs, N, pl, psum, cnt, st);
-    case 2048: return launch_x_bin<16, 8, 8>(fs, N, pl, psum, cnt, st);
+    case 64: return launch_x_bin<4, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 128: return launch_x_bin<8, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 256: return launch_x_bin<16, 1, 16>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 512: return launch_x_bin<16, 2, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 1024: return launch_x_bin<16, 4, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 2048: return launch_x_bin<16, 8, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
   }
   vp_set_error("fft x pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
@@ -623,6 +635,7 @@ static int pk_fields_generic(vp_pk_plan* pl, float* const* field_d, int ncomp, d
 extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && field_d && psum_d && nsample_d, "vp_pk_fields: null argument");
   VP_REQUIRE(ncomp >= 1 && ncomp <= 3, "vp_pk_fields: ncomp must be 1..3");
+  VP_REQUIRE(pl->nranks == 1, "vp_pk_fields: plan is distributed over %d ranks; use vp_pk_dist_local/final", pl->nranks);
   VP_CUDA(cudaSetDevice(pl->ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!pl->pow2) return pk_fields_generic(pl, field_d, ncomp, psum_d, nsample_d, st);
@@ -634,11 +647,11 @@ extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, do
   for (int c = 0; c < 3; ++c) fs.f[c] = nullptr;
   for (int c = 0; c < ncomp; ++c) {
     VP_REQUIRE(field_d[c], "vp_pk_fields: null field %d", c);
-    VP_TRY(run_z(field_d[c], N, pl, st));
-    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), N, pl, st));
+    VP_TRY(run_z(field_d[c], N, N, pl, st));
+    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), reinterpret_cast<float2*>(field_d[c]), N, N, N / 2, pl, st));
     fs.f[c] = reinterpret_cast<float2*>(field_d[c]);
   }
-  VP_TRY(run_x_bin(fs, N, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
+  VP_TRY(run_x_bin(fs, N, N / 2, 0, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
   vp_stage stage(pl->ctx, "k5_plane_bin", st, 1, 8.0 * double(N) * N * ncomp);
   k_plane_bin<<<unsigned((size_t(N) * N + 255) / 256), 256, 0, st>>>(pl->plane0, ncomp, N, pl->kk2, pl->thr, pl->nbins, psum_d,
                                                                   reinterpret_cast<unsigned long long*>(nsample_d));
@@ -646,12 +659,67 @@ extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, do
   return VP_OK;
 }
 
+extern "C" int vp_pk_plan_create_dist(vp_ctx* ctx, int N, int nranks, int rank, const double* k_h, const double* edges_h, int nbins,
+                                      vp_pk_plan** out) {
+  VP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "vp_pk_plan_create_dist: bad rank %d of %d", rank, nranks);
+  VP_TRY(vp_pk_plan_create(ctx, N, k_h, edges_h, nbins, out));
+  vp_pk_plan* p = *out;
+  if (nranks > 1) {
+    bool ok = p->pow2 && (N % nranks == 0) && ((N / 2) % nranks == 0);
+    if (!ok) {
+      vp_pk_plan_destroy(p);
+      *out = nullptr;
+      vp_set_error("vp_pk_plan_create_dist: N=%d over %d ranks needs the power-of-two path and N/2 divisible by the rank count", N, nranks);
+      return VP_ERR_UNSUPPORTED;
+    }
+  }
+  p->nranks = nranks;
+  p->rank = rank;
+  p->kzc = (N / 2) / nranks;
+  return VP_OK;
+}
+
+extern "C" int vp_pk_dist_local(vp_pk_plan* pl, float* const* field_d, int ncomp, float* const* send_d, void* stream) {
+  VP_REQUIRE(pl && field_d && send_d && ncomp >= 1 && ncomp <= 3, "vp_pk_dist_local: bad argument");
+  VP_REQUIRE(pl->pow2, "vp_pk_dist_local: N=%d has no slab path", pl->N);
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = pl->N, nx = N / pl->nranks;
+  for (int c = 0; c < ncomp; ++c) {
+    VP_REQUIRE(field_d[c] && send_d[c], "vp_pk_dist_local: null buffer %d", c);
+    VP_TRY(run_z(field_d[c], N, nx, pl, st));
+    VP_TRY(run_y(reinterpret_cast<const float2*>(field_d[c]), reinterpret_cast<float2*>(send_d[c]), N, nx, pl->kzc, pl, st));
+  }
+  return VP_OK;
+}
+
+extern "C" int vp_pk_dist_final(vp_pk_plan* pl, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
+  VP_REQUIRE(pl && recv_d && psum_d && nsample_d && ncomp >= 1 && ncomp <= 3, "vp_pk_dist_final: bad argument");
+  VP_REQUIRE(pl->pow2, "vp_pk_dist_final: N=%d has no slab path", pl->N);
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = pl->N;
+  VP_CUDA(cudaMemsetAsync(psum_d, 0, sizeof(double) * pl->nbins, st));
+  VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
+  FieldSet fs;
+  fs.n = ncomp;
+  for (int c = 0; c < 3; ++c) fs.f[c] = c < ncomp ? reinterpret_cast<float2*>(recv_d[c]) : nullptr;
+  VP_TRY(run_x_bin(fs, N, pl->kzc, pl->rank * pl->kzc, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
+  if (pl->rank == 0) {   // the packed kz=0 column (planes kz=0 and kz=N/2) lives on rank 0
+    vp_stage stage(pl->ctx, "k5_plane_bin", st, 1, 8.0 * double(N) * N * ncomp);
+    k_plane_bin<<<unsigned((size_t(N) * N + 255) / 256), 256, 0, st>>>(pl->plane0, ncomp, N, pl->kk2, pl->thr, pl->nbins, psum_d,
+                                                                    reinterpret_cast<unsigned long long*>(nsample_d));
+    VP_CHECK_LAUNCH();
+  }
+  return VP_OK;
+}
+
 extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) {
   VP_REQUIRE(pl && field_d, "vp_fft_r2c_inplace: null argument");
   if (!pl->pow2) { vp_set_error("vp_fft_r2c_inplace: N=%d has no packed fast path", pl->N); return VP_ERR_UNSUPPORTED; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VP_TRY(run_z(field_d, pl->N, pl, st));
-  VP_TRY(run_y(reinterpret_cast<float2*>(field_d), pl->N, pl, st));
+  VP_TRY(run_z(field_d, pl->N, pl->N, pl, st));
+  VP_TRY(run_y(reinterpret_cast<float2*>(field_d), reinterpret_cast<float2*>(field_d), pl->N, pl->N, pl->N / 2, pl, st));
   return run_x(reinterpret_cast<float2*>(field_d), pl->N, pl, st);
 }
 

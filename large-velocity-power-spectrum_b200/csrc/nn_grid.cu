@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, 
     x = pos[3 * i];
     y = pos[3 * i + 1];
     z = pos[3 * i + 2];
-    if (g.use_keep && !(x >= g.keep_lo && x <= g.keep_hi)) ok = false;
+    // slab filter: a particle beyond a CLOSED face is dropped; beyond an open (domain-edge) face it is kept and clamped
+    if (g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi)))) ok = false;
   }
   uint32_t key = 0;
   if (ok) {
@@ -417,14 +418,23 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
     if (o.use_x_keep) {
       // the x extent is the kept range; keep the same cell size as along y
       AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false);
-      int g = int((o.x_keep_hi - o.x_keep_lo) / ay.h + 0.999);
+      AxisPlan a0 = plan_axis(qx, nx, nx, 0, 0, false);
+      double lo = o.x_lo_is_domain_edge ? a0.o : o.x_keep_lo;
+      double hi = o.x_hi_is_domain_edge ? a0.o + a0.h * nx : o.x_keep_hi;
+      int g = int((hi - lo) / ay.h + 0.999);
       gx = g < 1 ? 1 : g;
     }
   }
   while (double(gx) * gy * gz >= 4294967295.0) {  // 32-bit keys
     gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
   }
-  AxisPlan ax = plan_axis(qx, nx, gx, o.x_keep_lo, o.x_keep_hi, o.use_x_keep != 0);
+  // x extent of the cell list: the kept range on closed sides, the lattice extent on open (domain-edge) sides
+  AxisPlan ax = plan_axis(qx, nx, gx, 0, 0, false);
+  if (o.use_x_keep) {
+    double lo = o.x_lo_is_domain_edge ? ax.o : o.x_keep_lo;
+    double hi = o.x_hi_is_domain_edge ? ax.o + ax.h * gx : o.x_keep_hi;
+    ax = plan_axis(qx, nx, gx, lo, hi, true);
+  }
   AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false);
   AxisPlan az = plan_axis(qz, nz, gz, 0, 0, false);
   Grid g;

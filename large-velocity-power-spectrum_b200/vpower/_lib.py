@@ -51,6 +51,9 @@ SIGNATURES = {
     "vp_deposit_ngp": (_I, [_P, _P, _I, _L, _P, _I, _I, _D, _P, _P]),
     "vp_pk_plan_create": (_I, [_P, _I, _dp, _dp, _I, C.POINTER(_P)]),
     "vp_pk_plan_destroy": (_I, [_P]),
+    "vp_pk_plan_create_dist": (_I, [_P, _I, _I, _I, _dp, _dp, _I, C.POINTER(_P)]),
+    "vp_pk_dist_local": (_I, [_P, C.POINTER(_P), _I, C.POINTER(_P), _P]),
+    "vp_pk_dist_final": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
     "vp_pk_fields": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
     "vp_fft_r2c_inplace": (_I, [_P, _P, _P]),
     "vp_fft_unpack_half": (_I, [_P, _P, _P, _P]),
@@ -268,14 +271,36 @@ def deposit_ngp(pos_t, w_t, N, Lbox):
 class PkPlan:
     """Geometry of one transform+binning: N, k axis table (2 pi fftfreq), bin edges."""
 
-    def __init__(self, N, k_axis, edges):
+    def __init__(self, N, k_axis, edges, nranks=1, rank=0):
         self.N = int(N)
         self.k_axis, kp = _as_dp(k_axis)
         self.edges, ep = _as_dp(edges)
         self.nbins = len(self.edges) - 1
+        self.nranks, self.rank = int(nranks), int(rank)
         assert len(self.k_axis) == self.N
         self._h = _P()
-        _check(load_library().vp_pk_plan_create(ctx(), self.N, kp, ep, self.nbins, C.byref(self._h)))
+        _check(load_library().vp_pk_plan_create_dist(ctx(), self.N, self.nranks, self.rank, kp, ep, self.nbins,
+                                                     C.byref(self._h)))
+
+    def dist_local(self, slabs):
+        """slabs: 1..3 float32 CUDA tensors [N/nranks, N, N] (overwritten) -> list of send buffers
+        [nranks, N/nranks, N, N/2/nranks] complex64 (block d goes to rank d)."""
+        torch = _torch()
+        nx, kzc = self.N // self.nranks, self.N // 2 // self.nranks
+        send = [torch.empty((self.nranks, nx, self.N, kzc), dtype=torch.complex64, device=slabs[0].device) for _ in slabs]
+        fp = (_P * len(slabs))(*[s.data_ptr() for s in slabs])
+        sp = (_P * len(slabs))(*[s.data_ptr() for s in send])
+        _check(load_library().vp_pk_dist_local(self._h, fp, len(slabs), sp, stream_ptr()))
+        return send
+
+    def dist_final(self, recv):
+        """recv: 1..3 complex64 CUDA tensors [N, N, N/2/nranks] -> partial (psum, nsample) CUDA tensors."""
+        torch = _torch()
+        rp = (_P * len(recv))(*[r.data_ptr() for r in recv])
+        psum = torch.empty(self.nbins, dtype=torch.float64, device=recv[0].device)
+        ns = torch.empty(self.nbins, dtype=torch.int64, device=recv[0].device)
+        _check(load_library().vp_pk_dist_final(self._h, rp, len(recv), _P(psum.data_ptr()), _P(ns.data_ptr()), stream_ptr()))
+        return psum, ns
 
     def __del__(self):
         try:

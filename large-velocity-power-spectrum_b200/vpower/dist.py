@@ -1,0 +1,133 @@
+"""Multi-GPU particles -> P(k): x-slab decomposition, one process per GPU (torch.distributed, NCCL).
+
+What is distributed, and how:
+  * the lattice is cut into x slabs; rank r grids the nodes of planes [r*N/P, (r+1)*N/P) from the particles inside
+    that slab plus a halo (exact: nodes the halo cannot prove are reported and the halo is widened);
+  * every real field is transformed along z and y locally; the store of the y pass is the transpose packing; ONE
+    all-to-all per field component moves 8*N^2*(N/2)/P^2 bytes between each pair of ranks; the x pass, |F|^2 and the
+    shell binning then run on kz slabs;
+  * the per-rank shell sums / counts are summed with one all-reduce.
+The reference instead replicates the particles and the search index on every MPI rank and builds each rank's
+residue class of k-space by an O(N^3 m^3) phase sum (scripts/parallel_optimized.py:228-236, 362-389, 455-456).
+
+The compute steps go through a small backend object so that the wiring (slab bounds, exchange layout, reductions)
+can be exercised on CPU with the gloo backend (tests/test_dist_cpu.py); `CudaBackend` is the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def slab_bounds(N, nranks, rank):
+    """x planes [x0, x1) and half-spectrum columns [z0, z1) owned by `rank`."""
+    if N % nranks or (N // 2) % nranks:
+        raise ValueError(f"N={N} is not divisible into {nranks} slabs")
+    nx, kzc = N // nranks, N // 2 // nranks
+    return rank * nx, (rank + 1) * nx, rank * kzc, (rank + 1) * kzc
+
+
+def keep_range(ax, x0, x1, nranks, rank, halo_cells):
+    """Particle x range a rank keeps: its slab widened by `halo_cells` node spacings; open at the domain ends."""
+    h = (ax[-1] - ax[0]) / (len(ax) - 1)
+    lo = ax[x0] - (halo_cells + 0.5) * h
+    hi = ax[x1 - 1] + (halo_cells + 0.5) * h
+    return lo, hi, rank == 0, rank == nranks - 1
+
+
+class CudaBackend:
+    """The product path: hand-written kernels behind the C ABI."""
+
+    def __init__(self, N, k_axis, edges, nranks, rank):
+        self.plan = _lib.PkPlan(N, k_axis, edges, nranks=nranks, rank=rank)
+
+    def grid_slab(self, pos, vel, rho, ax_loc, ax, lcell3, keep):
+        lo, hi, open_lo, open_hi = keep
+        o = _lib.NNOpts()
+        o.use_x_keep = 1
+        o.x_keep_lo, o.x_keep_hi = float(lo), float(hi)
+        o.x_lo_is_domain_edge, o.x_hi_is_domain_edge = int(open_lo), int(open_hi)
+        _, nn_pos, spay = _lib.nn_grid_payload(pos, vel, rho, ax_loc, ax, ax, lcell3, want_idx=False, opts=o)
+        st = _lib.nn_grid_stats()
+        return (nn_pos, spay), st["n_unresolved"]
+
+    def fields(self, gridded, quantity, strict):
+        nn_pos, spay = gridded
+        if quantity == "velocity":
+            f = _lib.fields_sorted(nn_pos, spay, want_v=True)
+            return [f["vx"], f["vy"], f["vz"]], 1.0
+        if quantity == "momentum":
+            if strict:
+                f = _lib.fields_sorted(nn_pos, spay, want_v=False, want_p=(True, False, False))
+                return [f["px"]], 3.0
+            f = _lib.fields_sorted(nn_pos, spay, want_v=False, want_p=(True, True, True))
+            return [f["px"], f["py"], f["pz"]], 1.0
+        f = _lib.fields_sorted(nn_pos, spay, want_v=False, want_e=True)
+        return [f["e"]], 1.0
+
+    def fft_local(self, slabs):
+        return self.plan.dist_local(slabs)
+
+    def fft_final(self, recv):
+        return self.plan.dist_final(recv)
+
+
+def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantities=("velocity",), momentum_strict=True,
+                         group=None, backend=None, halo_cells=4, max_halo_cells=None, timings=None):
+    """Whole path on `world_size` ranks.  Every rank passes the SAME particle arrays (replicated, as in the reference
+    MPI script) or at least all particles of its slab + halo; tensors live on the rank's device.
+    -> (dict quantity -> Psum[nbins] numpy, Nsample[nbins] numpy), identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    nranks = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N = len(ax)
+    x0, x1, _, _ = slab_bounds(N, nranks, rank)
+    if backend is None:
+        backend = CudaBackend(N, k_axis, edges, nranks, rank)
+    if max_halo_cells is None:
+        max_halo_cells = N
+
+    # ---- K1 on the slab; widen the halo until every node is proven (rarely more than once)
+    halo = halo_cells
+    while True:
+        gridded, unresolved = backend.grid_slab(pos, vel, rho, ax[x0:x1], ax, lcell3,
+                                                keep_range(ax, x0, x1, nranks, rank, halo))
+        flag = torch.tensor([int(unresolved > 0)], dtype=torch.int64, device=_device_of(pos))
+        if nranks > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            break
+        if halo >= max_halo_cells:
+            raise _lib.VPowerError("nearest-particle search could not be proven inside the widest halo")
+        halo = min(2 * halo, max_halo_cells)
+    if timings is not None:
+        timings["halo_cells"] = halo
+
+    out = {}
+    ns_total = None
+    for q in quantities:
+        slabs, mult = backend.fields(gridded, q, momentum_strict)
+        send = backend.fft_local(slabs)                              # [P, nx, N, kzc] complex64 per component
+        recv = []
+        for s in send:
+            r = torch.empty_like(s)
+            if nranks > 1:
+                dist.all_to_all_single(torch.view_as_real(r).reshape(-1), torch.view_as_real(s).reshape(-1), group=group)
+            else:
+                r.copy_(s)
+            recv.append(r.reshape(N, N, -1))                         # [x][ky][kz_local]
+        psum, ns = backend.fft_final(recv)
+        if nranks > 1:
+            dist.all_reduce(psum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(ns, op=dist.ReduceOp.SUM, group=group)
+        out[q] = psum.cpu().numpy() * (mult * norm)
+        ns_total = ns.cpu().numpy().astype(np.int64)
+    return out, ns_total
+
+
+def _device_of(t):
+    import torch
+    return t.device if isinstance(t, torch.Tensor) else torch.device("cpu")
