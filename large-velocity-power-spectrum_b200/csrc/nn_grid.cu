@@ -49,54 +49,87 @@ struct PayloadIn {
   T lcell3;
 };
 
-template <typename T, bool PAY>
+// ITEMS particles per thread: 1 without the slab filter (pure streaming), 8 with it so that the compaction needs
+// only one global atomic per 2048-particle block
+template <typename T, bool PAY, int kKeygenItems>
 __global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, Grid g,
                                                       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                       void* __restrict__ packed, unsigned long long* __restrict__ kept) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  bool ok = i < np;
-  double x = 0, y = 0, z = 0;
-  if (ok) {
-    x = pos[3 * i];
-    y = pos[3 * i + 1];
-    z = pos[3 * i + 2];
-    // slab filter: a particle beyond a CLOSED face is dropped; beyond an open (domain-edge) face it is kept and clamped
-    if (g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi)))) ok = false;
-  }
-  uint32_t key = 0;
-  if (ok) {
-    int cx = cell_of(x, g.ox, g.ihx, g.gx), cy = cell_of(y, g.oy, g.ihy, g.gy), cz = cell_of(z, g.oz, g.ihz, g.gz);
-    key = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
-  }
-  int64_t o = i;
-  if (g.use_keep) {
-    // compaction (order is irrelevant: the sort follows and ties are decided by index)
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0 && m) base = atomicAdd(kept, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    o = int64_t(base + __popc(m & ((1u << lane) - 1u)));
-  }
-  if (!ok) return;
-  keys[o] = key;
-  vals[o] = uint32_t(o);
-  const float4 a = make_float4(float(x - g.ox), float(y - g.oy), float(z - g.oz), __int_as_float(int(i)));
-  if (PAY) {
-    T vx = pin.vel[3 * i], vy = pin.vel[3 * i + 1], vz = pin.vel[3 * i + 2];
-    T m = pin.lcell3;
-    if (pin.rho) {
-      T r = pin.rho[i];
-      vx = (vx * r) / r;
-      vy = (vy * r) / r;
-      vz = (vz * r) / r;
-      m = r * pin.lcell3;
+  __shared__ unsigned warp_cnt[8];
+  __shared__ unsigned long long block_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t base_i = int64_t(blockIdx.x) * (256 * kKeygenItems);
+  bool ok[kKeygenItems];
+  uint32_t key[kKeygenItems];
+  float4 a[kKeygenItems];
+  unsigned mine = 0;
+#pragma unroll
+  for (int r = 0; r < kKeygenItems; ++r) {
+    const int64_t i = base_i + r * 256 + threadIdx.x;
+    ok[r] = i < np;
+    double x = 0, y = 0, z = 0;
+    if (ok[r]) {
+      x = pos[3 * i];
+      y = pos[3 * i + 1];
+      z = pos[3 * i + 2];
+      // slab filter: a particle beyond a CLOSED face is dropped; beyond an open (domain-edge) face it is kept and clamped
+      if (g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi)))) ok[r] = false;
     }
-    rec32_t* out = static_cast<rec32_t*>(packed) + o;
-    out->a = a;
-    out->b = make_float4(float(vx), float(vy), float(vz), float(m));
-  } else {
-    static_cast<float4*>(packed)[o] = a;
+    key[r] = 0;
+    if (ok[r]) {
+      int cx = cell_of(x, g.ox, g.ihx, g.gx), cy = cell_of(y, g.oy, g.ihy, g.gy), cz = cell_of(z, g.oz, g.ihz, g.gz);
+      key[r] = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+      a[r] = make_float4(float(x - g.ox), float(y - g.oy), float(z - g.oz), __int_as_float(int(i)));
+      ++mine;
+    }
+  }
+  // output slot: identity without the filter; with it, a block-wide exclusive scan + one atomic per block
+  // (order is irrelevant: the sort follows and ties are decided by particle index)
+  unsigned long long slot0 = 0;
+  if (g.use_keep) {
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_cnt[w] = incl;
+    __syncthreads();
+    unsigned woff = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q < w) woff += warp_cnt[q];
+      tot += warp_cnt[q];
+    }
+    if (threadIdx.x == 0) block_base = tot ? atomicAdd(kept, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    slot0 = block_base + woff + incl - mine;
+  }
+  unsigned nth = 0;
+#pragma unroll
+  for (int r = 0; r < kKeygenItems; ++r) {
+    if (!ok[r]) continue;
+    const int64_t i = base_i + r * 256 + threadIdx.x;
+    const int64_t o = g.use_keep ? int64_t(slot0 + nth) : i;
+    ++nth;
+    keys[o] = key[r];
+    vals[o] = uint32_t(o);
+    if (PAY) {
+      T vx = pin.vel[3 * i], vy = pin.vel[3 * i + 1], vz = pin.vel[3 * i + 2];
+      T m = pin.lcell3;
+      if (pin.rho) {
+        T rr = pin.rho[i];
+        vx = (vx * rr) / rr;
+        vy = (vy * rr) / rr;
+        vz = (vz * rr) / rr;
+        m = rr * pin.lcell3;
+      }
+      rec32_t* out = static_cast<rec32_t*>(packed) + o;
+      out->a = a[r];
+      out->b = make_float4(float(vx), float(vy), float(vz), float(m));
+    } else {
+      static_cast<float4*>(packed)[o] = a[r];
+    }
   }
 }
 
@@ -570,9 +603,16 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     pin.vel = has_pay ? pay->vel : nullptr;
     pin.rho = has_pay ? pay->rho : nullptr;
     pin.lcell3 = T(has_pay ? pay->lcell3 : 1.0);
-    const unsigned nb = unsigned((np + 255) / 256);
-    if (has_pay) k_keygen_pack<T, true><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, &ctx->nn_stats_d->n_kept);
-    else k_keygen_pack<T, false><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, &ctx->nn_stats_d->n_kept);
+    unsigned long long* kept_d = &ctx->nn_stats_d->n_kept;
+    if (o.use_x_keep) {
+      const unsigned nb = unsigned((np + 256 * 8 - 1) / (256 * 8));
+      if (has_pay) k_keygen_pack<T, true, 8><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, kept_d);
+      else k_keygen_pack<T, false, 8><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, kept_d);
+    } else {
+      const unsigned nb = unsigned((np + 255) / 256);
+      if (has_pay) k_keygen_pack<T, true, 1><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, kept_d);
+      else k_keygen_pack<T, false, 1><<<nb, 256, 0, st>>>(pos, pin, np, g, keys, vals, packed, kept_d);
+    }
     VP_CHECK_LAUNCH();
   }
   if (o.use_x_keep) {

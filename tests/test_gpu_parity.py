@@ -378,3 +378,31 @@ def test_slab_path_emulated_on_one_gpu(lib, orc, P):
         assert np.array_equal(ns.cpu().numpy(), ref_ns)
         got = psum.cpu().numpy() * (mult * 0.5 * a * a)
         assert np.allclose(got, ref[q], rtol=1e-6, atol=0), (q, np.max(np.abs(got / ref[q] - 1)))
+
+
+# ------------------------------------------------------------------------------------------ script drop-in
+def test_script_dropin_writes_reference_pk_txt(lib, golden, tmp_path):
+    """scripts/parallel_optimized.py drop-in: same flags, same Pk.txt as the verbatim reference run (single rank)."""
+    import importlib.util
+    import os
+    name = "script16"
+    snap = tmp_path / "snap.npz"
+    np.savez(snap, **{"PartType0/Coordinates": golden[f"{name}/pos"], "PartType0/Masses": golden[f"{name}/mass"],
+                      "PartType0/Velocities": golden[f"{name}/vel"]})
+    path = os.path.join(os.path.dirname(lib.LIB_PATH), "scripts", "parallel_optimized.py")
+    spec = importlib.util.spec_from_file_location("po_b200", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(["-i", str(snap), "-o", str(tmp_path), "-N", "16", "-M", "8", "-b", "512", "-f"]) == 0
+    got = np.loadtxt(tmp_path / "Pk.txt")
+    ref = golden[f"{name}/Pk"]
+    assert got.shape == ref.shape
+    assert np.allclose(got[:, 0], ref[:, 0], rtol=1e-6)
+    assert np.array_equal(got[:, 3], ref[:, 3])
+    assert np.allclose(got[:, 2], ref[:, 2], rtol=1e-3) and np.allclose(got[:, 1], ref[:, 1], rtol=1e-3)
+    # helper functions keep the script's conventions
+    assert mod.planner(1000, 1, 500, 8) == (1, 2, 500, 0.5)
+    P = np.random.default_rng(0).random((16, 16, 16))
+    pairs = mod.pair_power(P, 1.0, 16)
+    h = mod.hist_sample(pairs, 2 * np.pi, np.pi * 16, 2 * np.pi)
+    assert pairs.shape == (4096, 2) and h.shape == (8, 4) and np.array_equal(h[:, 3], ref[:, 3])
