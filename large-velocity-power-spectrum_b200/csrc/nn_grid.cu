@@ -222,22 +222,55 @@ struct Lattice {
   // with the cell-assignment slack already taken off; +inf when the block reaches an open end of the grid)
   const float *fx, *fy, *fz;
   const float *mx, *my, *mz;
+  // first cell of the node's 2-cell window per axis: [w, w+1] is the pair of cells whose common face is nearest
+  // to the node (with the default grid the nodes sit exactly on cell corners, so the 2x2x2 block proves radius h)
+  const int *wx, *wy, *wz;
   int nx, ny, nz;
 };
 
-// Ring-1 search, f32 prefilter.  One thread per lattice node (consecutive lanes = consecutive z nodes).
-// Distances are evaluated in f32 on origin-relative coordinates; the two smallest are tracked.  The node is
-// settled here only if (a) the runner-up is farther than the winner by more than a rigorous bound on the f32
-// error of both and (b) the winner (plus that bound) is strictly inside the proof margin.  Everything else --
-// near ties, exact ties, unproven nodes -- goes to k_search_exact.
+// Stage A of the search, f32 prefilter, one thread per lattice node (consecutive lanes = consecutive z nodes).
+// Candidates: the 2x2x2 cell block around the node (4 cell rows x 2 contiguous cells).  Distances are evaluated in f32
+// on origin-relative coordinates and the two smallest are tracked.  A node is settled here only if (a) the runner-up
+// is farther than the winner by more than a rigorous bound on the f32 error of both and (b) the winner (plus that
+// bound) is strictly inside the proof margin of the block.  Unproven nodes go to stage B (4x4x4 block); proven but
+// ambiguous ones (near ties, exact ties) go straight to the exact f64 kernel.
 //
 // f32 error bound: stored coordinate c~ = fl(p-o), query q~ = fl(q-o), d~x = fl(q~-c~):
 //   |d~x - dx| <= 2^-24 (|q-o| + |p-o| + |dx|) <= 2^-23 (E + |dx|) =: eps      (E = grid extent)
 //   |d~^2 - d^2| <= 2 sqrt(3) d eps + 3 eps^2 + 2^-22 d^2
-__global__ void __launch_bounds__(256) k_search_ring1(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
-                                                       Lattice L, float extent, int32_t* __restrict__ nn,
-                                                       int32_t* __restrict__ nn_pos, uint32_t* __restrict__ list,
-                                                       vp_nn_stats_dev* __restrict__ stats) {
+struct Cand {
+  float b1, b2;
+  int bi;
+};
+__device__ __forceinline__ void scan_row(const rec_t* __restrict__ part, uint32_t s, uint32_t e, float qx, float qy, float qz,
+                                         Cand& c) {
+#pragma unroll 1
+  for (uint32_t p = s; p < e; ++p) {
+    const float4 q = __ldg(part + p);
+    const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
+    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const bool lt = d < c.b1;
+    c.b2 = fminf(c.b2, lt ? c.b1 : d);
+    c.bi = lt ? int(p) : c.bi;
+    c.b1 = lt ? d : c.b1;
+  }
+}
+// 0: settled, 1: proven-or-not but ambiguous / empty -> exact, 2: unambiguous but unproven -> wider block
+__device__ __forceinline__ int judge(const Cand& c, float extent, float margin, float* tol_out) {
+  if (c.bi < 0) return 2;
+  const float rb = sqrtf(c.b2 < INFINITY ? c.b2 : c.b1);
+  const float eps = 1.5e-7f * (extent + rb);
+  const float tol = 8.f * rb * eps + 8.f * eps * eps + 1e-6f * rb * rb;   // >= err(b1) + err(b2)
+  *tol_out = tol;
+  const bool proven = (margin == INFINITY) || (margin > 0.f && c.b1 + tol < margin * margin);
+  if (!proven) return 2;
+  return (c.b2 - c.b1 > tol) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) k_search_block2(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
+                                                        Lattice L, float extent, int32_t* __restrict__ nn,
+                                                        int32_t* __restrict__ nn_pos, uint32_t* __restrict__ list_b,
+                                                        uint32_t* __restrict__ list_c, vp_nn_stats_dev* __restrict__ stats) {
   // block = (z nodes, y rows); grid = (z chunks, y chunks, x)
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -245,56 +278,96 @@ __global__ void __launch_bounds__(256) k_search_ring1(const rec_t* __restrict__ 
   if (k >= L.nz || j >= L.ny) return;
   const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
   const float qx = __ldg(L.fx + i), qy = __ldg(L.fy + j), qz = __ldg(L.fz + k);
-  const int cx = __ldg(L.cx + i), cy = __ldg(L.cy + j), cz = __ldg(L.cz + k);
-  const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
-  float b1 = INFINITY, b2 = INFINITY;
-  int bi = -1;
-  // all row bounds first (independent loads), then nine short, non-unrolled candidate loops
-  uint32_t rs[9], re[9];
+  const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
+  const int z1 = min(wz + 1, g.gz - 1);
+  Cand c;
+  c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+  uint32_t rs[4], re[4];
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int X = cx - 1 + a, Y = cy - 1 + b;
-      const bool in = X >= 0 && X < g.gx && Y >= 0 && Y < g.gy;
+    for (int b = 0; b < 2; ++b) {
+      const int X = wx + a, Y = wy + b;
+      const bool in = X < g.gx && Y < g.gy;
       const size_t row = in ? (size_t(X) * g.gy + Y) * g.gz : 0;
-      rs[a * 3 + b] = in ? __ldg(start + row + z0) : 0u;
-      re[a * 3 + b] = in ? __ldg(start + row + z1 + 1) : 0u;
+      rs[a * 2 + b] = in ? __ldg(start + row + wz) : 0u;
+      re[a * 2 + b] = in ? __ldg(start + row + z1 + 1) : 0u;
     }
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
-#pragma unroll 1
-    for (uint32_t p = rs[r]; p < re[r]; ++p) {
-      const float4 q = __ldg(part + p);
-      const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
-      const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      const bool lt = d < b1;
-      b2 = fminf(b2, lt ? b1 : d);
-      bi = lt ? int(p) : bi;
-      b1 = lt ? d : b1;
-    }
-  }
-  bool settled = false;
-  if (bi >= 0) {
-    const float rb = sqrtf(b2 < INFINITY ? b2 : b1);
-    const float eps = 1.5e-7f * (extent + rb);
-    const float tol = 8.f * rb * eps + 8.f * eps * eps + 1e-6f * rb * rb;   // >= err(b1) + err(b2)
-    if (b2 - b1 > tol) {
-      const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
-      settled = (m == INFINITY) || (m > 0.f && b1 + tol < m * m);
-    }
-  }
-  if (settled) {
-    if (nn) nn[node] = __float_as_int(__ldg(&part[bi].w));
-    if (nn_pos) nn_pos[node] = bi;
+  for (int r = 0; r < 4; ++r) scan_row(part, rs[r], re[r], qx, qy, qz, c);
+  const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
+  float tol;
+  const int verdict = judge(c, extent, m, &tol);
+  if (verdict == 0) {
+    if (nn) nn[node] = __float_as_int(__ldg(&part[c.bi].w));
+    if (nn_pos) nn_pos[node] = c.bi;
+  } else if (verdict == 1) {
+    list_c[atomicAdd(&stats->n_wide, 1ull)] = uint32_t(node);
   } else {
-    unsigned long long slot = atomicAdd(&stats->n_wide, 1ull);
-    list[slot] = uint32_t(node);
+    list_b[atomicAdd(&stats->pad, 1ull)] = uint32_t(node);
   }
 }
 
-// Exact search, one warp per listed node, f64 arithmetic on the caller's coordinates.  The searched block
-// starts at ring 1 and doubles until the proof holds (or every kept particle has been examined).
+// Stage B: the nodes stage A could not prove, one thread per listed node, the 32-cell union of the three 4x2x2 bars
+// through the window (proves sqrt(2) h with corner-aligned nodes), same f32 prefilter and verdict.  What is still
+// unproven or ambiguous goes to the exact kernel.
+__global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
+                                                        Lattice L, float extent, int32_t* __restrict__ nn,
+                                                        int32_t* __restrict__ nn_pos, const uint32_t* __restrict__ list_b,
+                                                        uint32_t* __restrict__ list_c, vp_nn_stats_dev* __restrict__ stats) {
+  const unsigned long long nb = stats->pad;
+  for (unsigned long long t = (unsigned long long)(blockIdx.x) * blockDim.x + threadIdx.x; t < nb;
+       t += (unsigned long long)(gridDim.x) * blockDim.x) {
+    const uint32_t node = list_b[t];
+    const int k = int(node % uint32_t(L.nz));
+    const uint32_t u = node / uint32_t(L.nz);
+    const int j = int(u % uint32_t(L.ny)), i = int(u / uint32_t(L.ny));
+    const float qx = L.fx[i], qy = L.fy[j], qz = L.fz[k];
+    // examined region = union of the three 4x2x2 bars through the 2x2x2 window (32 cells instead of 64):
+    //   central rows (x, y both inside the window): 4 cells along z;  rows one step outside in x OR y: 2 cells
+    const int wx = L.wx[i], wy = L.wy[j], wz = L.wz[k];
+    const int wx1 = min(wx + 1, g.gx - 1), wy1 = min(wy + 1, g.gy - 1), wz1 = min(wz + 1, g.gz - 1);
+    const int x0 = max(wx - 1, 0), x1 = min(wx + 2, g.gx - 1);
+    const int y0 = max(wy - 1, 0), y1 = min(wy + 2, g.gy - 1);
+    const int z0 = max(wz - 1, 0), z1 = min(wz + 2, g.gz - 1);
+    Cand c;
+    c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+    for (int X = x0; X <= x1; ++X)
+      for (int Y = y0; Y <= y1; ++Y) {
+        const bool xin = X >= wx && X <= wx1, yin = Y >= wy && Y <= wy1;
+        if (!xin && !yin) continue;                                  // corner rows are not part of the union
+        const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+        const int a = (xin && yin) ? z0 : wz, b = (xin && yin) ? z1 : wz1;
+        scan_row(part, __ldg(start + row + a), __ldg(start + row + b + 1), qx, qy, qz, c);
+      }
+    // nearest unexamined point: beyond a 4-cell bar end along one axis, or outside the 2-cell window along two axes
+    const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
+    const double m4 = fmin(axis_margin(qxd, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
+                           fmin(axis_margin(qyd, g.oy, g.hy, y0, y1, g.gy, false, false),
+                                axis_margin(qzd, g.oz, g.hz, z0, z1, g.gz, false, false)));
+    double a2 = axis_margin(qxd, g.ox, g.hx, wx, wx1, g.gx, g.closed_xlo, g.closed_xhi);
+    double b2 = axis_margin(qyd, g.oy, g.hy, wy, wy1, g.gy, false, false);
+    double c2 = axis_margin(qzd, g.oz, g.hz, wz, wz1, g.gz, false, false);
+    // two smallest of (a2, b2, c2)
+    double lo1 = fmin(a2, fmin(b2, c2));
+    double lo2 = (lo1 == a2) ? fmin(b2, c2) : ((lo1 == b2) ? fmin(a2, c2) : fmin(a2, b2));
+    const double diag = (lo2 == INFINITY) ? INFINITY : sqrt(lo1 * lo1 + lo2 * lo2);
+    const double md = fmin(m4, diag);
+    float m = INFINITY;
+    if (md != INFINITY) m = md > 0.0 ? __double2float_rd(md * (1.0 - 1.0 / 1048576.0)) : 0.f;
+    float tol;
+    if (judge(c, extent, m, &tol) == 0) {
+      if (nn) nn[node] = __float_as_int(__ldg(&part[c.bi].w));
+      if (nn_pos) nn_pos[node] = c.bi;
+    } else {
+      list_c[atomicAdd(&stats->n_wide, 1ull)] = node;
+    }
+  }
+}
+
+// Exact search, one warp per listed node, f64 arithmetic on the caller's coordinates.  The searched block starts
+// as the node's 2x2x2 window and is widened (1, 3, 7, ... cells per side) until the proof holds (or every kept
+// particle has been examined).
 template <typename T>
 __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ part, const uint32_t* __restrict__ start,
                                                        const T* __restrict__ pos, Grid g, Lattice L, int32_t* __restrict__ nn,
@@ -310,14 +383,15 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
     int64_t t = node / L.nz;
     int j = int(t % L.ny), i = int(t / L.ny);
     const double qx = L.qx[i], qy = L.qy[j], qz = L.qz[k];
-    const int cx = L.cx[i], cy = L.cy[j], cz = L.cz[k];
+    const int wx = L.wx[i], wy = L.wy[j], wz = L.wz[k];
     Best b;
     int bpos = -1;
     bool done = false;
-    for (int r = 1; !done; r *= 2) {
-      const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
-      const int y0 = max(cy - r, 0), y1 = min(cy + r, g.gy - 1);
-      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.gz - 1);
+    // block = the 2-cell window widened by r cells on every side, r = 0, 1, 3, 7, ...
+    for (int r = 0; !done; r = 2 * r + 1) {
+      const int x0 = max(wx - r, 0), x1 = min(wx + 1 + r, g.gx - 1);
+      const int y0 = max(wy - r, 0), y1 = min(wy + 1 + r, g.gy - 1);
+      const int z0 = max(wz - r, 0), z1 = min(wz + 1 + r, g.gz - 1);
       b.d2 = INFINITY;
       b.idx = 0x7fffffff;
       bpos = -1;
@@ -420,12 +494,14 @@ struct AxisPlan {
 
 // cell lattice for one axis: `g` cells of size h covering the node range widened by half a node
 // spacing on each side (so that for g == n uniform nodes every node sits at a cell centre)
-AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, bool use_ext) {
+// `corner`: g must be n+1; the cells have the node spacing and every node sits on a cell corner
+AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, bool use_ext, bool corner = false) {
   double qmin = q[0], qmax = q[0];
   for (int i = 1; i < n; ++i) { qmin = fmin(qmin, q[i]); qmax = fmax(qmax, q[i]); }
   double sp = n > 1 ? (qmax - qmin) / (n - 1) : 1.0;
   if (!(sp > 0)) sp = 1.0;
   double lo = qmin - 0.5 * sp, hi = qmax + 0.5 * sp;
+  if (corner) { lo = qmin - sp; hi = qmax + sp; }
   if (use_ext) { lo = lo_ext; hi = hi_ext; }
   AxisPlan a;
   a.g = g;
@@ -437,39 +513,44 @@ AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, 
 Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, const double* qz, int nz,
                const vp_nn_opts& o) {
   int gx = o.cells_x, gy = o.cells_y, gz = o.cells_z;
+  bool corner_x = false, corner_y = false, corner_z = false;
   if (gx <= 0 || gy <= 0 || gz <= 0) {
-    // about one particle per cell inside the lattice volume; when the particle count is comparable to the
-    // node count the lattice itself is the natural resolution (nodes then sit at cell centres)
+    // about one particle per cell inside the lattice volume; when the particle count is comparable to the node
+    // count the cells take the node spacing and are shifted so that every node sits on a cell CORNER: the 2x2x2
+    // block around a node then proves radius h with 8 candidate cells (a centred 3x3x3 block needs 27 for 1.5 h)
     double per_axis = cbrt(double(np > 0 ? np : 1) / (double(nx) * ny * nz));  // cells per node along an axis
-    auto pick = [&](int n) {
+    auto pick = [&](int n, bool& corner) {
       double g = n * per_axis;
-      if (g > 0.7 * n && g < 1.5 * n) return n;  // snap to the lattice
+      corner = (g > 0.7 * n && g < 1.5 * n && n > 1);
+      if (corner) return n + 1;
       int gi = int(g + 0.5);
       return gi < 1 ? 1 : gi;
     };
-    gx = pick(nx); gy = pick(ny); gz = pick(nz);
+    gx = pick(nx, corner_x); gy = pick(ny, corner_y); gz = pick(nz, corner_z);
     if (o.use_x_keep) {
-      // the x extent is the kept range; keep the same cell size as along y
-      AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false);
-      AxisPlan a0 = plan_axis(qx, nx, nx, 0, 0, false);
+      // the x extent is the kept range (closed sides) / the lattice extent (open sides); same cell size as along y
+      AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false, corner_y);
+      AxisPlan a0 = plan_axis(qx, nx, nx + 1, 0, 0, false, nx > 1);
       double lo = o.x_lo_is_domain_edge ? a0.o : o.x_keep_lo;
-      double hi = o.x_hi_is_domain_edge ? a0.o + a0.h * nx : o.x_keep_hi;
-      int g = int((hi - lo) / ay.h + 0.999);
+      double hi = o.x_hi_is_domain_edge ? a0.o + a0.h * (nx + 1) : o.x_keep_hi;
+      int g = int((hi - lo) / ay.h + 0.5);
       gx = g < 1 ? 1 : g;
+      corner_x = false;
     }
   }
   while (double(gx) * gy * gz >= 4294967295.0) {  // 32-bit keys
     gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
+    corner_x = corner_y = corner_z = false;
   }
-  // x extent of the cell list: the kept range on closed sides, the lattice extent on open (domain-edge) sides
-  AxisPlan ax = plan_axis(qx, nx, gx, 0, 0, false);
+  AxisPlan ax = plan_axis(qx, nx, gx, 0, 0, false, corner_x);
   if (o.use_x_keep) {
-    double lo = o.x_lo_is_domain_edge ? ax.o : o.x_keep_lo;
-    double hi = o.x_hi_is_domain_edge ? ax.o + ax.h * gx : o.x_keep_hi;
+    AxisPlan a0 = plan_axis(qx, nx, nx + 1, 0, 0, false, nx > 1);
+    double lo = o.x_lo_is_domain_edge ? a0.o : o.x_keep_lo;
+    double hi = o.x_hi_is_domain_edge ? a0.o + a0.h * (nx + 1) : o.x_keep_hi;
     ax = plan_axis(qx, nx, gx, lo, hi, true);
   }
-  AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false);
-  AxisPlan az = plan_axis(qz, nz, gz, 0, 0, false);
+  AxisPlan ay = plan_axis(qy, ny, gy, 0, 0, false, corner_y);
+  AxisPlan az = plan_axis(qz, nz, gz, 0, 0, false, corner_z);
   Grid g;
   g.ox = ax.o; g.oy = ay.o; g.oz = az.o;
   g.hx = ax.h; g.hy = ay.h; g.hz = az.h;
@@ -491,8 +572,8 @@ NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, int64_t nnodes) {
   s.packed = vp_align256(size_t(np) * (pay ? sizeof(rec32_t) : sizeof(float4)));
   s.spos = vp_align256(size_t(np) * sizeof(rec_t));
   s.start = vp_align256((ncells + 1) * 4);
-  size_t b_wide = vp_align256(size_t(nnodes) * 4), b_sort = vp_sort_scratch_bytes(np);
-  s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are permuted; the node list reuses it
+  size_t b_wide = 2 * vp_align256(size_t(nnodes) * 4), b_sort = vp_sort_scratch_bytes(np);
+  s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are permuted; the two node lists reuse it
   s.total = 2 * s.keys + s.packed + s.spos + s.start + s.tail + 2048;
   return s;
 }
@@ -527,7 +608,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   // ---- lattice tables (host -> pinned -> device)
   const size_t nt = size_t(nx) + ny + nz;
   const size_t off_c = vp_align256(nt * 8), off_f = off_c + vp_align256(nt * 4), off_m = off_f + vp_align256(nt * 4);
-  const size_t tab_bytes = off_m + vp_align256(nt * 4);
+  const size_t off_w = off_m + vp_align256(nt * 4);
+  const size_t tab_bytes = off_w + vp_align256(nt * 4);
   if (ctx->pinned_cap < tab_bytes) {
     if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
     VP_CUDA(cudaMallocHost(&ctx->pinned_h, tab_bytes));
@@ -545,6 +627,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   int* hc = reinterpret_cast<int*>(hb + off_c);
   float* hf = reinterpret_cast<float*>(hb + off_f);
   float* hm = reinterpret_cast<float*>(hb + off_m);
+  int* hw = reinterpret_cast<int*>(hb + off_w);
   auto fill_axis = [&](const double* q, int n, int at, double o_, double h_, double ih, int gg, bool closed_lo, bool closed_hi) {
     for (int i = 0; i < n; ++i) {
       double f = (q[i] - o_) * ih;
@@ -552,8 +635,13 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       hq[at + i] = q[i];
       hc[at + i] = c;
       hf[at + i] = float(q[i] - o_);
-      // same expression as the device axis_margin() for the ring-1 block [c-1, c+1]
-      const int c0 = c - 1 < 0 ? 0 : c - 1, c1 = c + 1 > gg - 1 ? gg - 1 : c + 1;
+      // 2-cell window [w, w+1]: the neighbour on the side of the nearer face of cell c
+      int w = (f - double(c) < 0.5) ? c - 1 : c;
+      if (w > gg - 2) w = gg - 2;
+      if (w < 0) w = 0;
+      hw[at + i] = w;
+      // same expression as the device axis_margin() for the block [c0, c1]
+      const int c0 = w, c1 = w + 1 > gg - 1 ? gg - 1 : w + 1;
       double m = INFINITY;
       if (c0 > 0) m = fmin(m, q[i] - (o_ + double(c0) * h_));
       else if (closed_lo) m = fmin(m, q[i] - o_);
@@ -578,6 +666,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   L.cx = reinterpret_cast<const int*>(db + off_c); L.cy = L.cx + nx; L.cz = L.cy + ny;
   L.fx = reinterpret_cast<const float*>(db + off_f); L.fy = L.fx + nx; L.fz = L.fy + ny;
   L.mx = reinterpret_cast<const float*>(db + off_m); L.my = L.mx + nx; L.mz = L.my + ny;
+  L.wx = reinterpret_cast<const int*>(db + off_w); L.wy = L.wx + nx; L.wz = L.wy + ny;
   L.nx = nx; L.ny = ny; L.nz = nz;
 
   // ---- scratch
@@ -591,7 +680,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   uint32_t* start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.start));
   void* scratch = vp_arena_alloc(ctx, sc.tail);
   VP_REQUIRE(keys && vals && packed && spos && start && scratch, "vp_nn_grid: arena carve failed");
-  uint32_t* node_list = static_cast<uint32_t*>(scratch);
+  uint32_t* node_list = static_cast<uint32_t*>(scratch);                                      // -> exact kernel
+  uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> 4x4x4 stage
 
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
   int64_t n = np;
@@ -642,16 +732,20 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   }
   VP_CHECK_LAUNCH();
   int32_t* nn_pos = has_pay ? pay->nn_pos_out : nullptr;
+  const float extent = float(fmax(fmax(g.gx * g.hx, g.gy * g.hy), g.gz * g.hz));
   {
     // sorted records read once + cell starts read once + one index written per node
-    vp_stage stage(ctx, "k1e_search_ring1", st, 1, double(n) * sizeof(rec_t) + double(ncells) * 4.0 + double(nnodes) * 4.0);
-    const float extent = float(fmax(fmax(g.gx * g.hx, g.gy * g.hy), g.gz * g.hz));
+    vp_stage stage(ctx, "k1e_search_block2", st, 1, double(n) * sizeof(rec_t) + double(ncells) * 4.0 + double(nnodes) * 4.0);
     // block = (z nodes, y rows), one x plane per blockIdx.z: no integer division in the kernel
     int bx = nz >= 256 ? 256 : ((nz + 31) / 32) * 32;
     int by = 256 / bx;
     dim3 block(bx, by, 1), grid((nz + bx - 1) / bx, (ny + by - 1) / by, nx);
-    VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the ring-1 launch");
-    k_search_ring1<<<grid, block, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, node_list, ctx->nn_stats_d);
+    VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
+    k_search_block2<<<grid, block, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, list_b, node_list, ctx->nn_stats_d);
+  }
+  {
+    vp_stage stage(ctx, "k1e_search_block4", st, 1);
+    k_search_block4<<<ctx->sm_count * 8, 256, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, list_b, node_list, ctx->nn_stats_d);
   }
   {
     vp_stage stage(ctx, "k1f_search_exact", st, 1);

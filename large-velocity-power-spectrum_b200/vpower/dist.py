@@ -29,10 +29,11 @@ def slab_bounds(N, nranks, rank):
 
 
 def keep_range(ax, x0, x1, nranks, rank, halo_cells):
-    """Particle x range a rank keeps: its slab widened by `halo_cells` node spacings; open at the domain ends."""
+    """Particle x range a rank keeps: its slab widened by `halo_cells` node spacings (a whole number keeps the
+    slab's cell list corner-aligned with the lattice nodes); open at the domain ends."""
     h = (ax[-1] - ax[0]) / (len(ax) - 1)
-    lo = ax[x0] - (halo_cells + 0.5) * h
-    hi = ax[x1 - 1] + (halo_cells + 0.5) * h
+    lo = ax[x0] - halo_cells * h
+    hi = ax[x1 - 1] + halo_cells * h
     return lo, hi, rank == 0, rank == nranks - 1
 
 

@@ -153,5 +153,5 @@ def test_slab_bounds():
         vd.slab_bounds(24, 5, 0)
     ax = np.linspace(0.5, 15.5, 16)
     lo, hi, ol, oh = vd.keep_range(ax, 4, 8, 4, 1, 2)
-    assert np.isclose(lo, 4.5 - 2.5) and np.isclose(hi, 7.5 + 2.5) and not ol and not oh
+    assert np.isclose(lo, 4.5 - 2.0) and np.isclose(hi, 7.5 + 2.0) and not ol and not oh
     assert vd.keep_range(ax, 0, 4, 4, 0, 2)[2] and vd.keep_range(ax, 12, 16, 4, 3, 2)[3]

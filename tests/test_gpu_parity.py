@@ -115,8 +115,8 @@ def test_nn_slab_matches_full(lib, orc):
         sl = slice(r * N // 4, (r + 1) * N // 4)
         o = lib.NNOpts()
         o.use_x_keep = 1
-        o.x_keep_lo = ax[sl][0] - 4.5 * h
-        o.x_keep_hi = ax[sl][-1] + 4.5 * h
+        o.x_keep_lo = ax[sl][0] - 4 * h
+        o.x_keep_hi = ax[sl][-1] + 4 * h
         o.x_lo_is_domain_edge = 0
         o.x_hi_is_domain_edge = 0
         part = lib.nn_grid(lib.to_device(pos), ax[sl], ax, ax, o).cpu().numpy()
