@@ -191,10 +191,15 @@ def main():
     if world > 1:
         from vpower import dist as vd
         backend = vd.CudaBackend(N, k, edges, world, rank)
+        # sharded input: rank r owns particles [r*Np/P, (r+1)*Np/P) of the synthetic set; the slab exchange is timed
+        lo_i, hi_i = rank * (Np // world), (rank + 1) * (Np // world)
+        pos, vel, rho = pos[lo_i:hi_i].clone(), vel[lo_i:hi_i].clone(), rho[lo_i:hi_i].clone()
+        torch.cuda.empty_cache()
 
     def step_dev():
         if world > 1:      # x-slab gridding, slab FFT with one all-to-all per field, all-reduce of the shells
-            return vd.particles_to_pk_dist(pos, vel, rho, ax, lc3, norm, k, edges, quantities=quantities, backend=backend)
+            return vd.particles_to_pk_dist(pos, vel, rho, ax, lc3, norm, k, edges, quantities=quantities, backend=backend,
+                                           sharded=True)
         return _lib.particles_to_pk(pos, vel, rho, ax, ax, ax, N, lc3, norm, k, edges, quantities=quantities)
 
     def barrier():

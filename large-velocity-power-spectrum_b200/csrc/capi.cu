@@ -55,6 +55,11 @@ extern "C" int vp_ctx_destroy(vp_ctx* ctx) {
   if (ctx->nn_stats_d) cudaFree(ctx->nn_stats_d);
   if (ctx->small_d) cudaFree(ctx->small_d);
   if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
+  }
   if (ctx->cached_plan) vp_pk_plan_destroy(ctx->cached_plan);
   if (ctx->cached_plan_key) free(ctx->cached_plan_key);
   delete ctx;

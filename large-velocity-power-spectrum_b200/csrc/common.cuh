@@ -77,6 +77,8 @@ struct vp_ctx {
   size_t small_cap = 0;
   void* pinned_h = nullptr;               // pinned staging for small host->device tables
   size_t pinned_cap = 0;
+  cudaStream_t copy_stream = nullptr;     // host-buffer entry point: H2D chunks overlap the keygen/pack kernel
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
 };
 
 // Stack discipline: every entry point opens a vp_arena_scope (restores the offset on exit), calls
@@ -98,6 +100,19 @@ struct vp_arena_scope {
 size_t vp_sort_scratch_bytes(int64_t n);
 int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
                        cudaStream_t st);
+
+// Host-resident particle arrays streamed to the device in chunks (vp_host_particles_to_pk): positions land in a
+// resident device array (the exact search needs them), velocity/density chunks only pass through two staging buffers.
+struct vp_host_chunks {
+  const void* pos_h = nullptr;
+  const void* vel_h = nullptr;
+  const void* rho_h = nullptr;
+  int64_t chunk = 0;     // particles per chunk
+};
+size_t vp_host_chunk_staging_bytes(int64_t chunk, int dtype, bool has_rho);
+int vp_nn_grid_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,
+                            const double* qy, int ny, const double* qz, int nz, double lcell3, int32_t* nn_pos_d, float* spay_d,
+                            cudaStream_t st);
 
 // internal forms used by pipeline.cu (typed device pointers, arena already reserved by the caller)
 size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* qx, int nx, const double* qy, int ny,

@@ -47,8 +47,10 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   const int n_pplanes = want_p ? (strict ? 1 : 3) : 0;
   const int nplanes = (want_v ? 3 : 0) + n_pplanes + (want_e ? 1 : 0);
 
+  // host arrays are streamed in chunks: only the positions stay resident (the exact search reads them)
+  const int64_t chunk = np < (int64_t(1) << 24) ? np : (int64_t(1) << 24);
   size_t own = 0;
-  if (on_host) own += vp_align256(size_t(np) * 3 * es) * 2 + (rho ? vp_align256(size_t(np) * es) : 0);
+  if (on_host) own += vp_align256(size_t(np) * 3 * es) + vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 1024;
   own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * 16) + vp_align256(size_t(nbins) * 16) + 8192;
   size_t inner = vp_nn_grid_scratch_bytes_tables(np, dtype, qx, N, qy, N, qz, N, nullptr);
   size_t inner2 = vp_pk_fields_scratch_bytes(plan);
@@ -56,15 +58,10 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   VP_TRY(vp_arena_reserve(ctx, own + (inner > inner2 ? inner : inner2)));
 
   const void *pos_d = pos, *vel_d = vel, *rho_d = rho;
+  void* pos_res = nullptr;
   if (on_host) {
-    void* p = vp_arena_alloc(ctx, size_t(np) * 3 * es);
-    void* v = vp_arena_alloc(ctx, size_t(np) * 3 * es);
-    void* r = rho ? vp_arena_alloc(ctx, size_t(np) * es) : nullptr;
-    VP_REQUIRE(p && v && (!rho || r), "particles_to_pk: arena carve failed");
-    VP_CUDA(cudaMemcpyAsync(p, pos, size_t(np) * 3 * es, cudaMemcpyHostToDevice, st));
-    VP_CUDA(cudaMemcpyAsync(v, vel, size_t(np) * 3 * es, cudaMemcpyHostToDevice, st));
-    if (rho) VP_CUDA(cudaMemcpyAsync(r, rho, size_t(np) * es, cudaMemcpyHostToDevice, st));
-    pos_d = p; vel_d = v; rho_d = r;
+    pos_res = vp_arena_alloc(ctx, size_t(np) * 3 * es);
+    VP_REQUIRE(pos_res, "particles_to_pk: arena carve failed");
   }
   int32_t* nn_pos = static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4));
   float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * 16));
@@ -77,7 +74,13 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   uint64_t* ns_d = static_cast<uint64_t*>(vp_arena_alloc(ctx, size_t(nbins) * 8));
   VP_REQUIRE(nn_pos && spay && psum_d && ns_d, "particles_to_pk: arena carve failed");
 
-  VP_TRY(vp_nn_grid_payload(ctx, pos_d, vel_d, rho_d, dtype, np, qx, N, qy, N, qz, N, lcell3, nullptr, nn_pos, spay, nullptr, st));
+  if (on_host) {
+    vp_host_chunks hc;
+    hc.pos_h = pos; hc.vel_h = vel; hc.rho_h = rho; hc.chunk = chunk;
+    VP_TRY(vp_nn_grid_payload_host(ctx, &hc, pos_res, dtype, np, qx, N, qy, N, qz, N, lcell3, nn_pos, spay, st));
+  } else {
+    VP_TRY(vp_nn_grid_payload(ctx, pos_d, vel_d, rho_d, dtype, np, qx, N, qy, N, qz, N, lcell3, nullptr, nn_pos, spay, nullptr, st));
+  }
 
   int at = 0;
   float *v3[3] = {nullptr, nullptr, nullptr}, *p3[3] = {nullptr, nullptr, nullptr}, *e1 = nullptr;

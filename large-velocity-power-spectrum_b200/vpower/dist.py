@@ -74,10 +74,46 @@ class CudaBackend:
         return self.plan.dist_final(recv)
 
 
+def exchange_particles(pos, vel, rho, ax, nranks, rank, halo_cells, group=None):
+    """Sharded input: every rank holds an arbitrary subset of the particles.  Each particle is sent to the rank(s)
+    whose slab + halo contains its x (one all-to-all-v of [pos|vel|rho] rows; a particle inside a halo goes to two
+    ranks).  -> (pos, vel, rho) of everything this rank needs.  torch ops only (plumbing around NCCL)."""
+    import torch
+    import torch.distributed as dist
+    N = len(ax)
+    rows = torch.cat([pos, vel] + ([rho[:, None]] if rho is not None else []), dim=1)
+    x = pos[:, 0]
+    parts, counts = [], []
+    for d in range(nranks):
+        x0, x1, _, _ = slab_bounds(N, nranks, d)
+        lo, hi, open_lo, open_hi = keep_range(ax, x0, x1, nranks, d, halo_cells)
+        m = torch.ones_like(x, dtype=torch.bool)
+        if not open_lo:
+            m &= x >= lo
+        if not open_hi:
+            m &= x <= hi
+        sel = rows[m]
+        parts.append(sel)
+        counts.append(sel.shape[0])
+    send = torch.cat(parts, dim=0).contiguous()
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=pos.device)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    rc = [int(v) for v in recv_counts.tolist()]
+    w = rows.shape[1]
+    recv = torch.empty((sum(rc), w), dtype=rows.dtype, device=pos.device)
+    dist.all_to_all_single(recv.reshape(-1), send.reshape(-1), output_split_sizes=[c * w for c in rc],
+                           input_split_sizes=[c * w for c in counts], group=group)
+    p, v = recv[:, 0:3].contiguous(), recv[:, 3:6].contiguous()
+    r = recv[:, 6].contiguous() if rho is not None else None
+    return p, v, r
+
+
 def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantities=("velocity",), momentum_strict=True,
-                         group=None, backend=None, halo_cells=4, max_halo_cells=None, timings=None):
-    """Whole path on `world_size` ranks.  Every rank passes the SAME particle arrays (replicated, as in the reference
-    MPI script) or at least all particles of its slab + halo; tensors live on the rank's device.
+                         group=None, backend=None, halo_cells=4, max_halo_cells=None, timings=None, sharded=False):
+    """Whole path on `world_size` ranks.  `sharded=False`: every rank passes the SAME particle arrays (replicated, as in
+    the reference MPI script).  `sharded=True`: every rank passes its own subset; the particles are first exchanged so that
+    each rank holds its slab + halo.  Tensors live on the rank's device.
     -> (dict quantity -> Psum[nbins] numpy, Nsample[nbins] numpy), identical on every rank."""
     import torch
     import torch.distributed as dist
@@ -90,10 +126,13 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
         backend = CudaBackend(N, k_axis, edges, nranks, rank)
     if max_halo_cells is None:
         max_halo_cells = N
+    shard = (pos, vel, rho)
 
     # ---- K1 on the slab; widen the halo until every node is proven (rarely more than once)
     halo = halo_cells
     while True:
+        if sharded and nranks > 1:
+            pos, vel, rho = exchange_particles(*shard, ax, nranks, rank, halo, group)
         gridded, unresolved = backend.grid_slab(pos, vel, rho, ax[x0:x1], ax, lcell3,
                                                 keep_range(ax, x0, x1, nranks, rank, halo))
         flag = torch.tensor([int(unresolved > 0)], dtype=torch.int64, device=_device_of(pos))

@@ -33,7 +33,14 @@ def main():
         d = [_lib.to_device(x) for x in (pos, vel, dens)]
         qs = ("velocity", "momentum", "energy")
         out, ns = vd.particles_to_pk_dist(*d, ax, (L / N) ** 3, 0.5 * a * a, k, edges, quantities=qs)
+        # sharded input: every rank passes only its own part of the particle list
+        sl = slice(rank * Np // world, (rank + 1) * Np // world)
+        out_s, ns_s = vd.particles_to_pk_dist(*[t[sl].contiguous() for t in d], ax, (L / N) ** 3, 0.5 * a * a, k, edges,
+                                              quantities=qs, sharded=True)
         if rank == 0:
+            same_s = np.array_equal(ns_s, ns) and all(np.allclose(out_s[q], out[q], rtol=1e-12) for q in qs)
+            print(f"N={N} world={world}: sharded input == replicated input: {same_s}", flush=True)
+            ok &= same_s
             ref, ref_ns = _lib.particles_to_pk(*d, ax, ax, ax, N, (L / N) ** 3, 0.5 * a * a, k, edges, quantities=qs)
             same = np.array_equal(ns, ref_ns)
             err = max(np.max(np.abs(out[q] / ref[q] - 1)) for q in qs)

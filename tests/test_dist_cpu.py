@@ -102,7 +102,7 @@ class OracleBackend:
         return torch.from_numpy(psum), torch.from_numpy(ns)
 
 
-def _worker(rank, world, port, N, Np, halo, q, ret):
+def _worker(rank, world, port, N, Np, halo, q, ret, sharded=False):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -118,22 +118,24 @@ def _worker(rank, world, port, N, Np, halo, q, ret):
     a = (L / (2 * np.pi)) ** 1.5 / N ** 3
     be = OracleBackend(orc, N, L, k, edges, centres, world, rank)
     tm = {}
-    out, ns = vd.particles_to_pk_dist(torch.from_numpy(pos), torch.from_numpy(vel), torch.from_numpy(dens), ax, (L / N) ** 3,
-                                      0.5 * a * a, k, edges, quantities=q, backend=be, halo_cells=halo, timings=tm)
+    sl = slice(rank * Np // world, (rank + 1) * Np // world) if sharded else slice(None)
+    out, ns = vd.particles_to_pk_dist(torch.from_numpy(pos[sl]), torch.from_numpy(vel[sl]), torch.from_numpy(dens[sl]), ax,
+                                      (L / N) ** 3, 0.5 * a * a, k, edges, quantities=q, backend=be, halo_cells=halo, timings=tm,
+                                      sharded=sharded)
     if rank == 0:
         ret["out"], ret["ns"], ret["halo"] = {k_: v.tolist() for k_, v in out.items()}, ns.tolist(), tm["halo_cells"]
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,halo", [(2, 4), (4, 1), (2, 0.25)])
-def test_slab_pipeline_matches_single_process_oracle(orc, world, halo):
+@pytest.mark.parametrize("world,halo,sharded", [(2, 4, False), (4, 1, False), (2, 0.25, False), (2, 2, True), (4, 0.25, True)])
+def test_slab_pipeline_matches_single_process_oracle(orc, world, halo, sharded):
     import torch.multiprocessing as mp
     N, Np = 16, 3000
     q = ("velocity", "momentum", "energy")
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000) + world
-    mp.spawn(_worker, args=(world, port, N, Np, halo, q, ret), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + world + (10 if sharded else 0)
+    mp.spawn(_worker, args=(world, port, N, Np, halo, q, ret, sharded), nprocs=world, join=True)
     pos, vel, dens, _ = orc.synth_particles(4, Np, 1.0)
     v, m, Lcell = orc.ann_interp_to_field(pos.astype(np.float64), dens.astype(np.float64), vel.astype(np.float64), 1.0, N)
     for name in q:
