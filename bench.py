@@ -196,10 +196,12 @@ def main():
         pos, vel, rho = pos[lo_i:hi_i].clone(), vel[lo_i:hi_i].clone(), rho[lo_i:hi_i].clone()
         torch.cuda.empty_cache()
 
+    phase_t = {}
+
     def step_dev():
         if world > 1:      # x-slab gridding, slab FFT with one all-to-all per field, all-reduce of the shells
             return vd.particles_to_pk_dist(pos, vel, rho, ax, lc3, norm, k, edges, quantities=quantities, backend=backend,
-                                           sharded=True)
+                                           sharded=True, timings=phase_t)
         return _lib.particles_to_pk(pos, vel, rho, ax, ax, ax, N, lc3, norm, k, edges, quantities=quantities)
 
     def barrier():
@@ -292,7 +294,7 @@ def main():
                                        f"library lattice and edges", "l2": "inputs larger than L2" if Np * 28 > 2e8 else "inputs fit L2",
                            "momentum": "reference-strict (vx*m x3)"},
                 "seconds_per_pk": ms * 1e-3, "nn_gridding_gpart_s": None, "gpu_launches": int(launches),
-                "roofline": roof, "stages": table, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk.summary()}
+                "roofline": roof, "stages": table, "dist_phases_ms_last_step": phase_t.get("phases_ms"), "cpu_baseline": cpu, "e2e": e2e, "clocks": clk.summary()}
         nn_ms = sum(table[n]["ms_per_step"] for n in table if n.startswith("k1"))
         if nn_ms > 0:
             line["nn_gridding_gpart_s"] = Np / (nn_ms * 1e-3) / 1e9

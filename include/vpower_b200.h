@@ -83,6 +83,8 @@ typedef struct vp_nn_opts {
   double x_keep_lo, x_keep_hi;   /* particles outside are dropped when use_x_keep */
   int x_lo_is_domain_edge;       /* 1: nothing exists below x_keep_lo (no constraint on that side) */
   int x_hi_is_domain_edge;
+  int row_stride;                /* 0: compact arrays ([np,3], [np,3], [np]); >0: pos/vel/rho are columns of one interleaved
+                                    row array with this many elements per particle (the layout vp_slab_bucket produces) */
 } vp_nn_opts;
 
 int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const double* qx_h, int nx,
@@ -169,6 +171,15 @@ int vp_pk_plan_create_dist(vp_ctx* ctx, int N, int nranks, int rank, const doubl
                            vp_pk_plan** out);
 int vp_pk_dist_local(vp_pk_plan* plan, float* const* field_d, int ncomp, float* const* send_d, void* stream);
 int vp_pk_dist_final(vp_pk_plan* plan, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream);
+
+/* Sharded particle input for the slab decomposition: every particle of this rank's subset is copied into the block of
+ * each destination rank d whose kept range lo_h[d] <= x <= hi_h[d] contains it (use -/+ infinity for open ends).
+ *   rows_d   [cap_rows, 7 (6 without rho)] of dtype: x y z vx vy vz rho, blocks in rank order;  counts_h[d] = rows for rank d.
+ * One counting pass, one scatter pass, one global atomic per block and destination.  Syncs (the split sizes of the
+ * all-to-all are needed on the host).  nranks <= 16. */
+int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                   const double* lo_h, const double* hi_h, int nranks, void* rows_d, int64_t cap_rows, int64_t* counts_h,
+                   void* stream);
 
 /* Test/diagnostic entry points */
 /* In-place 3-D r2c transform only.  Output layout: [N][N][N/2] complex64 where entry (x,y,0) packs

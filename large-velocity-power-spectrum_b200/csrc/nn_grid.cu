@@ -23,6 +23,7 @@ struct Grid {
   int use_keep;
   double keep_lo, keep_hi;
   int closed_xlo, closed_xhi;  // 1: particles beyond that x face were dropped (face constrains the proof)
+  int ps, vs, rs;              // element strides between consecutive particles in pos / vel / rho (3,3,1 when compact)
 };
 
 // Sorted particle record: position relative to the grid origin rounded to f32 (used only by the f32
@@ -70,9 +71,9 @@ __global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, 
     ok[r] = i < np;
     double x = 0, y = 0, z = 0;
     if (ok[r]) {
-      x = pos[3 * i];
-      y = pos[3 * i + 1];
-      z = pos[3 * i + 2];
+      x = pos[size_t(g.ps) * i];
+      y = pos[size_t(g.ps) * i + 1];
+      z = pos[size_t(g.ps) * i + 2];
       // slab filter: a particle beyond a CLOSED face is dropped; beyond an open (domain-edge) face it is kept and clamped
       if (g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi)))) ok[r] = false;
     }
@@ -116,10 +117,10 @@ __global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, 
     keys[o] = key[r];
     vals[o] = uint32_t(o);
     if (PAY) {
-      T vx = pin.vel[3 * i], vy = pin.vel[3 * i + 1], vz = pin.vel[3 * i + 2];
+      T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
       T m = pin.lcell3;
       if (pin.rho) {
-        T rr = pin.rho[i];
+        T rr = pin.rho[size_t(g.rs) * i];
         vx = (vx * rr) / rr;
         vy = (vy * rr) / rr;
         vz = (vz * rr) / rr;
@@ -405,7 +406,8 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
         for (uint32_t p = s; p < e; ++p) {
           const int id = __float_as_int(__ldg(&part[p].w));
           const int before = b.idx;
-          consider(b, qx, qy, qz, double(pos[3 * size_t(id)]), double(pos[3 * size_t(id) + 1]), double(pos[3 * size_t(id) + 2]), id);
+          const size_t pb = size_t(g.ps) * size_t(id);
+          consider(b, qx, qy, qz, double(pos[pb]), double(pos[pb + 1]), double(pos[pb + 2]), id);
           if (b.idx != before) bpos = int(p);
         }
       }
@@ -561,6 +563,9 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
   g.keep_lo = o.x_keep_lo; g.keep_hi = o.x_keep_hi;
   g.closed_xlo = o.use_x_keep && !o.x_lo_is_domain_edge;
   g.closed_xhi = o.use_x_keep && !o.x_hi_is_domain_edge;
+  g.ps = o.row_stride > 0 ? o.row_stride : 3;
+  g.vs = o.row_stride > 0 ? o.row_stride : 3;
+  g.rs = o.row_stride > 0 ? o.row_stride : 1;
   return g;
 }
 
@@ -709,6 +714,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       }
     };
     if (has_pay && pay->host) {
+      VP_REQUIRE(o.row_stride == 0, "vp_nn_grid: host chunk streaming needs compact arrays");
       // host arrays: H2D chunks on the copy stream, keygen/pack of chunk c overlaps the transfer of chunk c+1
       const vp_host_chunks* hc = pay->host;
       if (!ctx->copy_stream) {
@@ -809,7 +815,131 @@ int nn_payload_typed(vp_ctx* ctx, const void* pos, const void* vel, const void* 
   return nn_grid_typed<T>(ctx, static_cast<const T*>(pos), np, qx, nx, qy, ny, qz, nz, nn_idx, &pay, opts, st);
 }
 
+// ------------------------------------------------------------------------------------------ slab bucketing
+// Multi-GPU, sharded input: every particle goes to the rank(s) whose kept x range [lo_d, hi_d] contains it.
+struct SlabRanges {
+  double lo[16], hi[16];
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bucket_count(const T* __restrict__ pos, int64_t np, SlabRanges R, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned sc[16];
+  if (threadIdx.x < 16) sc[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool ok = i < np;
+  const double x = ok ? double(pos[3 * i]) : 0.0;
+  for (int d = 0; d < R.n; ++d) {
+    const unsigned m = __ballot_sync(0xffffffffu, ok && x >= R.lo[d] && x <= R.hi[d]);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&sc[d], __popc(m));
+  }
+  __syncthreads();
+  if (threadIdx.x < R.n && sc[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
+}
+
+// rows = [x y z vx vy vz (rho)] ; cursors[d] starts at the exclusive prefix of counts
+template <typename T>
+__global__ void __launch_bounds__(256) k_bucket_scatter(const T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ rho,
+                                                         int64_t np, SlabRanges R, unsigned long long* __restrict__ cursors,
+                                                         T* __restrict__ rows, int w) {
+  __shared__ unsigned sc[16];
+  __shared__ unsigned long long sbase[16];
+  if (threadIdx.x < 16) sc[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool ok = i < np;
+  const double x = ok ? double(pos[3 * i]) : 0.0;
+  const int lane = threadIdx.x & 31;
+  unsigned myoff[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    myoff[d] = 0xffffffffu;
+    if (d < R.n) {
+      const bool in = ok && x >= R.lo[d] && x <= R.hi[d];
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      unsigned wb = 0;
+      if (lane == 0 && m) wb = atomicAdd(&sc[d], __popc(m));
+      wb = __shfl_sync(0xffffffffu, wb, 0);
+      if (in) myoff[d] = wb + __popc(m & ((1u << lane) - 1u));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < R.n) sbase[threadIdx.x] = sc[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, (unsigned long long)sc[threadIdx.x]) : 0ull;
+  __syncthreads();
+  if (!ok) return;
+  T r[7];
+  r[0] = pos[3 * i]; r[1] = pos[3 * i + 1]; r[2] = pos[3 * i + 2];
+  r[3] = vel[3 * i]; r[4] = vel[3 * i + 1]; r[5] = vel[3 * i + 2];
+  r[6] = rho ? rho[i] : T(0);
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    if (d < R.n && myoff[d] != 0xffffffffu) {
+      T* o = rows + (sbase[d] + myoff[d]) * size_t(w);
+      for (int c = 0; c < w; ++c) o[c] = r[c];
+    }
+  }
+}
+
+__global__ void k_bucket_offsets(const unsigned long long* counts, unsigned long long* cursors, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long a = 0;
+    for (int d = 0; d < n; ++d) { cursors[d] = a; a += counts[d]; }
+  }
+}
+
+template <typename T>
+int slab_bucket_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int64_t np, const SlabRanges& R, T* rows, int64_t cap,
+                      int64_t* counts_h, cudaStream_t st) {
+  vp_arena_scope scope(ctx);
+  VP_TRY(vp_arena_reserve(ctx, 1024));
+  unsigned long long* cnt = static_cast<unsigned long long*>(vp_arena_alloc(ctx, 512));
+  VP_REQUIRE(cnt, "vp_slab_bucket: arena carve failed");
+  unsigned long long* cur = cnt + 16;
+  VP_CUDA(cudaMemsetAsync(cnt, 0, 512, st));
+  const unsigned nb = unsigned((np + 255) / 256);
+  const int w = rho ? 7 : 6;
+  if (np > 0) {
+    vp_stage stage(ctx, "k0_slab_bucket_count", st, 1, double(np) * 3.0 * sizeof(T));
+    k_bucket_count<T><<<nb, 256, 0, st>>>(pos, np, R, cnt);
+  }
+  k_bucket_offsets<<<1, 32, 0, st>>>(cnt, cur, R.n);
+  unsigned long long h[16];
+  VP_CUDA(cudaMemcpyAsync(h, cnt, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, st));
+  VP_CUDA(cudaStreamSynchronize(st));   // the split sizes are needed on the host for the all-to-all
+  int64_t total = 0;
+  for (int d = 0; d < R.n; ++d) { counts_h[d] = int64_t(h[d]); total += counts_h[d]; }
+  VP_REQUIRE(total <= cap, "vp_slab_bucket: %lld rows needed, capacity %lld", (long long)total, (long long)cap);
+  if (np > 0) {
+    vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * w * sizeof(T) + double(total) * w * sizeof(T));
+    k_bucket_scatter<T><<<nb, 256, 0, st>>>(pos, vel, rho, np, R, cur, rows, w);
+  }
+  VP_CHECK_LAUNCH();
+  VP_CUDA(cudaStreamSynchronize(st));   // cnt/cur live in the scope released on return
+  return VP_OK;
+}
+
 }  // namespace
+
+extern "C" int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                              const double* lo_h, const double* hi_h, int nranks, void* rows_d, int64_t cap_rows, int64_t* counts_h,
+                              void* stream) {
+  VP_REQUIRE(ctx && pos_d && vel_d && lo_h && hi_h && rows_d && counts_h, "vp_slab_bucket: null argument");
+  VP_REQUIRE(nranks >= 1 && nranks <= 16 && np >= 0, "vp_slab_bucket: 1..16 ranks supported");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  SlabRanges R;
+  R.n = nranks;
+  for (int d = 0; d < nranks; ++d) { R.lo[d] = lo_h[d]; R.hi[d] = hi_h[d]; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VP_F32)
+    return slab_bucket_typed<float>(ctx, static_cast<const float*>(pos_d), static_cast<const float*>(vel_d), static_cast<const float*>(rho_d),
+                                    np, R, static_cast<float*>(rows_d), cap_rows, counts_h, st);
+  if (dtype == VP_F64)
+    return slab_bucket_typed<double>(ctx, static_cast<const double*>(pos_d), static_cast<const double*>(vel_d),
+                                     static_cast<const double*>(rho_d), np, R, static_cast<double*>(rows_d), cap_rows, counts_h, st);
+  vp_set_error("vp_slab_bucket: unknown dtype %d", dtype);
+  return VP_ERR_ARG;
+}
 
 size_t vp_host_chunk_staging_bytes(int64_t chunk, int dtype, bool has_rho) {
   const size_t es = dtype == VP_F64 ? 8 : 4;

@@ -25,7 +25,7 @@ class VPowerError(RuntimeError):
 class NNOpts(C.Structure):
     _fields_ = [("cells_x", C.c_int), ("cells_y", C.c_int), ("cells_z", C.c_int), ("use_x_keep", C.c_int),
                 ("x_keep_lo", C.c_double), ("x_keep_hi", C.c_double), ("x_lo_is_domain_edge", C.c_int),
-                ("x_hi_is_domain_edge", C.c_int)]
+                ("x_hi_is_domain_edge", C.c_int), ("row_stride", C.c_int)]
 
 
 _P, _D, _I, _L = C.c_void_p, C.c_double, C.c_int, C.c_int64
@@ -46,6 +46,7 @@ SIGNATURES = {
     "vp_nn_grid_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _P]),
     "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
     "vp_fields_sorted": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
+    "vp_slab_bucket": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, _P, _L, C.POINTER(_L), _P]),
     "vp_gather_rows": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "vp_build_fields": (_I, [_P, _P, _L, _P, _P, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_deposit_ngp": (_I, [_P, _P, _I, _L, _P, _I, _I, _D, _P, _P]),
@@ -172,10 +173,37 @@ def nn_grid(pos_t, qx, qy, qz, opts: NNOpts | None = None):
     return out
 
 
-def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):
-    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, spay[np,4] f32 in cell order)."""
+def slab_bucket(pos_t, vel_t, rho_t, lo, hi):
+    """Sharded input -> rows [n,7|6] grouped by destination rank + counts per rank (see vp_slab_bucket)."""
     torch = _torch()
-    assert pos_t.is_cuda and pos_t.is_contiguous() and vel_t.is_contiguous() and vel_t.dtype == pos_t.dtype
+    P = len(lo)
+    n = pos_t.shape[0]
+    w = 7 if rho_t is not None else 6
+    lo_a, lop = _as_dp(lo)
+    hi_a, hip = _as_dp(hi)
+    cap = n + n // 2 + 1024          # halo duplicates; grown on demand
+    while True:
+        rows = torch.empty((cap, w), dtype=pos_t.dtype, device=pos_t.device)
+        counts = (_L * P)()
+        rc = load_library().vp_slab_bucket(ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()),
+                                           _P(rho_t.data_ptr()) if rho_t is not None else None, _dtype_code(pos_t), n, lop, hip, P,
+                                           _P(rows.data_ptr()), cap, counts, stream_ptr())
+        if rc == 0:
+            break
+        if cap > 3 * n + 4096:
+            _check(rc)
+        cap *= 2
+    counts = [int(c) for c in counts]
+    return rows[:sum(counts)], counts
+
+
+def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):
+    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, spay[np,4] f32 in cell order).
+    With opts.row_stride > 0 the three tensors are column views of one interleaved row tensor."""
+    torch = _torch()
+    assert pos_t.is_cuda and vel_t.dtype == pos_t.dtype
+    if opts is None or opts.row_stride == 0:
+        assert pos_t.is_contiguous() and vel_t.is_contiguous()
     qx_a, qx_p = _as_dp(qx)
     qy_a, qy_p = _as_dp(qy)
     qz_a, qz_p = _as_dp(qz)

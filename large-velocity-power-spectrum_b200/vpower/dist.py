@@ -49,9 +49,14 @@ class CudaBackend:
         o.use_x_keep = 1
         o.x_keep_lo, o.x_keep_hi = float(lo), float(hi)
         o.x_lo_is_domain_edge, o.x_hi_is_domain_edge = int(open_lo), int(open_hi)
+        if pos.stride(0) != 3:          # column views of the interleaved rows that came out of the particle exchange
+            o.row_stride = int(pos.stride(0))
         _, nn_pos, spay = _lib.nn_grid_payload(pos, vel, rho, ax_loc, ax, ax, lcell3, want_idx=False, opts=o)
         st = _lib.nn_grid_stats()
         return (nn_pos, spay), st["n_unresolved"]
+
+    def bucket(self, pos, vel, rho, lo, hi):
+        return _lib.slab_bucket(pos, vel, rho, lo, hi)
 
     def fields(self, gridded, quantity, strict):
         nn_pos, spay = gridded
@@ -74,36 +79,40 @@ class CudaBackend:
         return self.plan.dist_final(recv)
 
 
-def exchange_particles(pos, vel, rho, ax, nranks, rank, halo_cells, group=None):
+def exchange_particles(pos, vel, rho, ax, nranks, rank, halo_cells, group=None, backend=None):
     """Sharded input: every rank holds an arbitrary subset of the particles.  Each particle is sent to the rank(s)
     whose slab + halo contains its x (one all-to-all-v of [pos|vel|rho] rows; a particle inside a halo goes to two
     ranks).  -> (pos, vel, rho) of everything this rank needs.  torch ops only (plumbing around NCCL)."""
     import torch
     import torch.distributed as dist
     N = len(ax)
-    rows = torch.cat([pos, vel] + ([rho[:, None]] if rho is not None else []), dim=1)
-    x = pos[:, 0]
-    parts, counts = [], []
+    los, his = [], []
     for d in range(nranks):
         x0, x1, _, _ = slab_bounds(N, nranks, d)
         lo, hi, open_lo, open_hi = keep_range(ax, x0, x1, nranks, d, halo_cells)
-        m = torch.ones_like(x, dtype=torch.bool)
-        if not open_lo:
-            m &= x >= lo
-        if not open_hi:
-            m &= x <= hi
-        sel = rows[m]
-        parts.append(sel)
-        counts.append(sel.shape[0])
-    send = torch.cat(parts, dim=0).contiguous()
+        los.append(-np.inf if open_lo else lo)
+        his.append(np.inf if open_hi else hi)
+    if backend is not None and hasattr(backend, "bucket"):
+        send, counts = backend.bucket(pos, vel, rho, los, his)          # one counting + one scatter kernel
+    else:                                                               # generic torch form (CPU tests)
+        rows = torch.cat([pos, vel] + ([rho[:, None]] if rho is not None else []), dim=1)
+        x = pos[:, 0]
+        parts, counts = [], []
+        for d in range(nranks):
+            sel = rows[(x >= los[d]) & (x <= his[d])]
+            parts.append(sel)
+            counts.append(sel.shape[0])
+        send = torch.cat(parts, dim=0).contiguous()
+    w = send.shape[1]
     send_counts = torch.tensor(counts, dtype=torch.int64, device=pos.device)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     rc = [int(v) for v in recv_counts.tolist()]
-    w = rows.shape[1]
-    recv = torch.empty((sum(rc), w), dtype=rows.dtype, device=pos.device)
+    recv = torch.empty((sum(rc), w), dtype=send.dtype, device=pos.device)
     dist.all_to_all_single(recv.reshape(-1), send.reshape(-1), output_split_sizes=[c * w for c in rc],
                            input_split_sizes=[c * w for c in counts], group=group)
+    if pos.is_cuda:     # column views: the gridding kernels read the interleaved rows in place (vp_nn_opts.row_stride)
+        return recv[:, 0:3], recv[:, 3:6], (recv[:, 6] if rho is not None else None)
     p, v = recv[:, 0:3].contiguous(), recv[:, 3:6].contiguous()
     r = recv[:, 6].contiguous() if rho is not None else None
     return p, v, r
@@ -127,14 +136,24 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
     if max_halo_cells is None:
         max_halo_cells = N
     shard = (pos, vel, rho)
+    marks = []
+
+    def mark(name):
+        if timings is not None and isinstance(pos, torch.Tensor) and pos.is_cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
 
     # ---- K1 on the slab; widen the halo until every node is proven (rarely more than once)
     halo = halo_cells
     while True:
+        mark("start")
         if sharded and nranks > 1:
-            pos, vel, rho = exchange_particles(*shard, ax, nranks, rank, halo, group)
+            pos, vel, rho = exchange_particles(*shard, ax, nranks, rank, halo, group, backend)
+        mark("exchange_particles")
         gridded, unresolved = backend.grid_slab(pos, vel, rho, ax[x0:x1], ax, lcell3,
                                                 keep_range(ax, x0, x1, nranks, rank, halo))
+        mark("grid_slab")
         flag = torch.tensor([int(unresolved > 0)], dtype=torch.int64, device=_device_of(pos))
         if nranks > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
@@ -151,6 +170,7 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
     for q in quantities:
         slabs, mult = backend.fields(gridded, q, momentum_strict)
         send = backend.fft_local(slabs)                              # [P, nx, N, kzc] complex64 per component
+        mark("fields+fft_local")
         recv = []
         for s in send:
             r = torch.empty_like(s)
@@ -159,12 +179,21 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
             else:
                 r.copy_(s)
             recv.append(r.reshape(N, N, -1))                         # [x][ky][kz_local]
+        mark("all_to_all")
         psum, ns = backend.fft_final(recv)
+        mark("fft_final")
         if nranks > 1:
             dist.all_reduce(psum, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(ns, op=dist.ReduceOp.SUM, group=group)
         out[q] = psum.cpu().numpy() * (mult * norm)
         ns_total = ns.cpu().numpy().astype(np.int64)
+        mark("all_reduce+d2h")
+    if marks:
+        torch.cuda.synchronize()
+        acc = {}
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            acc[name] = acc.get(name, 0.0) + a.elapsed_time(b)
+        timings["phases_ms"] = acc
     return out, ns_total
 
 

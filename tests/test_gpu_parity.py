@@ -427,3 +427,30 @@ def test_host_chunk_streaming_equals_device_path(lib, orc):
     assert np.array_equal(ns, ref_ns)
     for q in qs:
         assert np.array_equal(out[q], ref[q])
+
+
+def test_slab_bucket_kernel(lib):
+    """vp_slab_bucket: every particle lands (once) in the block of each rank whose kept range contains it."""
+    import torch
+    n = 200003
+    g = torch.Generator(device="cuda").manual_seed(9)
+    pos = torch.rand((n, 3), generator=g, device="cuda")
+    vel = torch.randn((n, 3), generator=g, device="cuda")
+    rho = torch.rand(n, generator=g, device="cuda")
+    lo = [-np.inf, 0.2, 0.45, 0.7]
+    hi = [0.3, 0.55, 0.8, np.inf]
+    rows, counts = lib.slab_bucket(pos, vel, rho, lo, hi)
+    x = pos[:, 0].cpu().numpy()
+    ref = torch.cat([pos, vel, rho[:, None]], 1).cpu().numpy()
+    got = rows.cpu().numpy()
+    at = 0
+    for d in range(4):
+        m = (x >= lo[d]) & (x <= hi[d])
+        assert counts[d] == int(m.sum())
+        blk = got[at:at + counts[d]]
+        at += counts[d]
+        a = blk[np.lexsort(blk.T[::-1])]
+        b = ref[m][np.lexsort(ref[m].T[::-1])]
+        assert np.array_equal(a, b)
+    rows6, counts6 = lib.slab_bucket(pos, vel, None, lo, hi)
+    assert counts6 == counts and rows6.shape[1] == 6
