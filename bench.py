@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-to-all instead of the fused peer-store transpose")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -190,7 +191,7 @@ def main():
 
     if world > 1:
         from vpower import dist as vd
-        backend = vd.CudaBackend(N, k, edges, world, rank)
+        backend = vd.CudaBackend(N, k, edges, world, rank, p2p=not args.no_p2p)
         # sharded input: rank r owns particles [r*Np/P, (r+1)*Np/P) of the synthetic set; the slab exchange is timed
         lo_i, hi_i = rank * (Np // world), (rank + 1) * (Np // world)
         pos, vel, rho = pos[lo_i:hi_i].clone(), vel[lo_i:hi_i].clone(), rho[lo_i:hi_i].clone()

@@ -172,6 +172,19 @@ int vp_pk_plan_create_dist(vp_ctx* ctx, int N, int nranks, int rank, const doubl
 int vp_pk_dist_local(vp_pk_plan* plan, float* const* field_d, int ncomp, float* const* send_d, void* stream);
 int vp_pk_dist_final(vp_pk_plan* plan, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream);
 
+/* The same exchange FUSED into the y pass (no NCCL call on the data path): every rank allocates its receive buffers
+ * inside the plan and exports them through CUDA IPC; after the handles of all ranks have been gathered (any transport:
+ * the Python mirror uses torch.distributed.all_gather) and opened, the y-pass kernel stores every tile straight into
+ * the receive buffer of the rank that owns its kz columns -- local HBM for its own block, NVLink peer stores for the
+ * others.  The caller separates the passes with a stream-ordered barrier across ranks (a tiny NCCL all-reduce):
+ *   local_p2p (all ranks)  ->  barrier  ->  final_p2p  ->  all-reduce of the shells (doubles as the barrier that
+ *   protects the receive buffers from the next quantity's stores).
+ *   handles_out : ncomp_max * 64 bytes;   all_handles : [nranks][ncomp_max][64] bytes in rank order. */
+int vp_pk_dist_p2p_alloc(vp_pk_plan* plan, int ncomp_max, unsigned char* handles_out);
+int vp_pk_dist_p2p_open(vp_pk_plan* plan, const unsigned char* all_handles);
+int vp_pk_dist_local_p2p(vp_pk_plan* plan, float* const* field_d, int ncomp, void* stream);
+int vp_pk_dist_final_p2p(vp_pk_plan* plan, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream);
+
 /* Sharded particle input for the slab decomposition: every particle of this rank's subset is copied into the block of
  * each destination rank d whose kept range lo_h[d] <= x <= hi_h[d] contains it (use -/+ infinity for open ends).
  *   rows_d   [cap_rows, 7 (6 without rho)] of dtype: x y z vx vy vz rho, blocks in rank order;  counts_h[d] = rows for rank d.

@@ -27,6 +27,12 @@ struct vp_pk_plan {
   // and half-spectrum columns kz in [rank*kzc, (rank+1)*kzc) after it
   int nranks = 1, rank = 0;
   int kzc = 0;                // N/2/nranks
+  // peer-to-peer transpose: receive buffers [N][N][kzc] complex64 per component, allocated here (cudaMalloc, exported
+  // through CUDA IPC) and the same buffers of every other rank mapped into this process
+  int p2p_ncomp = 0;
+  float2* recv[3] = {nullptr, nullptr, nullptr};
+  float2* peer[3][16];        // peer[c][d]: rank d's recv[c] (own pointer for d == rank)
+  bool peer_open = false;
 };
 
 namespace {
@@ -77,11 +83,19 @@ __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const f
 }
 
 // ------------------------------------------------------------------ y pass: lines strided by NZ, C columns per CTA
-// `out` may be the input itself (single GPU, in place) or the all-to-all send buffer laid out
-// [dest rank][x_local][ky][kzc]: the transpose packing is fused into the store of this pass.
+// Destination of the y pass.  base[d] + (xoff + x_local)*N*kzc + ky*kzc + (kz - d*kzc):
+//   single GPU, in place      : base[0] = the field itself, xoff = 0, kzc = N/2
+//   NCCL exchange             : base[d] = send buffer block d ([dest][x_local][ky][kzc]), xoff = 0
+//   peer-to-peer (fused)      : base[d] = rank d's receive buffer mapped through CUDA IPC, xoff = rank*N/nranks --
+//                               the tile is stored over NVLink where the x pass of rank d will read it
+struct YDest {
+  float2* base[16];
+  int xoff;
+};
+
 template <int R2, int R3, int C>
-__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_y(const float2* __restrict__ data, float2* __restrict__ out,
-                                                                                   int nx, int NZ, int kzc, const float2* __restrict__ tw) {
+__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_y(const float2* __restrict__ data, YDest dst, int NZ, int kzc,
+                                                                                   const float2* __restrict__ tw) {
   using F = LineFFT<R2, R3, C>;
   constexpr int L = F::L, T = F::T;
   extern __shared__ float2 sm[];
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * NZ];
   F::run(v, t, sm + c, tw);
   const int kz0 = zt * C, d = kz0 / kzc;
-  float2* ob = out + (size_t(d) * nx + x) * L * kzc + (kz0 - d * kzc) + c;
+  float2* ob = dst.base[d] + (size_t(dst.xoff) + x) * L * kzc + (kz0 - d * kzc) + c;
 #pragma unroll
   for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * kzc] = v[j];
 }
@@ -383,7 +397,7 @@ int launch_z(float* data, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) 
 }
 
 template <int R2, int R3, int C>
-int launch_y(const float2* data, float2* out, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
+int launch_y(const float2* data, const YDest& dst, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
   size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2);
   static bool attr = false;
@@ -391,7 +405,7 @@ int launch_y(const float2* data, float2* out, int N, int nx, int kzc, const vp_p
   const int NZ = N / 2;
   VP_REQUIRE(kzc % C == 0, "fft y pass: %d columns per rank is not a multiple of the tile width %d", kzc, C);
   vp_stage stage(pl->ctx, "k4b_fft_y", st, 1, 8.0 * double(nx) * N * N);   // 8 B/mode read + written, nx*N*N/2 modes
-  k_fft_y<R2, R3, C><<<unsigned(nx * (NZ / C)), F::T * C, smem, st>>>(data, out, nx, NZ, kzc, pl->tw_full);
+  k_fft_y<R2, R3, C><<<unsigned(nx * (NZ / C)), F::T * C, smem, st>>>(data, dst, NZ, kzc, pl->tw_full);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
@@ -449,17 +463,24 @@ int run_z(float* d, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
   vp_set_error("fft z pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
 }
-int run_y(const float2* d, float2* out, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
+int run_y(const float2* d, const YDest& dst, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_y<4, 1, 32>(d, out, N, nx, kzc, pl, st);
-    case 128: return launch_y<8, 1, 32>(d, out, N, nx, kzc, pl, st);
-    case 256: return launch_y<16, 1, 16>(d, out, N, nx, kzc, pl, st);
-    case 512: return launch_y<16, 2, 8>(d, out, N, nx, kzc, pl, st);
-    case 1024: return launch_y<16, 4, 8>(d, out, N, nx, kzc, pl, st);
-    case 2048: return launch_y<16, 8, 8>(d, out, N, nx, kzc, pl, st);
+    case 64: return launch_y<4, 1, 32>(d, dst, N, nx, kzc, pl, st);
+    case 128: return launch_y<8, 1, 32>(d, dst, N, nx, kzc, pl, st);
+    case 256: return launch_y<16, 1, 16>(d, dst, N, nx, kzc, pl, st);
+    case 512: return launch_y<16, 2, 8>(d, dst, N, nx, kzc, pl, st);
+    case 1024: return launch_y<16, 4, 8>(d, dst, N, nx, kzc, pl, st);
+    case 2048: return launch_y<16, 8, 8>(d, dst, N, nx, kzc, pl, st);
   }
   vp_set_error("fft y pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
+}
+// destinations for the two single-buffer forms
+YDest ydest_blocks(float2* out, int nranks, int nx, int N, int kzc) {
+  YDest d;
+  for (int r = 0; r < 16; ++r) d.base[r] = r < nranks ? out + size_t(r) * nx * N * kzc : nullptr;
+  d.xoff = 0;
+  return d;
 }
 int run_x_bin(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   switch (N) {
@@ -583,6 +604,12 @@ extern "C" int vp_pk_plan_destroy(vp_pk_plan* p) {
   if (p->kk2) cudaFree(p->kk2);
   if (p->thr) cudaFree(p->thr);
   if (p->plane0) cudaFree(p->plane0);
+  for (int c = 0; c < 3; ++c) {
+    if (p->peer_open)
+      for (int d = 0; d < p->nranks; ++d)
+        if (d != p->rank && p->peer[c][d]) cudaIpcCloseMemHandle(p->peer[c][d]);
+    if (p->recv[c]) cudaFree(p->recv[c]);
+  }
   delete p;
   return VP_OK;
 }
@@ -648,7 +675,7 @@ extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, do
   for (int c = 0; c < ncomp; ++c) {
     VP_REQUIRE(field_d[c], "vp_pk_fields: null field %d", c);
     VP_TRY(run_z(field_d[c], N, N, pl, st));
-    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), reinterpret_cast<float2*>(field_d[c]), N, N, N / 2, pl, st));
+    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), ydest_blocks(reinterpret_cast<float2*>(field_d[c]), 1, N, N, N / 2), N, N, N / 2, pl, st));
     fs.f[c] = reinterpret_cast<float2*>(field_d[c]);
   }
   VP_TRY(run_x_bin(fs, N, N / 2, 0, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
@@ -688,7 +715,8 @@ extern "C" int vp_pk_dist_local(vp_pk_plan* pl, float* const* field_d, int ncomp
   for (int c = 0; c < ncomp; ++c) {
     VP_REQUIRE(field_d[c] && send_d[c], "vp_pk_dist_local: null buffer %d", c);
     VP_TRY(run_z(field_d[c], N, nx, pl, st));
-    VP_TRY(run_y(reinterpret_cast<const float2*>(field_d[c]), reinterpret_cast<float2*>(send_d[c]), N, nx, pl->kzc, pl, st));
+    VP_TRY(run_y(reinterpret_cast<const float2*>(field_d[c]), ydest_blocks(reinterpret_cast<float2*>(send_d[c]), pl->nranks, nx, N, pl->kzc), N, nx,
+                 pl->kzc, pl, st));
   }
   return VP_OK;
 }
@@ -714,12 +742,73 @@ extern "C" int vp_pk_dist_final(vp_pk_plan* pl, float* const* recv_d, int ncomp,
   return VP_OK;
 }
 
+// ---- peer-to-peer transpose (the exchange fused into the y pass)
+extern "C" int vp_pk_dist_p2p_alloc(vp_pk_plan* pl, int ncomp_max, unsigned char* handles_out) {
+  VP_REQUIRE(pl && handles_out && ncomp_max >= 1 && ncomp_max <= 3, "vp_pk_dist_p2p_alloc: bad argument");
+  VP_REQUIRE(pl->pow2 && pl->nranks <= 16, "vp_pk_dist_p2p_alloc: needs the power-of-two path and <= 16 ranks");
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  const size_t bytes = sizeof(float2) * size_t(pl->N) * pl->N * pl->kzc;
+  for (int c = 0; c < 3; ++c)
+    for (int d = 0; d < 16; ++d) pl->peer[c][d] = nullptr;
+  for (int c = 0; c < ncomp_max; ++c) {
+    if (!pl->recv[c]) VP_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl->recv[c]), bytes));
+    cudaIpcMemHandle_t h;
+    VP_CUDA(cudaIpcGetMemHandle(&h, pl->recv[c]));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles_out + size_t(c) * 64, &h, 64);
+    pl->peer[c][pl->rank] = pl->recv[c];
+  }
+  pl->p2p_ncomp = ncomp_max;
+  return VP_OK;
+}
+
+extern "C" int vp_pk_dist_p2p_open(vp_pk_plan* pl, const unsigned char* all_handles) {
+  VP_REQUIRE(pl && all_handles && pl->p2p_ncomp > 0, "vp_pk_dist_p2p_open: call vp_pk_dist_p2p_alloc first");
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  for (int d = 0; d < pl->nranks; ++d) {
+    if (d == pl->rank) continue;
+    for (int c = 0; c < pl->p2p_ncomp; ++c) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all_handles + (size_t(d) * pl->p2p_ncomp + c) * 64, 64);
+      void* p = nullptr;
+      VP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      pl->peer[c][d] = static_cast<float2*>(p);
+    }
+  }
+  pl->peer_open = true;
+  return VP_OK;
+}
+
+extern "C" int vp_pk_dist_local_p2p(vp_pk_plan* pl, float* const* field_d, int ncomp, void* stream) {
+  VP_REQUIRE(pl && field_d && ncomp >= 1 && ncomp <= pl->p2p_ncomp, "vp_pk_dist_local_p2p: bad argument");
+  VP_REQUIRE(pl->nranks == 1 || pl->peer_open, "vp_pk_dist_local_p2p: peer buffers not opened");
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = pl->N, nx = N / pl->nranks;
+  for (int c = 0; c < ncomp; ++c) {
+    VP_REQUIRE(field_d[c], "vp_pk_dist_local_p2p: null field %d", c);
+    VP_TRY(run_z(field_d[c], N, nx, pl, st));
+    YDest dst;
+    for (int d = 0; d < 16; ++d) dst.base[d] = d < pl->nranks ? pl->peer[c][d] : nullptr;
+    dst.xoff = pl->rank * nx;
+    VP_TRY(run_y(reinterpret_cast<const float2*>(field_d[c]), dst, N, nx, pl->kzc, pl, st));
+  }
+  return VP_OK;
+}
+
+extern "C" int vp_pk_dist_final_p2p(vp_pk_plan* pl, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
+  VP_REQUIRE(pl && ncomp >= 1 && ncomp <= pl->p2p_ncomp, "vp_pk_dist_final_p2p: bad argument");
+  float* r[3] = {reinterpret_cast<float*>(pl->recv[0]), reinterpret_cast<float*>(pl->recv[1]), reinterpret_cast<float*>(pl->recv[2])};
+  return vp_pk_dist_final(pl, r, ncomp, psum_d, nsample_d, stream);
+}
+
 extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) {
   VP_REQUIRE(pl && field_d, "vp_fft_r2c_inplace: null argument");
   if (!pl->pow2) { vp_set_error("vp_fft_r2c_inplace: N=%d has no packed fast path", pl->N); return VP_ERR_UNSUPPORTED; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VP_TRY(run_z(field_d, pl->N, pl->N, pl, st));
-  VP_TRY(run_y(reinterpret_cast<float2*>(field_d), reinterpret_cast<float2*>(field_d), pl->N, pl->N, pl->N / 2, pl, st));
+  VP_TRY(run_y(reinterpret_cast<float2*>(field_d), ydest_blocks(reinterpret_cast<float2*>(field_d), 1, pl->N, pl->N, pl->N / 2), pl->N, pl->N,
+               pl->N / 2, pl, st));
   return run_x(reinterpret_cast<float2*>(field_d), pl->N, pl, st);
 }
 

@@ -55,6 +55,10 @@ SIGNATURES = {
     "vp_pk_plan_create_dist": (_I, [_P, _I, _I, _I, _dp, _dp, _I, C.POINTER(_P)]),
     "vp_pk_dist_local": (_I, [_P, C.POINTER(_P), _I, C.POINTER(_P), _P]),
     "vp_pk_dist_final": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
+    "vp_pk_dist_p2p_alloc": (_I, [_P, _I, C.c_char_p]),
+    "vp_pk_dist_p2p_open": (_I, [_P, C.c_char_p]),
+    "vp_pk_dist_local_p2p": (_I, [_P, C.POINTER(_P), _I, _P]),
+    "vp_pk_dist_final_p2p": (_I, [_P, _I, _P, _P, _P]),
     "vp_pk_fields": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
     "vp_fft_r2c_inplace": (_I, [_P, _P, _P]),
     "vp_fft_unpack_half": (_I, [_P, _P, _P, _P]),
@@ -320,6 +324,30 @@ class PkPlan:
         sp = (_P * len(slabs))(*[s.data_ptr() for s in send])
         _check(load_library().vp_pk_dist_local(self._h, fp, len(slabs), sp, stream_ptr()))
         return send
+
+    def p2p_setup(self, group=None, ncomp_max=3):
+        """Allocate the receive buffers in the plan, exchange their CUDA IPC handles, map every peer's buffers."""
+        torch = _torch()
+        import torch.distributed as dist
+        buf = C.create_string_buffer(64 * ncomp_max)
+        _check(load_library().vp_pk_dist_p2p_alloc(self._h, ncomp_max, buf))
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(allh, mine, group=group)
+        raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        _check(load_library().vp_pk_dist_p2p_open(self._h, raw))
+        self.p2p = True
+
+    def dist_local_p2p(self, slabs):
+        fp = (_P * len(slabs))(*[s.data_ptr() for s in slabs])
+        _check(load_library().vp_pk_dist_local_p2p(self._h, fp, len(slabs), stream_ptr()))
+
+    def dist_final_p2p(self, ncomp, device):
+        torch = _torch()
+        psum = torch.empty(self.nbins, dtype=torch.float64, device=device)
+        ns = torch.empty(self.nbins, dtype=torch.int64, device=device)
+        _check(load_library().vp_pk_dist_final_p2p(self._h, ncomp, _P(psum.data_ptr()), _P(ns.data_ptr()), stream_ptr()))
+        return psum, ns
 
     def dist_final(self, recv):
         """recv: 1..3 complex64 CUDA tensors [N, N, N/2/nranks] -> partial (psum, nsample) CUDA tensors."""

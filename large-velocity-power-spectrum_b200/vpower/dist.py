@@ -40,8 +40,11 @@ def keep_range(ax, x0, x1, nranks, rank, halo_cells):
 class CudaBackend:
     """The product path: hand-written kernels behind the C ABI."""
 
-    def __init__(self, N, k_axis, edges, nranks, rank):
+    def __init__(self, N, k_axis, edges, nranks, rank, p2p=False, group=None):
         self.plan = _lib.PkPlan(N, k_axis, edges, nranks=nranks, rank=rank)
+        self.p2p = bool(p2p) and nranks > 1
+        if self.p2p:       # the exchange is fused into the y pass: peer stores over NVLink instead of an NCCL all-to-all
+            self.plan.p2p_setup(group)
 
     def grid_slab(self, pos, vel, rho, ax_loc, ax, lcell3, keep):
         lo, hi, open_lo, open_hi = keep
@@ -169,6 +172,22 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
     ns_total = None
     for q in quantities:
         slabs, mult = backend.fields(gridded, q, momentum_strict)
+        if getattr(backend, "p2p", False):
+            # fused exchange: the y pass stores into every rank's receive buffer; a stream-ordered tiny all-reduce is
+            # the barrier between "all ranks have written" and "this rank reads"
+            backend.plan.dist_local_p2p(slabs)
+            mark("fields+fft_local")
+            tok = torch.zeros(1, device=slabs[0].device)
+            dist.all_reduce(tok, group=group)
+            mark("all_to_all")
+            psum, ns = backend.plan.dist_final_p2p(len(slabs), slabs[0].device)
+            mark("fft_final")
+            dist.all_reduce(psum, op=dist.ReduceOp.SUM, group=group)      # also protects the buffers from the next stores
+            dist.all_reduce(ns, op=dist.ReduceOp.SUM, group=group)
+            out[q] = psum.cpu().numpy() * (mult * norm)
+            ns_total = ns.cpu().numpy().astype(np.int64)
+            mark("all_reduce+d2h")
+            continue
         send = backend.fft_local(slabs)                              # [P, nx, N, kzc] complex64 per component
         mark("fields+fft_local")
         recv = []
