@@ -100,6 +100,29 @@ def synth_on_device(torch, Np, seed, L=1.0):
     return pos, vel, rho
 
 
+def synth_clustered_on_device(torch, n_lat, seed, L=1.0, rms_cells=2.0):
+    """cfg3: n_lat^3 lattice particles displaced by a sum of long-wave sinusoids (Zel'dovich-like), rms ~2 cells:
+    voids and dense sheets -> exercises the wide stages of the nearest-particle search."""
+    rs = np.random.default_rng(seed)
+    g1 = (torch.arange(n_lat, device="cuda", dtype=torch.float32) + 0.5) / n_lat
+    q = torch.stack(torch.meshgrid(g1, g1, g1, indexing="ij"), dim=-1).reshape(-1, 3)
+    disp = torch.zeros_like(q)
+    for _ in range(64):     # wavenumbers up to 48: displacement gradients of order one -> shell crossing, voids, sheets
+        kv = torch.tensor(rs.integers(1, 49, size=3) * rs.choice([-1, 1], size=3), device="cuda", dtype=torch.float32)
+        kk = float(torch.linalg.norm(kv))
+        ph = float(rs.uniform(0, 2 * np.pi))
+        disp += (1.0 / kk) * (kv / kk)[None, :] * torch.sin(2 * np.pi * (q @ kv) + ph)[:, None]
+    disp *= (rms_cells / n_lat) / float(torch.sqrt((disp ** 2).sum(1).mean()))
+    pos = torch.remainder(q + disp, 1.0) * L
+    del q, disp
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99 + seed)
+    Np = pos.shape[0]
+    vel = torch.randn((Np, 3), generator=g, device="cuda", dtype=torch.float32)
+    rho = (Np / L ** 3) * (1.0 + 0.1 * torch.rand(Np, generator=g, device="cuda", dtype=torch.float32))
+    return pos.contiguous(), vel, rho
+
+
 def geometry(orc_like, N, L):
     Lcell = L / N
     ax = np.linspace(Lcell / 2, L + Lcell / 2, N)                         # library lattice, interp.py:1063
@@ -186,7 +209,10 @@ def main():
     ax, k, edges, lc3, norm = geometry(None, N, L)
     hbm_peak, peak_src = peaks()
 
-    pos, vel, rho = synth_on_device(torch, Np, seed=3)
+    if wname == "cfg3":
+        pos, vel, rho = synth_clustered_on_device(torch, round(Np ** (1 / 3)), seed=2)
+    else:
+        pos, vel, rho = synth_on_device(torch, Np, seed=3)
     torch.cuda.synchronize()
 
     if world > 1:
@@ -294,7 +320,7 @@ def main():
                 "config": {"workload": f"{wname}: {N}^3 lattice, {Np} particles (2^{int(np.log2(Np))}), velocity+momentum+energy P(k), "
                                        f"library lattice and edges", "l2": "inputs larger than L2" if Np * 28 > 2e8 else "inputs fit L2",
                            "momentum": "reference-strict (vx*m x3)"},
-                "seconds_per_pk": ms * 1e-3, "nn_gridding_gpart_s": None, "gpu_launches": int(launches),
+                "nn_stats": _lib.nn_grid_stats() if world == 1 else None, "seconds_per_pk": ms * 1e-3, "nn_gridding_gpart_s": None, "gpu_launches": int(launches),
                 "roofline": roof, "stages": table, "dist_phases_ms_last_step": phase_t.get("phases_ms"), "cpu_baseline": cpu, "e2e": e2e, "clocks": clk.summary()}
         nn_ms = sum(table[n]["ms_per_step"] for n in table if n.startswith("k1"))
         if nn_ms > 0:
