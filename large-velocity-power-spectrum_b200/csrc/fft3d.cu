@@ -141,7 +141,7 @@ __device__ __forceinline__ int first_row_at_or_above(const double* wrow, int nr,
 }
 
 template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
-__global__ void __launch_bounds__(R2* R3* C) k_fft_x_bin(FieldSet fs, int NZ, const float2* __restrict__ tw,
+__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 256 ? 2 : 1)) k_fft_x_bin(FieldSet fs, int NZ, const float2* __restrict__ tw,
                                                          const double* __restrict__ kk2, const double* __restrict__ thr_g,
                                                          int nbins, float inv_kf, float2* __restrict__ plane0, int kz_offset,
                                                          double* __restrict__ psum_g, unsigned long long* __restrict__ cnt_g) {
