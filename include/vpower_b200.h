@@ -194,6 +194,19 @@ int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void
                    const double* lo_h, const double* hi_h, int nranks, void* rows_d, int64_t cap_rows, int64_t* counts_h,
                    void* stream);
 
+/* The same exchange FUSED into the bucketing kernel: each rank owns a receive buffer (allocated here, exported with CUDA
+ * IPC, mapped by every peer); after vp_slab_count and an exchange of the counts (any transport) every rank knows the
+ * first row it may write in each destination's buffer, and vp_slab_scatter_p2p stores the rows there directly (own HBM
+ * or NVLink peer stores).  The caller separates "all ranks have stored" from "this rank reads" with a stream-ordered
+ * barrier across ranks.  Rows of one destination arrive grouped by source rank, in rank order. */
+int vp_slab_p2p_alloc(vp_ctx* ctx, size_t bytes, unsigned char* handle_out /* 64 bytes */);
+int vp_slab_p2p_open(vp_ctx* ctx, int nranks, int rank, const unsigned char* all_handles /* [nranks][64] */);
+int vp_slab_p2p_buffer(vp_ctx* ctx, void** ptr_out, size_t* bytes_out);
+int vp_slab_count(vp_ctx* ctx, const void* pos_d, int dtype, int64_t np, const double* lo_h, const double* hi_h, int nranks,
+                  int64_t* counts_h, void* stream);                                            /* syncs */
+int vp_slab_scatter_p2p(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                        const double* lo_h, const double* hi_h, int nranks, const int64_t* first_row_h, void* stream);
+
 /* Test/diagnostic entry points */
 /* In-place 3-D r2c transform only.  Output layout: [N][N][N/2] complex64 where entry (x,y,0) packs
  * (Re F(x,y,0), Re F_zNyquist-line ...) -- see DESIGN.md "half-spectrum layout"; use

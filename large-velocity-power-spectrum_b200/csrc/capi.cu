@@ -55,6 +55,10 @@ extern "C" int vp_ctx_destroy(vp_ctx* ctx) {
   if (ctx->nn_stats_d) cudaFree(ctx->nn_stats_d);
   if (ctx->small_d) cudaFree(ctx->small_d);
   if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
+  if (ctx->slab_open)
+    for (int d = 0; d < ctx->slab_nranks; ++d)
+      if (d != ctx->slab_rank && ctx->slab_peer[d]) cudaIpcCloseMemHandle(ctx->slab_peer[d]);
+  if (ctx->slab_recv) cudaFree(ctx->slab_recv);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);

@@ -77,6 +77,12 @@ struct vp_ctx {
   size_t small_cap = 0;
   void* pinned_h = nullptr;               // pinned staging for small host->device tables
   size_t pinned_cap = 0;
+  // sharded particle exchange over peer memory (vp_slab_p2p_*): this rank's receive buffer and every peer's, mapped
+  void* slab_recv = nullptr;
+  size_t slab_recv_bytes = 0;
+  void* slab_peer[16] = {nullptr};
+  int slab_nranks = 0, slab_rank = 0;
+  bool slab_open = false;
   cudaStream_t copy_stream = nullptr;     // host-buffer entry point: H2D chunks overlap the keygen/pack kernel
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
 };

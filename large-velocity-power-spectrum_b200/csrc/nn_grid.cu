@@ -838,11 +838,15 @@ __global__ void __launch_bounds__(256) k_bucket_count(const T* __restrict__ pos,
   if (threadIdx.x < R.n && sc[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
 }
 
-// rows = [x y z vx vy vz (rho)] ; cursors[d] starts at the exclusive prefix of counts
+// rows = [x y z vx vy vz (rho)] ; cursors[d] starts at the first row this rank may write in destination d's buffer
+// (exclusive prefix of counts for the single local buffer; with peer stores, the rows of lower ranks for d).
+struct SlabDest {
+  void* base[16];   // all equal for the local form; peer-mapped receive buffers for the fused exchange
+};
 template <typename T>
 __global__ void __launch_bounds__(256) k_bucket_scatter(const T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ rho,
                                                          int64_t np, SlabRanges R, unsigned long long* __restrict__ cursors,
-                                                         T* __restrict__ rows, int w) {
+                                                         SlabDest D, int w) {
   __shared__ unsigned sc[16];
   __shared__ unsigned long long sbase[16];
   if (threadIdx.x < 16) sc[threadIdx.x] = 0;
@@ -875,7 +879,7 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const T* __restrict__ po
 #pragma unroll
   for (int d = 0; d < 16; ++d) {
     if (d < R.n && myoff[d] != 0xffffffffu) {
-      T* o = rows + (sbase[d] + myoff[d]) * size_t(w);
+      T* o = static_cast<T*>(D.base[d]) + (sbase[d] + myoff[d]) * size_t(w);
       for (int c = 0; c < w; ++c) o[c] = r[c];
     }
   }
@@ -912,14 +916,136 @@ int slab_bucket_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int
   VP_REQUIRE(total <= cap, "vp_slab_bucket: %lld rows needed, capacity %lld", (long long)total, (long long)cap);
   if (np > 0) {
     vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * w * sizeof(T) + double(total) * w * sizeof(T));
-    k_bucket_scatter<T><<<nb, 256, 0, st>>>(pos, vel, rho, np, R, cur, rows, w);
+    SlabDest D;
+    for (int d = 0; d < 16; ++d) D.base[d] = rows;
+    k_bucket_scatter<T><<<nb, 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
   }
   VP_CHECK_LAUNCH();
   VP_CUDA(cudaStreamSynchronize(st));   // cnt/cur live in the scope released on return
   return VP_OK;
 }
 
+template <typename T>
+int slab_count_typed(vp_ctx* ctx, const T* pos, int64_t np, const SlabRanges& R, int64_t* counts_h, cudaStream_t st) {
+  vp_arena_scope scope(ctx);
+  VP_TRY(vp_arena_reserve(ctx, 1024));
+  unsigned long long* cnt = static_cast<unsigned long long*>(vp_arena_alloc(ctx, 256));
+  VP_REQUIRE(cnt, "vp_slab_count: arena carve failed");
+  VP_CUDA(cudaMemsetAsync(cnt, 0, 256, st));
+  if (np > 0) {
+    vp_stage stage(ctx, "k0_slab_bucket_count", st, 1, double(np) * 3.0 * sizeof(T));
+    k_bucket_count<T><<<unsigned((np + 255) / 256), 256, 0, st>>>(pos, np, R, cnt);
+  }
+  unsigned long long h[16];
+  VP_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+  VP_CUDA(cudaStreamSynchronize(st));
+  for (int d = 0; d < R.n; ++d) counts_h[d] = int64_t(h[d]);
+  return VP_OK;
+}
+
+template <typename T>
+int slab_scatter_p2p_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int64_t np, const SlabRanges& R,
+                           const int64_t* first_row_h, cudaStream_t st) {
+  vp_arena_scope scope(ctx);
+  VP_TRY(vp_arena_reserve(ctx, 1024));
+  unsigned long long* cur = static_cast<unsigned long long*>(vp_arena_alloc(ctx, 256));
+  VP_REQUIRE(cur, "vp_slab_scatter_p2p: arena carve failed");
+  unsigned long long h[16];
+  for (int d = 0; d < 16; ++d) h[d] = d < R.n ? (unsigned long long)first_row_h[d] : 0ull;
+  VP_CUDA(cudaMemcpyAsync(cur, h, sizeof h, cudaMemcpyHostToDevice, st));
+  const int w = rho ? 7 : 6;
+  if (np > 0) {
+    vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * 2.0 * w * sizeof(T));
+    SlabDest D;
+    for (int d = 0; d < 16; ++d) D.base[d] = d < R.n ? ctx->slab_peer[d] : nullptr;
+    k_bucket_scatter<T><<<unsigned((np + 255) / 256), 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
+    VP_CHECK_LAUNCH();
+  }
+  VP_CUDA(cudaStreamSynchronize(st));   // cur lives in the scope released on return
+  return VP_OK;
+}
+
 }  // namespace
+
+// ---- sharded particle exchange fused into the bucketing kernel (peer stores over NVLink)
+extern "C" int vp_slab_p2p_alloc(vp_ctx* ctx, size_t bytes, unsigned char* handle_out) {
+  VP_REQUIRE(ctx && handle_out && bytes > 0, "vp_slab_p2p_alloc: bad argument");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  VP_CUDA(cudaDeviceSynchronize());
+  if (ctx->slab_open) {
+    for (int d = 0; d < ctx->slab_nranks; ++d)
+      if (d != ctx->slab_rank && ctx->slab_peer[d]) { cudaIpcCloseMemHandle(ctx->slab_peer[d]); ctx->slab_peer[d] = nullptr; }
+    ctx->slab_open = false;
+  }
+  if (ctx->slab_recv) { VP_CUDA(cudaFree(ctx->slab_recv)); ctx->slab_recv = nullptr; }
+  VP_CUDA(cudaMalloc(&ctx->slab_recv, bytes));
+  ctx->slab_recv_bytes = bytes;
+  cudaIpcMemHandle_t h;
+  VP_CUDA(cudaIpcGetMemHandle(&h, ctx->slab_recv));
+  memcpy(handle_out, &h, 64);
+  return VP_OK;
+}
+
+extern "C" int vp_slab_p2p_open(vp_ctx* ctx, int nranks, int rank, const unsigned char* all_handles) {
+  VP_REQUIRE(ctx && all_handles && ctx->slab_recv && nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks,
+             "vp_slab_p2p_open: bad argument");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  for (int d = 0; d < nranks; ++d) {
+    if (d == rank) { ctx->slab_peer[d] = ctx->slab_recv; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + size_t(d) * 64, 64);
+    void* p = nullptr;
+    VP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->slab_peer[d] = p;
+  }
+  ctx->slab_nranks = nranks;
+  ctx->slab_rank = rank;
+  ctx->slab_open = true;
+  return VP_OK;
+}
+
+extern "C" int vp_slab_p2p_buffer(vp_ctx* ctx, void** ptr_out, size_t* bytes_out) {
+  VP_REQUIRE(ctx && ptr_out && bytes_out, "vp_slab_p2p_buffer: bad argument");
+  *ptr_out = ctx->slab_recv;
+  *bytes_out = ctx->slab_recv_bytes;
+  return VP_OK;
+}
+
+static SlabRanges make_ranges(const double* lo_h, const double* hi_h, int nranks) {
+  SlabRanges R;
+  R.n = nranks;
+  for (int d = 0; d < nranks; ++d) { R.lo[d] = lo_h[d]; R.hi[d] = hi_h[d]; }
+  return R;
+}
+
+extern "C" int vp_slab_count(vp_ctx* ctx, const void* pos_d, int dtype, int64_t np, const double* lo_h, const double* hi_h,
+                             int nranks, int64_t* counts_h, void* stream) {
+  VP_REQUIRE(ctx && pos_d && lo_h && hi_h && counts_h && nranks >= 1 && nranks <= 16 && np >= 0, "vp_slab_count: bad argument");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  const SlabRanges R = make_ranges(lo_h, hi_h, nranks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VP_F32) return slab_count_typed<float>(ctx, static_cast<const float*>(pos_d), np, R, counts_h, st);
+  if (dtype == VP_F64) return slab_count_typed<double>(ctx, static_cast<const double*>(pos_d), np, R, counts_h, st);
+  vp_set_error("vp_slab_count: unknown dtype %d", dtype);
+  return VP_ERR_ARG;
+}
+
+extern "C" int vp_slab_scatter_p2p(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                                   const double* lo_h, const double* hi_h, int nranks, const int64_t* first_row_h, void* stream) {
+  VP_REQUIRE(ctx && pos_d && vel_d && lo_h && hi_h && first_row_h, "vp_slab_scatter_p2p: null argument");
+  VP_REQUIRE(ctx->slab_open && ctx->slab_nranks == nranks, "vp_slab_scatter_p2p: peer buffers not opened for %d ranks", nranks);
+  VP_CUDA(cudaSetDevice(ctx->device));
+  const SlabRanges R = make_ranges(lo_h, hi_h, nranks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VP_F32)
+    return slab_scatter_p2p_typed<float>(ctx, static_cast<const float*>(pos_d), static_cast<const float*>(vel_d),
+                                         static_cast<const float*>(rho_d), np, R, first_row_h, st);
+  if (dtype == VP_F64)
+    return slab_scatter_p2p_typed<double>(ctx, static_cast<const double*>(pos_d), static_cast<const double*>(vel_d),
+                                          static_cast<const double*>(rho_d), np, R, first_row_h, st);
+  vp_set_error("vp_slab_scatter_p2p: unknown dtype %d", dtype);
+  return VP_ERR_ARG;
+}
 
 extern "C" int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
                               const double* lo_h, const double* hi_h, int nranks, void* rows_d, int64_t cap_rows, int64_t* counts_h,

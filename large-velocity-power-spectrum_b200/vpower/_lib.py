@@ -47,6 +47,11 @@ SIGNATURES = {
     "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
     "vp_fields_sorted": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_slab_bucket": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, _P, _L, C.POINTER(_L), _P]),
+    "vp_slab_p2p_alloc": (_I, [_P, C.c_size_t, C.c_char_p]),
+    "vp_slab_p2p_open": (_I, [_P, _I, _I, C.c_char_p]),
+    "vp_slab_p2p_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "vp_slab_count": (_I, [_P, _P, _I, _L, _dp, _dp, _I, C.POINTER(_L), _P]),
+    "vp_slab_scatter_p2p": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, C.POINTER(_L), _P]),
     "vp_gather_rows": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "vp_build_fields": (_I, [_P, _P, _L, _P, _P, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_deposit_ngp": (_I, [_P, _P, _I, _L, _P, _I, _I, _D, _P, _P]),
@@ -199,6 +204,68 @@ def slab_bucket(pos_t, vel_t, rho_t, lo, hi):
         cap *= 2
     counts = [int(c) for c in counts]
     return rows[:sum(counts)], counts
+
+
+class _RawCuda:
+    """Expose a raw device allocation of the library to torch (zero copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class SlabExchangeP2P:
+    """Sharded particle exchange with peer stores: receive buffers live in the library, mapped into every rank."""
+
+    def __init__(self, nranks, rank, group=None):
+        self.nranks, self.rank, self.group, self.cap_bytes = nranks, rank, group, 0
+
+    def _ensure(self, need_bytes):
+        """Collective: (re)allocate all receive buffers when any rank needs more room, then re-map the peers."""
+        torch = _torch()
+        import torch.distributed as dist
+        if need_bytes <= self.cap_bytes:
+            return
+        cap = int(need_bytes * 1.15) + (1 << 20)
+        buf = C.create_string_buffer(64)
+        _check(load_library().vp_slab_p2p_alloc(ctx(), cap, buf))
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(allh, mine, group=self.group)
+        raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        _check(load_library().vp_slab_p2p_open(ctx(), self.nranks, self.rank, raw))
+        self.cap_bytes = cap
+
+    def exchange(self, pos_t, vel_t, rho_t, lo, hi):
+        """-> torch tensor [rows, 7|6] aliasing this rank's receive buffer (all particles of its slab + halo)."""
+        torch = _torch()
+        import torch.distributed as dist
+        P = self.nranks
+        lo_a, lop = _as_dp(lo)
+        hi_a, hip = _as_dp(hi)
+        n = pos_t.shape[0]
+        w = 7 if rho_t is not None else 6
+        es = pos_t.element_size()
+        counts = (_L * P)()
+        _check(load_library().vp_slab_count(ctx(), _P(pos_t.data_ptr()), _dtype_code(pos_t), n, lop, hip, P, counts, stream_ptr()))
+        mine = torch.tensor([int(c) for c in counts], dtype=torch.int64, device=pos_t.device)
+        mat = [torch.empty_like(mine) for _ in range(P)]
+        dist.all_gather(mat, mine, group=self.group)                  # mat[src][dst]
+        M = torch.stack(mat).cpu().numpy()
+        need = int(M.sum(axis=0).max()) * w * es                       # the fullest receive buffer, same on every rank
+        self._ensure(need)
+        first = (_L * P)(*[int(M[:self.rank, d].sum()) for d in range(P)])
+        # barrier: every rank has finished reading its receive buffer from the previous exchange (stream ordered)
+        tok = torch.zeros(1, device=pos_t.device)
+        dist.all_reduce(tok, group=self.group)
+        _check(load_library().vp_slab_scatter_p2p(ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()),
+                                                  _P(rho_t.data_ptr()) if rho_t is not None else None, _dtype_code(pos_t), n,
+                                                  lop, hip, P, first, stream_ptr()))
+        dist.all_reduce(tok, group=self.group)                         # all ranks have stored
+        rows = int(M[:, self.rank].sum())
+        ptr, nbytes = _P(), C.c_size_t()
+        _check(load_library().vp_slab_p2p_buffer(ctx(), C.byref(ptr), C.byref(nbytes)))
+        typestr = "<f8" if es == 8 else "<f4"
+        return torch.as_tensor(_RawCuda(ptr.value, (rows, w), typestr), device=pos_t.device)
 
 
 def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):

@@ -43,8 +43,10 @@ class CudaBackend:
     def __init__(self, N, k_axis, edges, nranks, rank, p2p=False, group=None):
         self.plan = _lib.PkPlan(N, k_axis, edges, nranks=nranks, rank=rank)
         self.p2p = bool(p2p) and nranks > 1
-        if self.p2p:       # the exchange is fused into the y pass: peer stores over NVLink instead of an NCCL all-to-all
+        self.slab_x = None
+        if self.p2p:       # both exchanges fused into kernels: peer stores over NVLink instead of NCCL all-to-all
             self.plan.p2p_setup(group)
+            self.slab_x = _lib.SlabExchangeP2P(nranks, rank, group)
 
     def grid_slab(self, pos, vel, rho, ax_loc, ax, lcell3, keep):
         lo, hi, open_lo, open_hi = keep
@@ -95,6 +97,9 @@ def exchange_particles(pos, vel, rho, ax, nranks, rank, halo_cells, group=None, 
         lo, hi, open_lo, open_hi = keep_range(ax, x0, x1, nranks, d, halo_cells)
         los.append(-np.inf if open_lo else lo)
         his.append(np.inf if open_hi else hi)
+    if backend is not None and getattr(backend, "slab_x", None) is not None:
+        recv = backend.slab_x.exchange(pos, vel, rho, los, his)         # rows stored straight into the peers' buffers
+        return recv[:, 0:3], recv[:, 3:6], (recv[:, 6] if rho is not None else None)
     if backend is not None and hasattr(backend, "bucket"):
         send, counts = backend.bucket(pos, vel, rho, los, his)          # one counting + one scatter kernel
     else:                                                               # generic torch form (CPU tests)

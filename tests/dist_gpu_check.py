@@ -40,11 +40,15 @@ def main():
         # exchange fused into the y pass (CUDA IPC peer stores) instead of the NCCL all-to-all
         be = vd.CudaBackend(N, k, edges, world, rank, p2p=True)
         out_p, ns_p = vd.particles_to_pk_dist(*d, ax, (L / N) ** 3, 0.5 * a * a, k, edges, quantities=qs, backend=be)
-        out_p2, ns_p2 = vd.particles_to_pk_dist(*d, ax, (L / N) ** 3, 0.5 * a * a, k, edges, quantities=qs, backend=be)
+        sl = slice(rank * Np // world, (rank + 1) * Np // world)      # sharded input + peer-store particle exchange, twice
+        shard = [t[sl].contiguous() for t in d]
+        vd.particles_to_pk_dist(*shard, ax, (L / N) ** 3, 0.5 * a * a, k, edges, quantities=qs, backend=be, sharded=True)
+        out_p2, ns_p2 = vd.particles_to_pk_dist(*shard, ax, (L / N) ** 3, 0.5 * a * a, k, edges, quantities=qs, backend=be,
+                                                sharded=True)
         if rank == 0:
             same_p = all(np.array_equal(x, ns) for x in (ns_p, ns_p2)) and all(
                 np.allclose(o[q], out[q], rtol=1e-12) for o in (out_p, out_p2) for q in qs)
-            print(f"N={N} world={world}: peer-to-peer fused transpose == NCCL all-to-all: {same_p}", flush=True)
+            print(f"N={N} world={world}: fused peer-store transpose and particle exchange == NCCL paths: {same_p}", flush=True)
             ok &= same_p
         del be
         if rank == 0:
