@@ -843,45 +843,81 @@ __global__ void __launch_bounds__(256) k_bucket_count(const T* __restrict__ pos,
 struct SlabDest {
   void* base[16];   // all equal for the local form; peer-mapped receive buffers for the fused exchange
 };
+// 512 particles per block.  Every block claims one contiguous row range per destination (one global atomic each),
+// stages its rows in shared memory grouped by destination and writes each group out as one coalesced run -- 128-byte
+// store instructions whether the destination is local HBM or a peer's buffer over NVLink.
+constexpr int kBktItems = 2;
+// staged rows per block (a particle inside a halo goes to two ranks); overflow -> direct stores
+template <typename T> struct BktCap { static constexpr int v = sizeof(T) == 4 ? 1024 : 768; };
 template <typename T>
 __global__ void __launch_bounds__(256) k_bucket_scatter(const T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ rho,
                                                          int64_t np, SlabRanges R, unsigned long long* __restrict__ cursors,
                                                          SlabDest D, int w) {
-  __shared__ unsigned sc[16];
+  __shared__ unsigned sc[16];             // rows of this block per destination
+  __shared__ unsigned pre[17];            // exclusive prefix of sc
   __shared__ unsigned long long sbase[16];
+  constexpr int kBktCap = BktCap<T>::v;
+  __shared__ T stage[kBktCap * 7];
   if (threadIdx.x < 16) sc[threadIdx.x] = 0;
   __syncthreads();
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool ok = i < np;
-  const double x = ok ? double(pos[3 * i]) : 0.0;
   const int lane = threadIdx.x & 31;
-  unsigned myoff[16];
+  const int64_t i0 = int64_t(blockIdx.x) * (256 * kBktItems);
+  unsigned myoff[kBktItems][16];
+  bool okv[kBktItems];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    myoff[d] = 0xffffffffu;
-    if (d < R.n) {
-      const bool in = ok && x >= R.lo[d] && x <= R.hi[d];
-      const unsigned m = __ballot_sync(0xffffffffu, in);
-      unsigned wb = 0;
-      if (lane == 0 && m) wb = atomicAdd(&sc[d], __popc(m));
-      wb = __shfl_sync(0xffffffffu, wb, 0);
-      if (in) myoff[d] = wb + __popc(m & ((1u << lane) - 1u));
+  for (int r = 0; r < kBktItems; ++r) {
+    const int64_t i = i0 + r * 256 + threadIdx.x;
+    okv[r] = i < np;
+    const double x = okv[r] ? double(pos[3 * i]) : 0.0;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      myoff[r][d] = 0xffffffffu;
+      if (d < R.n) {
+        const bool in = okv[r] && x >= R.lo[d] && x <= R.hi[d];
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        unsigned wb = 0;
+        if (lane == 0 && m) wb = atomicAdd(&sc[d], __popc(m));
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+        if (in) myoff[r][d] = wb + __popc(m & ((1u << lane) - 1u));
+      }
     }
   }
   __syncthreads();
   if (threadIdx.x < R.n) sbase[threadIdx.x] = sc[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, (unsigned long long)sc[threadIdx.x]) : 0ull;
+  if (threadIdx.x == 0) {
+    unsigned a = 0;
+    for (int d = 0; d < R.n; ++d) { pre[d] = a; a += sc[d]; }
+    for (int d = R.n; d <= 16; ++d) pre[d] = a;
+  }
   __syncthreads();
-  if (!ok) return;
-  T r[7];
-  r[0] = pos[3 * i]; r[1] = pos[3 * i + 1]; r[2] = pos[3 * i + 2];
-  r[3] = vel[3 * i]; r[4] = vel[3 * i + 1]; r[5] = vel[3 * i + 2];
-  r[6] = rho ? rho[i] : T(0);
 #pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    if (d < R.n && myoff[d] != 0xffffffffu) {
-      T* o = static_cast<T*>(D.base[d]) + (sbase[d] + myoff[d]) * size_t(w);
-      for (int c = 0; c < w; ++c) o[c] = r[c];
+  for (int r = 0; r < kBktItems; ++r) {
+    if (!okv[r]) continue;
+    const int64_t i = i0 + r * 256 + threadIdx.x;
+    T row[7];
+    row[0] = pos[3 * i]; row[1] = pos[3 * i + 1]; row[2] = pos[3 * i + 2];
+    row[3] = vel[3 * i]; row[4] = vel[3 * i + 1]; row[5] = vel[3 * i + 2];
+    row[6] = rho ? rho[i] : T(0);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      if (d < R.n && myoff[r][d] != 0xffffffffu) {
+        const unsigned p = pre[d] + myoff[r][d];
+        if (p < unsigned(kBktCap)) {
+          for (int c = 0; c < w; ++c) stage[p * w + c] = row[c];
+        } else {   // staging area full (very wide halos): store directly
+          T* o = static_cast<T*>(D.base[d]) + (sbase[d] + myoff[r][d]) * size_t(w);
+          for (int c = 0; c < w; ++c) o[c] = row[c];
+        }
+      }
     }
+  }
+  __syncthreads();
+  const unsigned tot = min(pre[16], unsigned(kBktCap));
+  int d = 0;
+  for (unsigned f = threadIdx.x; f < tot * unsigned(w); f += 256) {
+    const unsigned rr = f / unsigned(w), c = f - rr * unsigned(w);
+    while (rr >= pre[d + 1]) ++d;                  // f only grows: the destination index is monotone per thread
+    static_cast<T*>(D.base[d])[(sbase[d] + (rr - pre[d])) * size_t(w) + c] = stage[f];
   }
 }
 
@@ -918,7 +954,7 @@ int slab_bucket_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int
     vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * w * sizeof(T) + double(total) * w * sizeof(T));
     SlabDest D;
     for (int d = 0; d < 16; ++d) D.base[d] = rows;
-    k_bucket_scatter<T><<<nb, 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
+    k_bucket_scatter<T><<<unsigned((np + 256 * kBktItems - 1) / (256 * kBktItems)), 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
   }
   VP_CHECK_LAUNCH();
   VP_CUDA(cudaStreamSynchronize(st));   // cnt/cur live in the scope released on return
@@ -958,7 +994,7 @@ int slab_scatter_p2p_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho
     vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * 2.0 * w * sizeof(T));
     SlabDest D;
     for (int d = 0; d < 16; ++d) D.base[d] = d < R.n ? ctx->slab_peer[d] : nullptr;
-    k_bucket_scatter<T><<<unsigned((np + 255) / 256), 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
+    k_bucket_scatter<T><<<unsigned((np + 256 * kBktItems - 1) / (256 * kBktItems)), 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
     VP_CHECK_LAUNCH();
   }
   VP_CUDA(cudaStreamSynchronize(st));   // cur lives in the scope released on return
