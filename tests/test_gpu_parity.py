@@ -454,3 +454,35 @@ def test_slab_bucket_kernel(lib):
         assert np.array_equal(a, b)
     rows6, counts6 = lib.slab_bucket(pos, vel, None, lo, hi)
     assert counts6 == counts and rows6.shape[1] == 6
+
+
+def test_fft_2048_single_mode_and_low_shells(lib, orc):
+    """N = 2048 (cfg5's lattice): the 1024-thread y/x kernels and the non-prefetch x pass.  No CPU oracle can transform
+    2048^3, so: a single plane wave must put N^6/2 into its shell and (to rounding) nothing elsewhere, and the mode counts
+    of the first 40 shells must equal a brute-force count of integer lattice points."""
+    import torch
+    N, L = 2048, 1.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~40 GB of device memory")
+    f = torch.empty((N, N, N), dtype=torch.float32, device="cuda")
+    ar = torch.arange(N, device="cuda", dtype=torch.float64)
+    for x0 in range(0, N, 32):
+        ph = (3 * ar[x0:x0 + 32, None, None] + 5 * ar[None, :, None] + 7 * ar[None, None, :]) * (2 * np.pi / N)
+        f[x0:x0 + 32] = torch.cos(ph).to(torch.float32)
+        del ph
+    centres, edges = orc.edges_lib(2 * np.pi / L, np.pi * N / L, 2 * np.pi / L)
+    plan = lib.PkPlan(N, orc.k_axis(L, N), edges)
+    psum, ns = plan.fields([f])
+    del f
+    j0 = int(np.floor(np.sqrt(9 + 25 + 49) + 0.5)) - 1            # shell of |k| = sqrt(83) kf
+    expect = float(N) ** 6 / 2
+    assert abs(psum[j0] / expect - 1) < 1e-5
+    assert (np.delete(psum, j0).sum()) < 1e-6 * expect
+    m = 41
+    n1 = np.arange(-m, m + 1)
+    r = np.sqrt(n1[:, None, None] ** 2 + n1[None, :, None] ** 2 + n1[None, None, :] ** 2)
+    shell = np.floor(r + 0.5).astype(int)
+    ref = np.bincount(shell.ravel(), minlength=m + 1)[1:m]
+    assert np.array_equal(ns[:m - 1], ref)
+    assert ns.sum() > 0.5 * (4 / 3) * np.pi * (N / 2) ** 3
