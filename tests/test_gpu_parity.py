@@ -486,3 +486,47 @@ def test_fft_2048_single_mode_and_low_shells(lib, orc):
     ref = np.bincount(shell.ravel(), minlength=m + 1)[1:m]
     assert np.array_equal(ns[:m - 1], ref)
     assert ns.sum() > 0.5 * (4 / 3) * np.pi * (N / 2) ** 3
+
+
+def test_nn_full_size_spot_check(lib, orc):
+    """cfg3 scale (512^3 lattice, 2^27 particles, clustered: voids and sheets).  The CPU oracle cannot build a kd-tree of
+    1.3e8 points in test time, so 600 random lattice nodes are re-decided independently: all particles inside a generous
+    cube around the node (torch mask on the device) -> exact f64 argmin with lowest-index ties on the host."""
+    import torch
+    N, L = 512, 1.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~25 GB of device memory")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    g1 = (torch.arange(N, device="cuda", dtype=torch.float32) + 0.5) / N
+    q = torch.stack(torch.meshgrid(g1, g1, g1, indexing="ij"), dim=-1).reshape(-1, 3)
+    rs = np.random.default_rng(11)
+    disp = torch.zeros_like(q)
+    for _ in range(24):
+        kv = torch.tensor(rs.integers(1, 40, size=3) * rs.choice([-1, 1], size=3), device="cuda", dtype=torch.float32)
+        kk = float(torch.linalg.norm(kv))
+        disp += (1.0 / kk) * (kv / kk)[None, :] * torch.sin(2 * np.pi * (q @ kv) + float(rs.uniform(0, 6.28)))[:, None]
+    disp *= (2.0 / N) / float(torch.sqrt((disp ** 2).sum(1).mean()))
+    pos = torch.remainder(q + disp, 1.0).contiguous()
+    del q, disp
+    ax = orc.lattice_axis_lib(L, N)
+    nn = lib.nn_grid(pos, ax, ax, ax)
+    st = lib.nn_grid_stats()
+    assert st["n_unresolved"] == 0 and st["n_kept"] == N ** 3
+    h = ax[1] - ax[0]
+    pick = rs.integers(0, N, size=(600, 3))
+    bad = 0
+    for i, j, k in pick:
+        node = np.array([ax[i], ax[j], ax[k]])
+        got = int(nn[i, j, k])
+        pg = pos[got].cpu().numpy().astype(np.float64)
+        dg = ((node[0] - pg[0]) ** 2 + (node[1] - pg[1]) ** 2) + (node[2] - pg[2]) ** 2
+        R = np.sqrt(dg) * 1.0001 + 1e-6                       # anything nearer than the answer lies inside this cube
+        m = ((pos[:, 0] - float(node[0])).abs() <= R) & ((pos[:, 1] - float(node[1])).abs() <= R) & ((pos[:, 2] - float(node[2])).abs() <= R)
+        idx = torch.nonzero(m).reshape(-1).cpu().numpy()
+        c = pos[m].cpu().numpy().astype(np.float64)
+        d2 = ((node[0] - c[:, 0]) ** 2 + (node[1] - c[:, 1]) ** 2) + (node[2] - c[:, 2]) ** 2
+        best = idx[np.lexsort((idx, d2))[0]]
+        bad += int(best != got)
+    assert bad == 0
+    assert R < 20 * h
