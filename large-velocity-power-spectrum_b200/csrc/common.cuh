@@ -51,6 +51,7 @@ struct vp_nn_stats_dev {
   unsigned long long n_unresolved;  // nodes still unproven afterwards
   unsigned long long n_kept;        // particles that survived the x filter
   unsigned long long pad;
+  unsigned long long row_cursor;    // dynamic row assignment of k_group_permute
 };
 
 // optional per-stage timing with CUDA events on the launching stream (vp_profile_enable / vp_profile_report)
@@ -106,6 +107,9 @@ struct vp_arena_scope {
 size_t vp_sort_scratch_bytes(int64_t n);
 int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
                        cudaStream_t st);
+// stable sort on key bits [lo, lo + nbits) only
+int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, void* scratch,
+                        cudaStream_t st);
 
 // Host-resident particle arrays streamed to the device in chunks (vp_host_particles_to_pk): positions land in a
 // resident device array (the exact search needs them), velocity/density chunks only pass through two staging buffers.

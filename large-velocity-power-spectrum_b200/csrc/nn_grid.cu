@@ -1,7 +1,9 @@
 // K1: exact nearest-particle gridding on a sorted cell list.  See include/vpower_b200.h (vp_nn_grid).
 //
 // Pipeline:  keygen + pack (cell key per particle, optional x filter, one packed record per particle)
-//            ->  radix sort of (key, slot)  ->  permute the packed records into cell order  ->  cell starts
+//            ->  radix sort of (key, slot) on the ROW bits of the key only (a row = one x plane, a chunk of y, all z)
+//            ->  row starts  ->  one CTA per row: counting sort of the row by cell in shared memory, fused with the
+//                permutation of the packed records into cell order and with the cell-start table
 //            ->  ring-1 search per lattice node (f32 prefilter)  ->  exact f64 search (warp per node, growing ring)
 //                for every node the prefilter could not settle.
 //
@@ -24,6 +26,8 @@ struct Grid {
   double keep_lo, keep_hi;
   int closed_xlo, closed_xhi;  // 1: particles beyond that x face were dropped (face constrains the proof)
   int ps, vs, rs;              // element strides between consecutive particles in pos / vel / rho (3,3,1 when compact)
+  // sort key = (row << lb) | local,  row = cx * nyc + (cy >> yb),  local = (cy & (2^yb - 1)) * gz + cz  (< bins <= 2^lb)
+  int yb, lb, nyc, bins;
 };
 
 // Sorted particle record: position relative to the grid origin rounded to f32 (used only by the f32
@@ -80,7 +84,9 @@ __global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, 
     key[r] = 0;
     if (ok[r]) {
       int cx = cell_of(x, g.ox, g.ihx, g.gx), cy = cell_of(y, g.oy, g.ihy, g.gy), cz = cell_of(z, g.oz, g.ihz, g.gz);
-      key[r] = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+      const uint32_t row = uint32_t(cx) * uint32_t(g.nyc) + (uint32_t(cy) >> g.yb);
+      const uint32_t loc = (uint32_t(cy) & ((1u << g.yb) - 1u)) * uint32_t(g.gz) + uint32_t(cz);
+      key[r] = (row << g.lb) | loc;
       a[r] = make_float4(float(x - g.ox), float(y - g.oy), float(z - g.oz), __int_as_float(int(i0 + i)));
       ++mine;
     }
@@ -151,34 +157,198 @@ __global__ void __launch_bounds__(256) k_permute(const void* __restrict__ packed
   }
 }
 
-// start[c] = first sorted position whose key >= c, for c in [0, ncells]; start[ncells] = n
-__global__ void __launch_bounds__(256) k_cell_starts(const uint32_t* __restrict__ keys, int64_t n, uint32_t ncells,
-                                                      uint32_t* __restrict__ start) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  int64_t lo = 1, hi = 0;  // empty range
-  uint32_t v = 0;
-  if (i < n) {
-    uint32_t k = keys[i];
-    int64_t kp = (i == 0) ? -1 : int64_t(keys[i - 1]);
-    if (int64_t(k) != kp) { lo = kp + 1; hi = k; v = uint32_t(i); }
-    if (i == n - 1) {
-      // tail: cells after the last key (done by this thread after its own range)
-      for (int64_t c = lo; c <= hi; ++c) start[c] = v;
-      lo = int64_t(k) + 1; hi = ncells; v = uint32_t(n);
+// row_start[r] = first sorted position whose row (key >> shift) is >= r, for r in [0, nrows]; row_start[nrows] = n.
+// Four consecutive keys per thread (one 16-byte load).
+__global__ void __launch_bounds__(256) k_row_starts(const uint32_t* __restrict__ keys, int64_t n, int shift, uint32_t nrows,
+                                                     uint32_t* __restrict__ start) {
+  const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const int lane = threadIdx.x & 31;
+  uint32_t k4[4] = {0u, 0u, 0u, 0u};
+  if (i0 + 3 < n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
+    k4[0] = v.x; k4[1] = v.y; k4[2] = v.z; k4[3] = v.w;
+  } else {
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < n) k4[u] = keys[i0 + u];
+  }
+  int64_t kp = (i0 == 0 || i0 >= n) ? -1 : int64_t(keys[i0 - 1] >> shift);
+#pragma unroll 1
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = i0 + u;
+    int64_t lo = 1, hi = 0;  // empty range
+    uint32_t v = 0;
+    if (i < n) {
+      const uint32_t k = k4[u] >> shift;
+      if (int64_t(k) != kp) { lo = kp + 1; hi = k; v = uint32_t(i); }
+      kp = k;
+      if (i == n - 1) {
+        // tail: rows after the last key (done by this thread after its own range)
+        for (int64_t c = lo; c <= hi; ++c) start[c] = v;
+        lo = int64_t(k) + 1; hi = nrows; v = uint32_t(n);
+      }
+    }
+    // long gaps are filled by the whole warp
+    unsigned big = __ballot_sync(0xffffffffu, hi - lo >= 32);
+    while (big) {
+      int src = __ffs(big) - 1;
+      big &= big - 1;
+      int64_t l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
+      uint32_t vv = __shfl_sync(0xffffffffu, v, src);
+      for (int64_t c = l + lane; c <= h; c += 32) start[c] = vv;
+      if (lane == src) { lo = 1; hi = 0; }
+    }
+    for (int64_t c = lo; c <= hi; ++c) start[c] = v;
+  }
+}
+
+// One CTA per SM, rows of cells handed out by a global cursor (a row = one x plane, 2^yb consecutive y, all z: `bins`
+// cells, contiguous in the linear cell order).  The radix sort has brought the row's (key, slot) pairs together; here
+// they are counted per cell in shared memory, the exclusive prefix gives the row's part of the cell-start table, and
+// every slot is written to its place inside the row (taken from the per-cell cursors) in a shared-memory order table
+// that is then copied out coalesced: this finishes the sort without the two radix passes over the low key bits.
+// (Scattering the slots straight to global memory is transaction bound, ~45 G scattered stores/s.  Gathering the packed
+// records in the same kernel was tried and lost: 51 ms against 29 ms for the plain k_permute that follows.)
+//   short rows (len <= ordcap < 65536): 16-bit counters, two per word, + u32 order table   -- the common case
+//   long rows (dense clusters):         32-bit counters, slots scattered to the global array
+// The order of the particles INSIDE a cell is whatever the cursors hand out; no result depends on it (ties are decided
+// by particle index).
+constexpr int kGroupThreads = 1024;
+constexpr int kGroupUnroll = 8;
+constexpr int kMaxBins = 33 * 1024;         // 132 KB of u32 counters: a 32 x 1025 (y, z) tile of the 1024^3 cell grid fits
+constexpr int kGroupSmemMax = 227 * 1024 - 256;   // opt-in dynamic shared memory, minus the static part
+
+template <bool SHORT>
+__device__ __forceinline__ uint32_t group_bump(uint32_t* cnt, uint32_t l) {   // previous value of counter l, then +1
+  if (SHORT) {
+    const uint32_t old = atomicAdd(&cnt[l >> 1], (l & 1u) ? 0x10000u : 1u);
+    return (l & 1u) ? (old >> 16) : (old & 0xffffu);
+  }
+  return atomicAdd(&cnt[l], 1u);
+}
+
+template <bool SHORT>
+__device__ __forceinline__ void group_row(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                          uint32_t* __restrict__ start, uint32_t* __restrict__ ordg, uint32_t* cnt, uint32_t* ord,
+                                          uint32_t* wsum, uint32_t lmask, uint32_t s, uint32_t e, uint32_t used, size_t cell0,
+                                          bool last, uint32_t n) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t len = e - s;
+  const uint32_t words = SHORT ? (used + 1) / 2 : used;
+  for (uint32_t l = tid; l < words; l += kGroupThreads) cnt[l] = 0;
+  __syncthreads();
+  for (uint32_t p0 = s; p0 < e; p0 += kGroupThreads * kGroupUnroll) {
+    uint32_t k[kGroupUnroll];
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u) {
+      const uint32_t p = p0 + u * kGroupThreads + tid;
+      k[u] = p < e ? keys[p] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u)
+      if (p0 + u * kGroupThreads + tid < e) group_bump<SHORT>(cnt, k[u] & lmask);
+  }
+  __syncthreads();
+  // exclusive scan of the counters: thread t owns words [t*ch, (t+1)*ch)
+  const uint32_t ch = ((words + kGroupThreads - 1) / kGroupThreads) | 1u;   // odd: conflict-free strided scan
+  const uint32_t b0 = min(uint32_t(tid) * ch, words), b1 = min(b0 + ch, words);
+  uint32_t sum = 0;
+  for (uint32_t l = b0; l < b1; ++l) {
+    const uint32_t c = cnt[l];
+    sum += SHORT ? (c & 0xffffu) + (c >> 16) : c;
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = wsum[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += t;
+    }
+    wsum[lane] = iv - v;
+  }
+  __syncthreads();
+  uint32_t run = wsum[w] + incl - sum;   // row-relative
+  for (uint32_t l = b0; l < b1; ++l) {
+    const uint32_t c = cnt[l];
+    if (SHORT) {
+      const uint32_t c0 = c & 0xffffu, c1 = c >> 16;
+      cnt[l] = run | ((run + c0) << 16);
+      run += c0 + c1;
+    } else {
+      cnt[l] = run;
+      run += c;
     }
   }
-  // long gaps are filled by the whole warp
-  const int lane = threadIdx.x & 31;
-  unsigned big = __ballot_sync(0xffffffffu, hi - lo >= 32);
-  while (big) {
-    int src = __ffs(big) - 1;
-    big &= big - 1;
-    int64_t l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
-    uint32_t vv = __shfl_sync(0xffffffffu, v, src);
-    for (int64_t c = l + lane; c <= h; c += 32) start[c] = vv;
-    if (lane == src) { lo = 1; hi = 0; }
+  __syncthreads();
+  if (SHORT) {
+    const uint16_t* c16 = reinterpret_cast<const uint16_t*>(cnt);
+    for (uint32_t l = tid; l < used; l += kGroupThreads) start[cell0 + l] = s + c16[l];
+  } else {
+    for (uint32_t l = tid; l < used; l += kGroupThreads) start[cell0 + l] = s + cnt[l];
   }
-  for (int64_t c = lo; c <= hi; ++c) start[c] = v;
+  if (last && tid == 0) start[cell0 + used] = n;
+  __syncthreads();   // the cursors move only after the table has been copied out
+  for (uint32_t p0 = s; p0 < e; p0 += kGroupThreads * kGroupUnroll) {
+    uint32_t k[kGroupUnroll], v[kGroupUnroll];
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u) {
+      const uint32_t p = p0 + u * kGroupThreads + tid;
+      k[u] = p < e ? keys[p] : 0xffffffffu;
+      v[u] = p < e ? vals[p] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u) {
+      if (p0 + u * kGroupThreads + tid >= e) continue;
+      const uint32_t d = group_bump<SHORT>(cnt, k[u] & lmask);
+      if (SHORT) ord[d] = v[u];
+      else ordg[s + d] = v[u];
+    }
+  }
+  __syncthreads();
+  if (SHORT) {
+    for (uint32_t t = tid; t < len; t += kGroupThreads) ordg[s + t] = ord[t];
+  }
+  __syncthreads();   // before the next row clears the counters
+}
+
+__global__ void __launch_bounds__(kGroupThreads, 1) k_group_rows(const uint32_t* __restrict__ keys,
+                                                                  const uint32_t* __restrict__ vals,
+                                                                  const uint32_t* __restrict__ row_start,
+                                                                  uint32_t* __restrict__ start, uint32_t* __restrict__ ordg, Grid g,
+                                                                  uint32_t nrows, uint32_t n, uint32_t ordcap,
+                                                                  unsigned long long* __restrict__ cursor) {
+  extern __shared__ __align__(16) uint32_t cnt[];   // counters / cursors (u16 pairs or u32), then the order table of short rows
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t next_row;
+  uint32_t* ord = cnt + ((uint32_t(g.bins) + 1) / 2 + 3 & ~3u);
+  const int tid = threadIdx.x;
+  const uint32_t lmask = (1u << g.lb) - 1u;
+  if (tid == 0) next_row = uint32_t(min(atomicAdd(cursor, 1ull), (unsigned long long)nrows));
+  __syncthreads();
+  uint32_t row = next_row;
+  while (row < nrows) {
+    __syncthreads();   // everybody has read next_row
+    if (tid == 0) next_row = uint32_t(min(atomicAdd(cursor, 1ull), (unsigned long long)nrows));
+    const uint32_t s = row_start[row], e = row_start[row + 1];
+    const uint32_t cx = row / uint32_t(g.nyc), ycb = row - cx * uint32_t(g.nyc);
+    const int y0 = int(ycb << g.yb);
+    const int ny_here = min(1 << g.yb, g.gy - y0);
+    const uint32_t used = uint32_t(ny_here) * uint32_t(g.gz);
+    const size_t cell0 = (size_t(cx) * g.gy + size_t(y0)) * g.gz;
+    const bool last = row == nrows - 1;
+    if (e - s <= ordcap)
+      group_row<true>(keys, vals, start, ordg, cnt, ord, wsum, lmask, s, e, used, cell0, last, n);
+    else
+      group_row<false>(keys, vals, start, ordg, cnt, ord, wsum, lmask, s, e, used, cell0, last, n);
+    row = next_row;   // written before the barriers inside group_row
+  }
 }
 
 __global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
@@ -541,7 +711,19 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
       corner_x = false;
     }
   }
-  while (double(gx) * gy * gz >= 4294967295.0) {  // 32-bit keys
+  // key layout: the widest y chunk whose (y, z) tile of cells fits the shared-memory counters of k_group_permute;
+  // the grid is coarsened until a z row fits the counters and (row << lb | local) fits 32 bits
+  int yb = 0, lb = 0, nyc = 1;
+  for (;;) {
+    bool fits = gz <= kMaxBins;
+    if (fits) {
+      yb = 0;
+      while ((int64_t(2) << yb) * gz <= kMaxBins && (1 << yb) < gy) ++yb;
+      lb = vp_ceil_log2(uint64_t(gz) << yb);
+      nyc = (gy + (1 << yb) - 1) >> yb;
+      fits = (uint64_t(gx) * uint64_t(nyc)) <= (uint64_t(1) << (32 - lb)) && double(gx) * gy * gz < 4294967295.0;
+    }
+    if (fits) break;
     gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
     corner_x = corner_y = corner_z = false;
   }
@@ -566,21 +748,23 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
   g.ps = o.row_stride > 0 ? o.row_stride : 3;
   g.vs = o.row_stride > 0 ? o.row_stride : 3;
   g.rs = o.row_stride > 0 ? o.row_stride : 1;
+  g.yb = yb; g.lb = lb; g.nyc = nyc; g.bins = gz << yb;
   return g;
 }
 
 struct NNScratch {
-  size_t keys, packed, spos, start, tail, total;
+  size_t keys, packed, spos, start, rows, tail, total;
 };
-NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, int64_t nnodes) {
+NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint64_t nrows, int64_t nnodes) {
   NNScratch s;
   s.keys = vp_align256(size_t(np) * 4);
   s.packed = vp_align256(size_t(np) * (pay ? sizeof(rec32_t) : sizeof(float4)));
   s.spos = vp_align256(size_t(np) * sizeof(rec_t));
   s.start = vp_align256((ncells + 1) * 4);
+  s.rows = vp_align256((nrows + 1) * 4);
   size_t b_wide = 2 * vp_align256(size_t(nnodes) * 4), b_sort = vp_sort_scratch_bytes(np);
   s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are permuted; the two node lists reuse it
-  s.total = 2 * s.keys + s.packed + s.spos + s.start + s.tail + 2048;
+  s.total = 2 * s.keys + s.packed + s.spos + s.start + s.rows + s.tail + 2048;
   return s;
 }
 
@@ -610,7 +794,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   const Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
   const int gx = g.gx, gy = g.gy, gz = g.gz;
   const uint64_t ncells = uint64_t(gx) * gy * gz;
-  const int bits = vp_ceil_log2(ncells);
+  const uint64_t nrows = uint64_t(gx) * g.nyc;
+  const int row_bits = vp_ceil_log2(nrows);
 
   // ---- lattice tables (host -> pinned -> device)
   const size_t nt = size_t(nx) + ny + nz;
@@ -677,7 +862,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   L.nx = nx; L.ny = ny; L.nz = nz;
 
   // ---- scratch
-  const NNScratch sc = nn_scratch(np, has_pay, ncells, nnodes);
+  const NNScratch sc = nn_scratch(np, has_pay, ncells, nrows, nnodes);
   const size_t stage_bytes = (has_pay && pay->host) ? vp_host_chunk_staging_bytes(pay->host->chunk, sizeof(T) == 8 ? VP_F64 : VP_F32, pay->host->rho_h != nullptr) + 512 : 0;
   vp_arena_scope scope(ctx);
   VP_TRY(vp_arena_reserve(ctx, sc.total + stage_bytes));
@@ -686,8 +871,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   void* packed = vp_arena_alloc(ctx, sc.packed);
   rec_t* spos = static_cast<rec_t*>(vp_arena_alloc(ctx, sc.spos));
   uint32_t* start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.start));
+  uint32_t* row_start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.rows));
   void* scratch = vp_arena_alloc(ctx, sc.tail);
-  VP_REQUIRE(keys && vals && packed && spos && start && scratch, "vp_nn_grid: arena carve failed");
+  VP_REQUIRE(keys && vals && packed && spos && start && row_start && scratch, "vp_nn_grid: arena carve failed");
   uint32_t* node_list = static_cast<uint32_t*>(scratch);                                      // -> exact kernel
   uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> 4x4x4 stage
 
@@ -761,18 +947,34 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     unsigned long long kept = (unsigned long long)np;
     VP_CUDA(cudaMemcpyAsync(&ctx->nn_stats_d->n_kept, &kept, 8, cudaMemcpyHostToDevice, st));
   }
-  VP_TRY(vp_sort_pairs_impl(ctx, keys, vals, n, bits, scratch, st));
+  // rows brought together by the sort (stable LSD passes over the row bits only), cells inside a row by the group kernel
+  VP_TRY(vp_sort_pairs_range(ctx, keys, vals, n, g.lb, row_bits, scratch, st));
   if (n > 0) {
+    {
+      vp_stage stage(ctx, "k1d_row_starts", st, 1, double(n) * 4.0 + double(nrows) * 4.0);
+      k_row_starts<<<unsigned((n + 1023) / 1024), 256, 0, st>>>(keys, n, g.lb, uint32_t(nrows), row_start);
+    }
+    uint32_t* svals = static_cast<uint32_t*>(scratch);          // first alternate buffer of the finished sort
+    {
+      // key read twice (count, place), slot read and written, cell table written
+      vp_stage stage(ctx, "k1c_group_rows", st, 1, double(n) * 16.0 + double(ncells) * 4.0);
+      const size_t ord_off = (((size_t(g.bins) + 1) / 2 + 3) & ~size_t(3)) * 4;      // bytes of the packed 16-bit counters
+      const uint32_t room = uint32_t((kGroupSmemMax - ord_off) / 4);
+      const uint32_t ordcap = room < 65535u ? room : 65535u;    // a short row's cursors fit 16 bits
+      size_t smem = ord_off + size_t(ordcap) * 4;
+      if (smem < size_t(g.bins) * 4) smem = size_t(g.bins) * 4;   // long rows: 32-bit counters
+      const unsigned nb = unsigned(nrows < uint64_t(ctx->sm_count) ? nrows : uint64_t(ctx->sm_count));
+      unsigned long long* cursor = &ctx->nn_stats_d->row_cursor;   // zeroed with the stats block above
+      VP_CUDA(cudaFuncSetAttribute(k_group_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kGroupSmemMax));
+      k_group_rows<<<nb, kGroupThreads, smem, st>>>(keys, vals, row_start, start, svals, g, uint32_t(nrows), uint32_t(n), ordcap,
+                                                    cursor);
+    }
     {
       // slot read, one packed record gathered, sorted records written
       vp_stage stage(ctx, "k1c_permute", st, 1, double(n) * (4.0 + (has_pay ? 64.0 : 32.0)));
       const unsigned nb = unsigned((n + 255) / 256);
-      if (has_pay) k_permute<true><<<nb, 256, 0, st>>>(packed, vals, n, spos, pay->spay_out);
-      else k_permute<false><<<nb, 256, 0, st>>>(packed, vals, n, spos, nullptr);
-    }
-    {
-      vp_stage stage(ctx, "k1d_cell_starts", st, 1, double(n) * 4.0 + double(ncells) * 4.0);
-      k_cell_starts<<<unsigned((n + 255) / 256), 256, 0, st>>>(keys, n, uint32_t(ncells), start);
+      if (has_pay) k_permute<true><<<nb, 256, 0, st>>>(packed, svals, n, spos, pay->spay_out);
+      else k_permute<false><<<nb, 256, 0, st>>>(packed, svals, n, spos, nullptr);
     }
   } else {
     k_fill_u32<<<unsigned((ncells + 1 + 255) / 256), 256, 0, st>>>(start, int64_t(ncells + 1), 0u);
@@ -1129,7 +1331,7 @@ size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* 
   if (opts) o = *opts;
   Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
   (void)pos_dtype;
-  return nn_scratch(np, true, uint64_t(g.gx) * g.gy * g.gz, int64_t(nx) * ny * nz).total + 4096;
+  return nn_scratch(np, true, uint64_t(g.gx) * g.gy * g.gz, uint64_t(g.gx) * g.nyc, int64_t(nx) * ny * nz).total + 4096;
 }
 
 extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,

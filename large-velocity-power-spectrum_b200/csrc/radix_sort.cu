@@ -1,4 +1,4 @@
-// LSD radix sort of (key,value) u32 pairs, 8 bits per pass -- builds the cell list of K1.
+// LSD radix sort of (key,value) u32 pairs on a bit range, 7 or 8 bits per pass -- builds the cell list of K1.
 //
 // Per pass:  (1) tile digit histograms  (2) exclusive scan, digit-major  (3) stable scatter with
 // warp-level match ranking and a shared-memory staged, digit-run coalesced write.
@@ -10,7 +10,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kItems = 16;
 constexpr int kTile = kThreads * kItems;  // 4096 keys per CTA
-constexpr int kRadix = 256;
+constexpr int kRadix = 256;   // widest digit; the histogram scratch is sized for it
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -41,19 +41,21 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wa
 }
 
 // (1) per-tile digit histogram, written digit-major: hist[d * nblocks + b]
+template <int BITS>
 __global__ void __launch_bounds__(kThreads) k_tile_hist(const uint32_t* __restrict__ keys, int64_t n, int shift,
                                                          uint32_t* __restrict__ hist, int nblocks) {
-  __shared__ uint32_t sh[kRadix];
-  sh[threadIdx.x] = 0;
+  constexpr int R = 1 << BITS;
+  __shared__ uint32_t sh[R];
+  if (threadIdx.x < R) sh[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = int64_t(blockIdx.x) * kTile;
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     int64_t i = base + r * kThreads + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 0xff], 1u);
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (R - 1)], 1u);
   }
   __syncthreads();
-  hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = sh[threadIdx.x];
+  if (threadIdx.x < R) hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = sh[threadIdx.x];
 }
 
 // (2) exclusive scan of m u32 values in three kernels (chunk sums, scan of sums, apply)
@@ -106,13 +108,15 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t* __restrict__ 
 }
 
 // (3) stable scatter
+template <int BITS>
 __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                        uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                        int64_t n, int shift, const uint32_t* __restrict__ hist,
                                                        int nblocks) {
-  __shared__ uint32_t wcnt[kWarps][kRadix];
-  __shared__ uint32_t dbase[kRadix];   // exclusive prefix of digit totals inside this tile
-  __shared__ uint32_t gbase[kRadix];   // global output offset of the digit run minus dbase
+  constexpr int R = 1 << BITS;
+  __shared__ uint32_t wcnt[kWarps][R];
+  __shared__ uint32_t dbase[R];   // exclusive prefix of digit totals inside this tile
+  __shared__ uint32_t gbase[R];   // global output offset of the digit run minus dbase
   __shared__ uint32_t skey[kTile];
   __shared__ uint32_t sval[kTile];
   __shared__ uint32_t ws[kWarps];
@@ -122,8 +126,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
   const int64_t rem = n - tile0;
   const int count = rem < kTile ? int(rem) : kTile;
 
+  if (tid < R) {
 #pragma unroll
-  for (int i = 0; i < kWarps; ++i) wcnt[i][tid] = 0;
+    for (int i = 0; i < kWarps; ++i) wcnt[i][tid] = 0;
+  }
   __syncthreads();
 
   uint32_t key[kItems], val[kItems], rank[kItems];
@@ -139,12 +145,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
   for (int r = 0; r < kItems; ++r) {
     int li = wbase + r * 32 + lane;
     bool ok = li < count;
-    uint32_t d = ok ? ((key[r] >> shift) & 0xff) : 256u;
-    // lanes holding the same digit: eight ballots, one per digit bit (MATCH.ANY serialises over distinct values)
+    uint32_t d = ok ? ((key[r] >> shift) & (R - 1)) : uint32_t(R);
+    // lanes holding the same digit: one ballot per digit bit (MATCH.ANY serialises over distinct values)
     uint32_t peers = __ballot_sync(0xffffffffu, ok);
     if (!ok) peers = ~peers;
 #pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
+    for (int bit = 0; bit < BITS; ++bit) {
       const uint32_t m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
       peers &= ((d >> bit) & 1u) ? m : ~m;
     }
@@ -163,23 +169,27 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
 
   // digit `tid`: exclusive offsets across warps, then across digits
   uint32_t tot = 0;
+  if (tid < R) {
 #pragma unroll
-  for (int i = 0; i < kWarps; ++i) {
-    uint32_t c = wcnt[i][tid];
-    wcnt[i][tid] = tot;
-    tot += c;
+    for (int i = 0; i < kWarps; ++i) {
+      uint32_t c = wcnt[i][tid];
+      wcnt[i][tid] = tot;
+      tot += c;
+    }
   }
   uint32_t blocktot;
   uint32_t ex = block_excl_scan_256(tot, ws, &blocktot);
-  dbase[tid] = ex;
-  gbase[tid] = hist[size_t(tid) * nblocks + blockIdx.x] - ex;
+  if (tid < R) {
+    dbase[tid] = ex;
+    gbase[tid] = hist[size_t(tid) * nblocks + blockIdx.x] - ex;
+  }
   __syncthreads();
 
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     int li = wbase + r * 32 + lane;
     if (li < count) {
-      uint32_t d = (key[r] >> shift) & 0xff;
+      uint32_t d = (key[r] >> shift) & (R - 1);
       uint32_t p = dbase[d] + wcnt[w][d] + rank[r];
       skey[p] = key[r];
       sval[p] = val[r];
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
     int i = r * kThreads + tid;
     if (i < count) {
       uint32_t k = skey[i];
-      uint32_t d = (k >> shift) & 0xff;
+      uint32_t d = (k >> shift) & (R - 1);
       size_t o = size_t(gbase[d]) + i;
       kout[o] = k;
       vout[o] = sval[i];
@@ -212,13 +222,26 @@ size_t vp_sort_scratch_bytes(int64_t n) {
          + vp_align256(size_t(nchunks) * 4);  // scan partials
 }
 
-int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
-                       cudaStream_t st) {
-  if (n <= 1 || bits <= 0) return VP_OK;
+template <int BITS>
+static void sort_pass(const uint32_t* ka, const uint32_t* va, uint32_t* kb, uint32_t* vb, int64_t n, int shift, uint32_t* hist,
+                      uint32_t* sums, int nb, cudaStream_t st) {
+  const int64_t m = int64_t(nb) << BITS;
+  const int nchunks = int((m + kScanChunk - 1) / kScanChunk);
+  k_tile_hist<BITS><<<nb, kThreads, 0, st>>>(ka, n, shift, hist, nb);
+  k_scan_sums<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
+  k_scan_top<<<1, kThreads, 0, st>>>(sums, nchunks);
+  k_scan_apply<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
+  k_scatter<BITS><<<nb, kThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nb);
+}
+
+// Stable sort on key bits [lo, lo + nbits); the other bits travel with the key untouched.
+int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, void* scratch,
+                        cudaStream_t st) {
+  if (n <= 1 || nbits <= 0) return VP_OK;
   VP_REQUIRE(n < (int64_t(1) << 32), "vp_sort_pairs: n=%lld exceeds 2^32", (long long)n);
+  VP_REQUIRE(lo >= 0 && lo + nbits <= 32, "vp_sort_pairs: bit range [%d,%d) outside the key", lo, lo + nbits);
   const int nb = int(sort_nblocks(n));
   const int64_t m = int64_t(nb) * kRadix;
-  const int nchunks = int((m + kScanChunk - 1) / kScanChunk);
   char* p = static_cast<char*>(scratch);
   uint32_t* k2 = reinterpret_cast<uint32_t*>(p);
   p += vp_align256(size_t(n) * 4);
@@ -229,16 +252,16 @@ int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, i
   uint32_t* sums = reinterpret_cast<uint32_t*>(p);
 
   uint32_t *ka = keys, *va = vals, *kb = k2, *vb = v2;
-  const int passes = (bits + 7) / 8;
+  const int passes = (nbits + 7) / 8;
+  const int digit = passes * 7 >= nbits ? 7 : 8;   // 7-bit digits when they cover the range in as many passes (one ballot less per key)
   // algorithmic bytes: 4 (histogram read) + 16 (pair read + write) per element per pass
   vp_stage stage(ctx, "k1b_radix_sort", st, 5 * passes, double(n) * 20.0 * passes);
   for (int pass = 0; pass < passes; ++pass) {
-    const int shift = pass * 8;
-    k_tile_hist<<<nb, kThreads, 0, st>>>(ka, n, shift, hist, nb);
-    k_scan_sums<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
-    k_scan_top<<<1, kThreads, 0, st>>>(sums, nchunks);
-    k_scan_apply<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
-    k_scatter<<<nb, kThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nb);
+    // a digit reaching past the range (or past bit 31) only re-sorts bits a later pass / nothing overrides: harmless for LSD
+    int shift = lo + pass * digit;
+    if (shift + digit > 32) shift = 32 - digit;
+    if (digit == 7) sort_pass<7>(ka, va, kb, vb, n, shift, hist, sums, nb, st);
+    else sort_pass<8>(ka, va, kb, vb, n, shift, hist, sums, nb, st);
     VP_CHECK_LAUNCH();
     uint32_t* t;
     t = ka; ka = kb; kb = t;
@@ -249,4 +272,9 @@ int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, i
     VP_CUDA(cudaMemcpyAsync(vals, va, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
   }
   return VP_OK;
+}
+
+int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
+                       cudaStream_t st) {
+  return vp_sort_pairs_range(ctx, keys, vals, n, 0, bits, scratch, st);
 }

@@ -33,7 +33,8 @@ def _pos_seen_by_ann(g, name):
 
 
 # ------------------------------------------------------------------------------------------ radix sort
-@pytest.mark.parametrize("n,bits", [(1, 8), (1000, 8), (4096, 16), (100003, 24), (1 << 20, 30), ((1 << 21) + 17, 32)])
+@pytest.mark.parametrize("n,bits", [(1, 8), (1000, 8), (4096, 16), (100003, 24), (1 << 20, 30), ((1 << 21) + 17, 32),
+                                    (5000, 7), (70001, 14), (300007, 21), (1 << 19, 28)])
 def test_sort_pairs(lib, n, bits):
     import torch
     rng = np.random.default_rng(n)
@@ -102,6 +103,21 @@ def test_nn_edge_cases(lib, orc):
     pos = np.random.default_rng(2).random((3000, 3))
     ref = orc.nn_exact_lattice(pos, qx, qy, qz)
     assert np.array_equal(lib.nn_grid(lib.to_device(pos), qx, qy, qz).cpu().numpy(), ref)
+
+
+def test_nn_dense_cluster_long_rows(lib, orc):
+    """A blob holding far more particles than one row of cells can order in shared memory (> 65536 per row):
+    the cell-list build takes its global-scratch path; the answers stay exact."""
+    rng = np.random.default_rng(21)
+    N = 24
+    blob = 0.5 + 0.004 * rng.standard_normal((260000, 3))
+    pos = np.concatenate([blob, rng.random((N ** 3 - 1000, 3))]).astype(np.float32)
+    rng.shuffle(pos)
+    ax = orc.lattice_axis_lib(1.0, N)
+    ref = orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax)
+    nn = lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy()
+    assert np.array_equal(nn, ref)
+    assert lib.nn_grid_stats()["n_unresolved"] == 0
 
 
 def test_nn_slab_matches_full(lib, orc):
