@@ -172,6 +172,19 @@ __global__ void __launch_bounds__(256) k_row_starts(const uint32_t* __restrict__
       if (i0 + u < n) k4[u] = keys[i0 + u];
   }
   int64_t kp = (i0 == 0 || i0 >= n) ? -1 : int64_t(keys[i0 - 1] >> shift);
+  // almost every warp sees no row boundary at all (2^30 keys, 3e4 rows): leave before the per-key logic
+  bool change = false;
+  {
+    int64_t prev = kp;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < n) {
+        const int64_t k = int64_t(k4[u] >> shift);
+        change |= (k != prev) || (i0 + u == n - 1);
+        prev = k;
+      }
+  }
+  if (!__any_sync(0xffffffffu, change)) return;
 #pragma unroll 1
   for (int u = 0; u < 4; ++u) {
     const int64_t i = i0 + u;
