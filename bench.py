@@ -19,6 +19,7 @@ import time
 
 import numpy as np
 
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "large-velocity-power-spectrum_b200"))
@@ -199,7 +200,19 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout when the first communicator
+        # comes up, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     free_b, total_b = torch.cuda.mem_get_info()
     wname = args.workload or ("cfg4" if free_b > 140e9 else "cfg2")
@@ -273,8 +286,16 @@ def main():
                        "GBps": None if gbs is None else round(gbs, 1), "frac": None if gbs is None else round(gbs / hbm_peak, 4)}
     dom = max(table, key=lambda n: table[n]["ms_per_step"])
     kernel_ms = sum(v["ms_per_step"] for v in table.values())
+    # DRAM bytes of that kernel's launch from a committed `ncu --set full` capture of the same workload (single GPU only)
+    traffic, traffic_src = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wname, {}) if world == 1 else {}
+        if dom in cap:
+            traffic, traffic_src = float(cap[dom]), cap.get("source")
+    except (OSError, ValueError):
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-            "frac": table[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": table[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "share_of_step": round(table[dom]["ms_per_step"] / kernel_ms, 4) if kernel_ms > 0 else None,
             "alg_bytes_per_launch": table[dom]["alg_GB_per_step"] * 1e9 / max(1, table[dom]["launches_per_step"])}
 
