@@ -60,6 +60,8 @@ extern "C" int vp_ctx_destroy(vp_ctx* ctx) {
       if (d != ctx->slab_rank && ctx->slab_peer[d]) cudaIpcCloseMemHandle(ctx->slab_peer[d]);
   if (ctx->slab_recv) cudaFree(ctx->slab_recv);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
+  if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
     if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);

@@ -86,6 +86,8 @@ struct vp_ctx {
   bool slab_open = false;
   cudaStream_t copy_stream = nullptr;     // host-buffer entry point: H2D chunks overlap the keygen/pack kernel
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+  cudaStream_t pack_stream = nullptr;     // payload chunks are packed here while the gridding runs on the caller's stream
+  cudaEvent_t ev_pack = nullptr;
 };
 
 // Stack discipline: every entry point opens a vp_arena_scope (restores the offset on exit), calls
@@ -123,6 +125,17 @@ size_t vp_host_chunk_staging_bytes(int64_t chunk, int dtype, bool has_rho);
 int vp_nn_grid_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,
                             const double* qy, int ny, const double* qz, int nz, double lcell3, int32_t* nn_pos_d, float* spay_d,
                             cudaStream_t st);
+// Positions only: pos_h chunks -> resident pos_d on the copy stream, keys/records made chunk by chunk behind them, then the
+// whole gridding on `st`; nn_idx_d [nx,ny,nz] = ORIGINAL particle index.  Everything is enqueued, nothing is waited for.
+int vp_nn_grid_host_pos(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,
+                        const double* qy, int ny, const double* qz, int nz, int32_t* nn_idx_d, cudaStream_t st);
+// vel_h / rho_h chunks -> pay_d [np] float4 (v', m) in INPUT order: copies on the copy stream (behind whatever is queued
+// there), packing on a side stream; `st` is made to wait for the last chunk.
+int vp_pack_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, int dtype, int64_t np, double lcell3, void* staging_d, float* pay_d,
+                         cudaStream_t st);
+int vp_host_streams(vp_ctx* ctx);
+// copy and pack streams wait for everything queued on st so far (scratch of earlier calls is then free to reuse)
+int vp_host_fork(vp_ctx* ctx, cudaStream_t st);
 
 // internal forms used by pipeline.cu (typed device pointers, arena already reserved by the caller)
 size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* qx, int nx, const double* qy, int ny,

@@ -795,7 +795,8 @@ struct NNPayload {
 
 template <typename T>
 int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int nx, const double* qy, int ny,
-                  const double* qz, int nz, int32_t* nn, const NNPayload<T>* pay, const vp_nn_opts* opts, cudaStream_t st) {
+                  const double* qz, int nz, int32_t* nn, const NNPayload<T>* pay, const vp_nn_opts* opts, cudaStream_t st,
+                  const vp_host_chunks* host_pos = nullptr) {
   const int64_t nnodes = int64_t(nx) * ny * nz;
   VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
   VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
@@ -912,17 +913,27 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         else k_keygen_pack<T, false, 1><<<nb, 256, 0, st>>>(p, pin, n_c, i0, g, keys, vals, packed, kept_d);
       }
     };
-    if (has_pay && pay->host) {
+    if (host_pos) {
+      // positions arrive from the host in chunks (copy stream); keys + records of chunk c are made while chunk c+1 moves
+      VP_REQUIRE(!has_pay && o.row_stride == 0 && !o.use_x_keep, "vp_nn_grid: host position streaming is the plain compact form");
+      VP_TRY(vp_host_streams(ctx));
+      const int64_t chunk = host_pos->chunk;
+      T* posd = const_cast<T*>(pos);
+      VP_CUDA(cudaEventRecord(ctx->ev_used[0], st));   // order the copy stream after everything already queued on st
+      VP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+      int c = 0;
+      for (int64_t i0 = 0; i0 < np; i0 += chunk, ++c) {
+        const int64_t n_c = np - i0 < chunk ? np - i0 : chunk;
+        VP_CUDA(cudaMemcpyAsync(posd + 3 * i0, static_cast<const T*>(host_pos->pos_h) + 3 * i0, size_t(n_c) * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
+        VP_CUDA(cudaEventRecord(ctx->ev_h2d[c & 1], ctx->copy_stream));
+        VP_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[c & 1], 0));
+        launch(posd + 3 * i0, nullptr, nullptr, n_c, i0);
+      }
+    } else if (has_pay && pay->host) {
       VP_REQUIRE(o.row_stride == 0, "vp_nn_grid: host chunk streaming needs compact arrays");
       // host arrays: H2D chunks on the copy stream, keygen/pack of chunk c overlaps the transfer of chunk c+1
       const vp_host_chunks* hc = pay->host;
-      if (!ctx->copy_stream) {
-        VP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int e = 0; e < 2; ++e) {
-          VP_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[e], cudaEventDisableTiming));
-          VP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[e], cudaEventDisableTiming));
-        }
-      }
+      VP_TRY(vp_host_streams(ctx));
       const int64_t chunk = hc->chunk;
       const size_t sb = vp_host_chunk_staging_bytes(chunk, sizeof(T) == 8 ? VP_F64 : VP_F32, hc->rho_h != nullptr);
       char* stage_d = static_cast<char*>(vp_arena_alloc(ctx, sb));
@@ -1335,6 +1346,94 @@ int vp_nn_grid_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, 
   NNPayload<double> pay;
   pay.lcell3 = lcell3; pay.spay_out = reinterpret_cast<float4*>(spay_d); pay.nn_pos_out = nn_pos_d; pay.host = hc;
   return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx, nx, qy, ny, qz, nz, nullptr, &pay, nullptr, st);
+}
+
+int vp_host_streams(vp_ctx* ctx) {
+  if (!ctx->copy_stream) {
+    VP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // highest priority: the small pack kernels must slip in between the blocks of the gridding kernels, or the two staging
+    // buffers (and with them the upload) stall behind whatever large grid is resident
+    int prio_lo = 0, prio_hi = 0;
+    VP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    VP_CUDA(cudaStreamCreateWithPriority(&ctx->pack_stream, cudaStreamNonBlocking, prio_hi));
+    for (int e = 0; e < 2; ++e) {
+      VP_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[e], cudaEventDisableTiming));
+      VP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[e], cudaEventDisableTiming));
+    }
+    VP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
+  }
+  return VP_OK;
+}
+
+int vp_host_fork(vp_ctx* ctx, cudaStream_t st) {
+  VP_TRY(vp_host_streams(ctx));
+  VP_CUDA(cudaEventRecord(ctx->ev_pack, st));
+  VP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pack, 0));
+  VP_CUDA(cudaStreamWaitEvent(ctx->pack_stream, ctx->ev_pack, 0));
+  return VP_OK;
+}
+
+int vp_nn_grid_host_pos(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,
+                        const double* qy, int ny, const double* qz, int nz, int32_t* nn_idx_d, cudaStream_t st) {
+  VP_REQUIRE(ctx && hc && hc->pos_h && hc->chunk > 0 && pos_d && nn_idx_d, "vp_nn_grid_host_pos: bad argument");
+  if (dtype == VP_F32)
+    return nn_grid_typed<float>(ctx, static_cast<const float*>(pos_d), np, qx, nx, qy, ny, qz, nz, nn_idx_d, nullptr, nullptr, st, hc);
+  return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx, nx, qy, ny, qz, nz, nn_idx_d, nullptr, nullptr, st, hc);
+}
+
+// (v', m) of one chunk, the arithmetic of k_keygen_pack (input dtype, then rounded to f32)
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack_payload(const T* __restrict__ vel, const T* __restrict__ rho, int64_t n, T lcell3,
+                                                       float4* __restrict__ pay) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+  T m = lcell3;
+  if (rho) {
+    const T rr = rho[i];
+    vx = (vx * rr) / rr;
+    vy = (vy * rr) / rr;
+    vz = (vz * rr) / rr;
+    m = rr * lcell3;
+  }
+  pay[i] = make_float4(float(vx), float(vy), float(vz), float(m));
+}
+
+template <typename T>
+static int pack_payload_host_typed(vp_ctx* ctx, const vp_host_chunks* hc, int64_t np, double lcell3, char* stage_d, float4* pay,
+                                   cudaStream_t st) {
+  VP_TRY(vp_host_streams(ctx));
+  const int64_t chunk = hc->chunk;
+  const size_t vb = vp_align256(size_t(chunk) * 3 * sizeof(T)), rb = vp_align256(size_t(chunk) * sizeof(T));
+  // (the side streams were ordered behind the caller's earlier work by vp_host_fork; they must NOT wait for the gridding
+  // that has just been queued on st)
+  int c = 0;
+  for (int64_t i0 = 0; i0 < np; i0 += chunk, ++c) {
+    const int64_t n_c = np - i0 < chunk ? np - i0 : chunk;
+    const int b = c & 1;
+    T* vbuf = reinterpret_cast<T*>(stage_d + size_t(b) * (vb + rb));
+    T* rbuf = hc->rho_h ? reinterpret_cast<T*>(stage_d + size_t(b) * (vb + rb) + vb) : nullptr;
+    if (c >= 2) VP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));   // staging buffer free again
+    VP_CUDA(cudaMemcpyAsync(vbuf, static_cast<const T*>(hc->vel_h) + 3 * i0, size_t(n_c) * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (rbuf) VP_CUDA(cudaMemcpyAsync(rbuf, static_cast<const T*>(hc->rho_h) + i0, size_t(n_c) * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
+    VP_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_stream));
+    VP_CUDA(cudaStreamWaitEvent(ctx->pack_stream, ctx->ev_h2d[b], 0));
+    k_pack_payload<T><<<unsigned((n_c + 255) / 256), 256, 0, ctx->pack_stream>>>(vbuf, rbuf, n_c, T(lcell3), pay + i0);
+    VP_CUDA(cudaEventRecord(ctx->ev_used[b], ctx->pack_stream));
+  }
+  VP_CHECK_LAUNCH();
+  ctx->n_launch += c;
+  VP_CUDA(cudaEventRecord(ctx->ev_pack, ctx->pack_stream));
+  VP_CUDA(cudaStreamWaitEvent(st, ctx->ev_pack, 0));
+  return VP_OK;
+}
+
+int vp_pack_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, int dtype, int64_t np, double lcell3, void* staging_d, float* pay_d,
+                         cudaStream_t st) {
+  VP_REQUIRE(ctx && hc && hc->vel_h && hc->chunk > 0 && staging_d && pay_d, "vp_pack_payload_host: bad argument");
+  if (dtype == VP_F32)
+    return pack_payload_host_typed<float>(ctx, hc, np, lcell3, static_cast<char*>(staging_d), reinterpret_cast<float4*>(pay_d), st);
+  return pack_payload_host_typed<double>(ctx, hc, np, lcell3, static_cast<char*>(staging_d), reinterpret_cast<float4*>(pay_d), st);
 }
 
 size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* qx, int nx, const double* qy, int ny,

@@ -47,7 +47,8 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   const int n_pplanes = want_p ? (strict ? 1 : 3) : 0;
   const int nplanes = (want_v ? 3 : 0) + n_pplanes + (want_e ? 1 : 0);
 
-  // host arrays are streamed in chunks: only the positions stay resident (the exact search reads them)
+  // host arrays are streamed in chunks: only the positions stay resident (the exact search reads them); velocity and
+  // density chunks pass through two staging buffers into the (v', m) records
   const int64_t chunk = np < (int64_t(1) << 24) ? np : (int64_t(1) << 24);
   size_t own = 0;
   if (on_host) own += vp_align256(size_t(np) * 3 * es) + vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 1024;
@@ -75,9 +76,17 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   VP_REQUIRE(nn_pos && spay && psum_d && ns_d, "particles_to_pk: arena carve failed");
 
   if (on_host) {
+    // Host arrays: the positions cross PCIe first and the whole gridding (keys as the chunks land, sort, search) runs
+    // while velocity and density follow; those are packed chunk by chunk into (v', m) records in INPUT order on a side
+    // stream, and the planes are gathered through the ORIGINAL particle index (nn_pos / spay then hold that index and
+    // those records).  Only the plane gather and the transforms remain after the last byte has arrived.
     vp_host_chunks hc;
     hc.pos_h = pos; hc.vel_h = vel; hc.rho_h = rho; hc.chunk = chunk;
-    VP_TRY(vp_nn_grid_payload_host(ctx, &hc, pos_res, dtype, np, qx, N, qy, N, qz, N, lcell3, nn_pos, spay, st));
+    void* staging = vp_arena_alloc(ctx, vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 512);
+    VP_REQUIRE(staging, "particles_to_pk: arena carve failed (staging)");
+    VP_TRY(vp_host_fork(ctx, st));
+    VP_TRY(vp_nn_grid_host_pos(ctx, &hc, pos_res, dtype, np, qx, N, qy, N, qz, N, nn_pos, st));
+    VP_TRY(vp_pack_payload_host(ctx, &hc, dtype, np, lcell3, staging, spay, st));
   } else {
     VP_TRY(vp_nn_grid_payload(ctx, pos_d, vel_d, rho_d, dtype, np, qx, N, qy, N, qz, N, lcell3, nullptr, nn_pos, spay, nullptr, st));
   }

@@ -425,8 +425,9 @@ def test_script_dropin_writes_reference_pk_txt(lib, golden, tmp_path):
 
 
 def test_host_chunk_streaming_equals_device_path(lib, orc):
-    """vp_host_particles_to_pk streams the host arrays in 2^24-particle chunks (H2D overlapped with keygen/pack);
-    three chunks here.  Must be bit-identical to the device-resident path."""
+    """vp_host_particles_to_pk streams the host arrays in 2^24-particle chunks: positions first (gridding overlaps the
+    rest of the upload), then velocity/density packed into input-order records on a side stream, planes gathered through
+    the original particle index.  Three chunks here.  Must be bit-identical to the device-resident path."""
     import torch
     N, Np, L = 256, (1 << 25) + 777, 1.0
     g = torch.Generator(device="cuda").manual_seed(5)
