@@ -2,7 +2,8 @@
 """Drop-in for the reference driver `scripts/parallel_optimized.py` on B200.
 
 Same command line (-i -o -N -M -l -b -f), same output file `<output>/Pk.txt` = np.savetxt of [nbins,4]
-(k, P, Psum, Nsample), same helper names (`planner`, `FFTW_power`, `pair_power`, `hist_sample`, `main`).
+(k, P, Psum, Nsample), same helper names (`planner`, `FFTW_vector_power`, `FFTW_power`, `pair_power`, `hist_sample`,
+`main`).
 
     python parallel_optimized.py -i snapshot.hdf5 -o out/ -N 1024 -f                      # one GPU
     python -m torch.distributed.run --nproc-per-node 8 parallel_optimized.py -i ... -f     # one process per GPU
@@ -72,18 +73,32 @@ def planner(n_total_res, l_total_length, n_box_affordable, n_total_threads):
     return n_loops_per_axis ** 3, tpa, int(n_box), int(n_box) / n_total_res * l_total_length
 
 
+def _real_cube(f, torch):
+    f = np.asarray(f)
+    if np.iscomplexobj(f):
+        if np.abs(f.imag).max() > 0:
+            raise Exception("vpower_b200: the power helpers take the real (unfolded) field")
+        f = f.real
+    return _lib.to_device(np.ascontiguousarray(f), dtype=torch.float32)
+
+
+def FFTW_vector_power(fx, fy, fz, Lbox, Nsize):
+    """sum over the three components of 1/2 |const * FFT(f_c)|^2, const = (Lbox/2pi)^1.5 / Nsize^3 (:92-121): one
+    in-place r2c transform per component, accumulated into one power cube on the device."""
+    import torch
+    const = (Lbox / (2 * np.pi)) ** 1.5 / Nsize ** 3
+    plan = _lib.PkPlan(Nsize, 2 * np.pi * np.fft.fftfreq(Nsize, Lbox / float(Nsize)), np.array([0.0, 1.0]))
+    P = plan.power_cube([_real_cube(f, torch) for f in (fx, fy, fz)])
+    return (P * (0.5 * const * const)).cpu().numpy().astype(np.float32)
+
+
 def FFTW_power(f, Lbox, Nsize):
     """1/2 |const * FFT(f)|^2 with const = (Lbox/2pi)^1.5 / Nsize^3 (:124-141).  f: real [N,N,N] cube
     (the unfolded path never forms the complex folded field)."""
     import torch
-    f = np.asarray(f)
-    if np.iscomplexobj(f):
-        if np.abs(f.imag).max() > 0:
-            raise Exception("vpower_b200: FFTW_power takes the real (unfolded) field")
-        f = f.real
     const = (Lbox / (2 * np.pi)) ** 1.5 / Nsize ** 3
     plan = _lib.PkPlan(Nsize, 2 * np.pi * np.fft.fftfreq(Nsize, Lbox / float(Nsize)), np.array([0.0, 1.0]))
-    P = plan.power_cube([_lib.to_device(np.ascontiguousarray(f), dtype=torch.float32)])
+    P = plan.power_cube([_real_cube(f, torch)])
     return (P * (0.5 * const * const)).cpu().numpy().astype(np.float32)
 
 

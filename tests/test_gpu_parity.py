@@ -422,6 +422,14 @@ def test_script_dropin_writes_reference_pk_txt(lib, golden, tmp_path):
     pairs = mod.pair_power(P, 1.0, 16)
     h = mod.hist_sample(pairs, 2 * np.pi, np.pi * 16, 2 * np.pi)
     assert pairs.shape == (4096, 2) and h.shape == (8, 4) and np.array_equal(h[:, 3], ref[:, 3])
+    # FFTW_vector_power / FFTW_power (:92-141): 1/2 |const FFT|^2 summed over components, against numpy's c2c transform
+    f3 = np.random.default_rng(1).standard_normal((3, 16, 16, 16)).astype(np.float32)
+    const = (2.0 / (2 * np.pi)) ** 1.5 / 16 ** 3
+    want = sum(0.5 * np.abs(np.fft.fftn(f.astype(np.float64)) * const) ** 2 for f in f3)
+    got3 = mod.FFTW_vector_power(f3[0], f3[1], f3[2], 2.0, 16)
+    assert got3.dtype == np.float32 and np.allclose(got3, want, rtol=2e-4, atol=1e-6 * want.max())
+    want1 = 0.5 * np.abs(np.fft.fftn(f3[0].astype(np.float64)) * const) ** 2
+    assert np.allclose(mod.FFTW_power(f3[0].astype(np.complex64), 2.0, 16), want1, rtol=2e-4, atol=1e-6 * want1.max())
 
 
 def test_host_chunk_streaming_equals_device_path(lib, orc):
