@@ -164,10 +164,27 @@ class BoxField:
             self._materialise()
         return self._host[name]
 
-    vx = property(lambda self: self._get("vx"))
-    vy = property(lambda self: self._get("vy"))
-    vz = property(lambda self: self._get("vz"))
-    mass = property(lambda self: self._get("mass"))
+    def _set(self, name, value):
+        # assigning a plane (trim, down_sample, user code) detaches the field from its device-resident form
+        if self._dev is not None:
+            self._materialise()
+            self._dev = None
+        self._host[name] = value
+
+    vx = property(lambda self: self._get("vx"), lambda self, a: self._set("vx", a))
+    vy = property(lambda self: self._get("vy"), lambda self, a: self._set("vy", a))
+    vz = property(lambda self: self._get("vz"), lambda self, a: self._set("vz", a))
+    mass = property(lambda self: self._get("mass"), lambda self, a: self._set("mass", a))
+
+    def __getitem__(self, index):                                   # interp.py:474
+        return BoxField(self.get_v()[index], self.mass[index], self.Lcell)
+
+    def __array__(self, dtype=None, copy=None):                     # interp.py:478
+        a = self.get_data()
+        return a if dtype is None else a.astype(dtype)
+
+    def __array_wrap__(self, arr, context=None, return_scalar=False):   # interp.py:482 (mass = arr[..., :3], as there)
+        return BoxField(arr[..., :3], arr[..., :3], self.Lcell)
 
     def get_v(self):
         return np.stack((self.vx, self.vy, self.vz), axis=3)
@@ -177,6 +194,30 @@ class BoxField:
 
     def get_data(self):
         return np.stack((self.vx, self.vy, self.vz, self.mass), axis=3)
+
+    # -- lattice surgery (interp.py:611-636) -----------------------------------------------------------
+    def trim(self, Nmargin, Nbrick) -> None:
+        """Keep the central Nbrick^3 block (drop Nmargin nodes on every side); Nsize and Lbox follow as in the reference."""
+        n1, n2 = Nmargin, Nmargin + Nbrick
+        vx, vy, vz, m = self.vx, self.vy, self.vz, self.mass
+        self.vx, self.vy, self.vz = vx[n1:n2, n1:n2, n1:n2], vy[n1:n2, n1:n2, n1:n2], vz[n1:n2, n1:n2, n1:n2]
+        self.mass = m[n1:n2, n1:n2, n1:n2]
+        self.Nsize = self.Nsize - 2 * Nmargin
+        self.Lbox = self.Lbox * Nbrick / (Nbrick + 2 * Nmargin)
+
+    def down_sample(self, n) -> None:
+        """Average n^3 blocks of mass and momentum; the velocity becomes the mass-weighted one.  `Nsize /= n` turns Nsize
+        into a float exactly as interp.py:635 does."""
+        px, py, pz = (down_sample(c * self.mass, n) for c in (self.vx, self.vy, self.vz))
+        m = down_sample(self.mass, n)
+        m[np.where(m == 0)] = 1e-10                                   # avoid zero mass (:630)
+        self.mass = m
+        self.vx, self.vy, self.vz = px / m, py / m, pz / m
+        self.Nsize /= n
+        self.Lcell *= n
+
+    def mean_kinetic_energy(self) -> float:                          # interp.py:639
+        return 0.5 * np.mean(self.mass * (self.vx ** 2 + self.vy ** 2 + self.vz ** 2))
 
     # -- totals (interp.py:639-666) -----------------------------------------------------------------
     def total_mass(self):
@@ -379,6 +420,17 @@ def _scalar_power(f, Lbox, Nsize):
     return _power_cube([f], Lbox, Nsize)
 
 
+def _FFTW_vector_power(f, Lbox, Nsize, fft_object=None):
+    """interp.py:1390-1405 with the transform on the GPU: f is [N,N,N,3]; `fft_object` (a pyFFTW plan there) is ignored."""
+    f = np.asarray(f)
+    return _vector_power(f[..., 0], f[..., 1], f[..., 2], Lbox, Nsize)
+
+
+def _FFTW_scalar_power(f, Lbox, Nsize, fft_object=None):
+    """interp.py:1424-1437; `fft_object` is ignored."""
+    return _scalar_power(f, Lbox, Nsize)
+
+
 def _pair_power(Pk, Lbox, Nsize, shift=np.array([0, 0, 0])):
     """[N^3,2] (|k|, P) pairs, C order.  interp.py:1440-1467 (shift applied only where > 0, as there)."""
     ks = _k_axis(Lbox, Nsize)
@@ -398,6 +450,30 @@ def _hist_sample(Pk_pair, kmin, kmax, spacing):
         P = Psum / Nsample
     P[Nsample == 0] = 0
     return np.column_stack((centres, P, Psum, Nsample))
+
+
+def down_sample(r, n):
+    """Mean over n^3 blocks (interp.py:1255-1267).  The reference indexes a fourth axis unconditionally; here trailing axes
+    are optional, so the 3-D planes BoxField.down_sample passes work as well."""
+    if n == 1:
+        return r
+    d = 0.0
+    for i in range(n):
+        for j in range(n):
+            for k in range(n):
+                d = d + r[i::n, j::n, k::n, ...]
+    d /= n ** 3
+    return d
+
+
+def _vec_to_vm_grid(vec_grid, Lcell):
+    """[N,N,N,4] (rho*v, rho) -> (v [N,N,N,3], m [N,N,N]) in place, interp.py:970-992 (deprecated there, kept for callers)."""
+    rho_grid = vec_grid[:, :, :, 3]
+    m_grid = rho_grid * Lcell ** 3
+    vec_grid[:, :, :, 0] /= rho_grid
+    vec_grid[:, :, :, 1] /= rho_grid
+    vec_grid[:, :, :, 2] /= rho_grid
+    return vec_grid[:, :, :, 0:3], m_grid
 
 
 def check_conservation(gasParticles, boxField) -> tuple:

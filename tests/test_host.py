@@ -184,3 +184,39 @@ def test_fft_index_model():
         L = 16 * R2 * R3
         x = rng.normal(size=L) + 1j * rng.normal(size=L)
         assert np.abs(model(x, R2, R3) - np.fft.fft(x)).max() < 1e-11 * L
+
+
+
+def test_boxfield_host_helpers_match_reference_expressions():
+    """trim / down_sample / mean_kinetic_energy / slicing / _vec_to_vm_grid (interp.py:474-482, 611-641, 970-992, 1255-1267):
+    pure host code, checked against the reference's expressions written out independently."""
+    import vpower.interp as vi
+    rng = np.random.default_rng(3)
+    N = 12
+    v = rng.standard_normal((N, N, N, 3))
+    m = 1.0 + rng.random((N, N, N))
+    bf = vi.BoxField(v.copy(), m.copy(), 0.25)
+    assert bf.Nsize == N and bf.Lbox == N * 0.25
+    assert np.isclose(bf.mean_kinetic_energy(), 0.5 * np.mean(m * (v ** 2).sum(-1)))
+    sub = bf[2:6]
+    assert isinstance(sub, vi.BoxField) and sub.Nsize == 4 and np.array_equal(sub.vy, v[2:6, ..., 1])
+    assert np.array_equal(np.asarray(bf), np.concatenate([v, m[..., None]], axis=3))
+    # trim
+    t = vi.BoxField(v.copy(), m.copy(), 0.25)
+    t.trim(2, 8)
+    assert t.Nsize == 8 and np.isclose(t.Lbox, N * 0.25 * 8 / 12)
+    assert np.array_equal(t.vx, v[2:10, 2:10, 2:10, 0]) and np.array_equal(t.mass, m[2:10, 2:10, 2:10])
+    # down_sample: block means of mass and momentum, mass-weighted velocity
+    d = vi.BoxField(v.copy(), m.copy(), 0.25)
+    d.down_sample(2)
+    blk = lambda a: a.reshape(N // 2, 2, N // 2, 2, N // 2, 2).mean(axis=(1, 3, 5))
+    assert np.allclose(d.mass, blk(m)) and np.allclose(d.vz, blk(v[..., 2] * m) / blk(m))
+    assert d.Nsize == N / 2 and d.Lcell == 0.5
+    assert np.allclose(vi.down_sample(np.stack([m, m], axis=3), 3)[..., 1], m.reshape(4, 3, 4, 3, 4, 3).mean(axis=(1, 3, 5)))
+    assert vi.down_sample(m, 1) is m
+    # _vec_to_vm_grid
+    rho = 1.0 + rng.random((N, N, N))
+    vec = np.concatenate([v * rho[..., None], rho[..., None]], axis=3)
+    vv, mm = vi._vec_to_vm_grid(vec, 0.5)
+    assert np.allclose(vv, v) and np.allclose(mm, rho * 0.125)
+
