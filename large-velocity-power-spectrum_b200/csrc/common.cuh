@@ -122,9 +122,6 @@ struct vp_host_chunks {
   int64_t chunk = 0;     // particles per chunk
 };
 size_t vp_host_chunk_staging_bytes(int64_t chunk, int dtype, bool has_rho);
-int vp_nn_grid_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,
-                            const double* qy, int ny, const double* qz, int nz, double lcell3, int32_t* nn_pos_d, float* spay_d,
-                            cudaStream_t st);
 // Positions only: pos_h chunks -> resident pos_d on the copy stream, keys/records made chunk by chunk behind them, then the
 // whole gridding on `st`; nn_idx_d [nx,ny,nz] = ORIGINAL particle index.  Everything is enqueued, nothing is waited for.
 int vp_nn_grid_host_pos(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,

@@ -790,7 +790,6 @@ struct NNPayload {
   double lcell3 = 1.0;
   float4* spay_out = nullptr;    // [np]
   int32_t* nn_pos_out = nullptr;  // [nnodes]
-  const vp_host_chunks* host = nullptr;   // vel/rho (and the source of pos) are HOST arrays streamed in chunks
 };
 
 template <typename T>
@@ -801,7 +800,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
   VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
   const bool has_pay = pay != nullptr;
-  if (has_pay) VP_REQUIRE((pay->vel || pay->host) && pay->spay_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
+  if (has_pay) VP_REQUIRE(pay->vel && pay->spay_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
   vp_nn_opts o;
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
@@ -877,9 +876,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
 
   // ---- scratch
   const NNScratch sc = nn_scratch(np, has_pay, ncells, nrows, nnodes);
-  const size_t stage_bytes = (has_pay && pay->host) ? vp_host_chunk_staging_bytes(pay->host->chunk, sizeof(T) == 8 ? VP_F64 : VP_F32, pay->host->rho_h != nullptr) + 512 : 0;
   vp_arena_scope scope(ctx);
-  VP_TRY(vp_arena_reserve(ctx, sc.total + stage_bytes));
+  VP_TRY(vp_arena_reserve(ctx, sc.total));
   uint32_t* keys = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
   uint32_t* vals = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
   void* packed = vp_arena_alloc(ctx, sc.packed);
@@ -896,7 +894,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   if (np > 0) {
     // read pos (+vel, rho), write key, slot and the packed record
     const double es = sizeof(T);
-    vp_stage stage(ctx, "k1a_keygen_pack", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho || (pay->host && pay->host->rho_h) ? 1 : 0)) * es + 8.0 + 32.0 : 3 * es + 8.0 + 16.0));
+    vp_stage stage(ctx, "k1a_keygen_pack", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 8.0 + 32.0 : 3 * es + 8.0 + 16.0));
     unsigned long long* kept_d = &ctx->nn_stats_d->n_kept;
     auto launch = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
@@ -928,34 +926,6 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         VP_CUDA(cudaEventRecord(ctx->ev_h2d[c & 1], ctx->copy_stream));
         VP_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[c & 1], 0));
         launch(posd + 3 * i0, nullptr, nullptr, n_c, i0);
-      }
-    } else if (has_pay && pay->host) {
-      VP_REQUIRE(o.row_stride == 0, "vp_nn_grid: host chunk streaming needs compact arrays");
-      // host arrays: H2D chunks on the copy stream, keygen/pack of chunk c overlaps the transfer of chunk c+1
-      const vp_host_chunks* hc = pay->host;
-      VP_TRY(vp_host_streams(ctx));
-      const int64_t chunk = hc->chunk;
-      const size_t sb = vp_host_chunk_staging_bytes(chunk, sizeof(T) == 8 ? VP_F64 : VP_F32, hc->rho_h != nullptr);
-      char* stage_d = static_cast<char*>(vp_arena_alloc(ctx, sb));
-      VP_REQUIRE(stage_d, "vp_nn_grid: arena carve failed (host chunk staging)");
-      const size_t vb = vp_align256(size_t(chunk) * 3 * sizeof(T)), rb = vp_align256(size_t(chunk) * sizeof(T));
-      T* posd = const_cast<T*>(pos);
-      VP_CUDA(cudaEventRecord(ctx->ev_used[0], st));   // order the copy stream after everything already queued on st
-      VP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
-      int c = 0;
-      for (int64_t i0 = 0; i0 < np; i0 += chunk, ++c) {
-        const int64_t n_c = np - i0 < chunk ? np - i0 : chunk;
-        const int b = c & 1;
-        T* vbuf = reinterpret_cast<T*>(stage_d + size_t(b) * (vb + rb));
-        T* rbuf = hc->rho_h ? reinterpret_cast<T*>(stage_d + size_t(b) * (vb + rb) + vb) : nullptr;
-        if (c >= 2) VP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[b], 0));   // staging buffer free again
-        VP_CUDA(cudaMemcpyAsync(posd + 3 * i0, static_cast<const T*>(hc->pos_h) + 3 * i0, size_t(n_c) * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
-        VP_CUDA(cudaMemcpyAsync(vbuf, static_cast<const T*>(hc->vel_h) + 3 * i0, size_t(n_c) * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
-        if (rbuf) VP_CUDA(cudaMemcpyAsync(rbuf, static_cast<const T*>(hc->rho_h) + i0, size_t(n_c) * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
-        VP_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_stream));
-        VP_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[b], 0));
-        launch(posd + 3 * i0, vbuf, rbuf, n_c, i0);
-        VP_CUDA(cudaEventRecord(ctx->ev_used[b], st));
       }
     } else {
       launch(pos, has_pay ? pay->vel : nullptr, has_pay ? pay->rho : nullptr, np, 0);
@@ -1332,20 +1302,6 @@ extern "C" int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d,
 size_t vp_host_chunk_staging_bytes(int64_t chunk, int dtype, bool has_rho) {
   const size_t es = dtype == VP_F64 ? 8 : 4;
   return 2 * (vp_align256(size_t(chunk) * 3 * es) + (has_rho ? vp_align256(size_t(chunk) * es) : vp_align256(size_t(chunk) * es)));
-}
-
-int vp_nn_grid_payload_host(vp_ctx* ctx, const vp_host_chunks* hc, void* pos_d, int dtype, int64_t np, const double* qx, int nx,
-                            const double* qy, int ny, const double* qz, int nz, double lcell3, int32_t* nn_pos_d, float* spay_d,
-                            cudaStream_t st) {
-  VP_REQUIRE(ctx && hc && hc->pos_h && hc->vel_h && hc->chunk > 0 && pos_d && nn_pos_d && spay_d, "vp_nn_grid_payload_host: bad argument");
-  if (dtype == VP_F32) {
-    NNPayload<float> pay;
-    pay.lcell3 = lcell3; pay.spay_out = reinterpret_cast<float4*>(spay_d); pay.nn_pos_out = nn_pos_d; pay.host = hc;
-    return nn_grid_typed<float>(ctx, static_cast<const float*>(pos_d), np, qx, nx, qy, ny, qz, nz, nullptr, &pay, nullptr, st);
-  }
-  NNPayload<double> pay;
-  pay.lcell3 = lcell3; pay.spay_out = reinterpret_cast<float4*>(spay_d); pay.nn_pos_out = nn_pos_d; pay.host = hc;
-  return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx, nx, qy, ny, qz, nz, nullptr, &pay, nullptr, st);
 }
 
 int vp_host_streams(vp_ctx* ctx) {
