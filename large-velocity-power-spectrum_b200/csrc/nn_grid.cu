@@ -582,16 +582,40 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
       bpos = -1;
       const int nyb = y1 - y0 + 1;
       const int nrows = (x1 - x0 + 1) * nyb;
-      for (int rr = lane; rr < nrows; rr += 32) {
-        int X = x0 + rr / nyb, Y = y0 + rr % nyb;
-        size_t row = (size_t(X) * g.gy + Y) * g.gz;
-        uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
-        for (uint32_t p = s; p < e; ++p) {
+      if (nrows <= 4) {
+        // the 2x2x2 window (almost every listed node ends here): its ~8 particles ONE PER LANE, so that the dependent
+        // chain record -> index -> caller's coordinates is walked once instead of once per particle of a row
+        const int k4 = lane & 3;
+        uint32_t s = 0, e = 0;
+        if (k4 < nrows) {
+          const size_t row = (size_t(x0 + k4 / nyb) * g.gy + (y0 + k4 % nyb)) * g.gz;
+          s = __ldg(start + row + z0);
+          e = __ldg(start + row + z1 + 1);
+        }
+        const uint32_t s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 1);
+        const uint32_t s2 = __shfl_sync(0xffffffffu, s, 2), s3 = __shfl_sync(0xffffffffu, s, 3);
+        const uint32_t c0 = __shfl_sync(0xffffffffu, e - s, 0), c1 = c0 + __shfl_sync(0xffffffffu, e - s, 1);
+        const uint32_t c2 = c1 + __shfl_sync(0xffffffffu, e - s, 2), c3 = c2 + __shfl_sync(0xffffffffu, e - s, 3);
+        for (uint32_t t = lane; t < c3; t += 32) {
+          const uint32_t p = t < c0 ? s0 + t : (t < c1 ? s1 + (t - c0) : (t < c2 ? s2 + (t - c1) : s3 + (t - c2)));
           const int id = __float_as_int(__ldg(&part[p].w));
           const int before = b.idx;
           const size_t pb = size_t(g.ps) * size_t(id);
           consider(b, qx, qy, qz, double(pos[pb]), double(pos[pb + 1]), double(pos[pb + 2]), id);
           if (b.idx != before) bpos = int(p);
+        }
+      } else {
+        for (int rr = lane; rr < nrows; rr += 32) {
+          int X = x0 + rr / nyb, Y = y0 + rr % nyb;
+          size_t row = (size_t(X) * g.gy + Y) * g.gz;
+          uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
+          for (uint32_t p = s; p < e; ++p) {
+            const int id = __float_as_int(__ldg(&part[p].w));
+            const int before = b.idx;
+            const size_t pb = size_t(g.ps) * size_t(id);
+            consider(b, qx, qy, qz, double(pos[pb]), double(pos[pb + 1]), double(pos[pb + 2]), id);
+            if (b.idx != before) bpos = int(p);
+          }
         }
       }
 #pragma unroll
