@@ -49,10 +49,25 @@ __global__ void __launch_bounds__(kThreads) k_tile_hist(const uint32_t* __restri
   if (threadIdx.x < R) sh[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = int64_t(blockIdx.x) * kTile;
+  if (base + kTile <= n) {
+    // full tile: four 16-byte loads per thread
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
+    uint4 v[kItems / 4];
 #pragma unroll
-  for (int r = 0; r < kItems; ++r) {
-    int64_t i = base + r * kThreads + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (R - 1)], 1u);
+    for (int r = 0; r < kItems / 4; ++r) v[r] = k4[r * kThreads + threadIdx.x];
+#pragma unroll
+    for (int r = 0; r < kItems / 4; ++r) {
+      atomicAdd(&sh[(v[r].x >> shift) & (R - 1)], 1u);
+      atomicAdd(&sh[(v[r].y >> shift) & (R - 1)], 1u);
+      atomicAdd(&sh[(v[r].z >> shift) & (R - 1)], 1u);
+      atomicAdd(&sh[(v[r].w >> shift) & (R - 1)], 1u);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+      int64_t i = base + r * kThreads + threadIdx.x;
+      if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (R - 1)], 1u);
+    }
   }
   __syncthreads();
   if (threadIdx.x < R) hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = sh[threadIdx.x];
