@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(kThreads) k_tile_hist(const uint32_t* __restri
   if (threadIdx.x < R) sh[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = int64_t(blockIdx.x) * kTile;
-  if (base + kTile <= n) {
-    // full tile: four 16-byte loads per thread
+  if (base + kTile <= n && (reinterpret_cast<uintptr_t>(keys) & 15) == 0) {
+    // full tile of a 16-byte aligned array: four 16-byte loads per thread
     const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
     uint4 v[kItems / 4];
 #pragma unroll

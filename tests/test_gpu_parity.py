@@ -48,6 +48,23 @@ def test_sort_pairs(lib, n, bits):
     assert np.array_equal(vt.cpu().numpy().view(np.uint32), vals[order])          # stable
 
 
+def test_sort_pairs_unaligned_views(lib):
+    """Key/value arrays that start 4 bytes into an allocation (tensor views): the 16-byte load path must not be taken."""
+    import torch
+    n, bits = 50001, 20
+    rng = np.random.default_rng(7)
+    keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(np.uint32)
+    kt = torch.zeros(n + 1, dtype=torch.int32, device="cuda")[1:]
+    vt = torch.zeros(n + 1, dtype=torch.int32, device="cuda")[1:]
+    kt.copy_(torch.from_numpy(keys.view(np.int32)))
+    vt.copy_(torch.arange(n, dtype=torch.int32))
+    assert kt.data_ptr() % 16 == 4
+    lib.sort_pairs(kt, vt, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(kt.cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(vt.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+
+
 # ------------------------------------------------------------------------------------------ K1 nearest particle
 @pytest.mark.parametrize("name,N", [("lib16", 16), ("lib24", 24), ("lib32c", 32)])
 def test_nn_vs_ann_golden(lib, golden, name, N):
