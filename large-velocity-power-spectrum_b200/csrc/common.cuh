@@ -109,8 +109,8 @@ struct vp_arena_scope {
 size_t vp_sort_scratch_bytes(int64_t n);
 int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
                        cudaStream_t st);
-// stable sort on key bits [lo, lo + nbits) only; iota_vals: vals[] is unset and stands for 0, 1, 2, ...
-int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, bool iota_vals, void* scratch,
+// stable sort on key bits [lo, lo + nbits) only
+int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, void* scratch,
                         cudaStream_t st);
 
 // Host-resident particle arrays streamed to the device in chunks (vp_host_particles_to_pk): positions land in a

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, 
     const int64_t i = base_i + r * 256 + threadIdx.x;
     const int64_t o = g.use_keep ? int64_t(slot0 + nth) : i0 + i;
     ++nth;
-    keys[o] = key[r];   // the slot of a record is its position o: the sort synthesises the values
+    keys[o] = key[r];
+    vals[o] = uint32_t(o);
     if (PAY) {
       T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
       T m = pin.lcell3;
@@ -915,9 +916,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
   int64_t n = np;
   if (np > 0) {
-    // read pos (+vel, rho), write key and the packed record
+    // read pos (+vel, rho), write key, slot and the packed record
     const double es = sizeof(T);
-    vp_stage stage(ctx, "k1a_keygen_pack", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 4.0 + 32.0 : 3 * es + 4.0 + 16.0));
+    vp_stage stage(ctx, "k1a_keygen_pack", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 8.0 + 32.0 : 3 * es + 8.0 + 16.0));
     unsigned long long* kept_d = &ctx->nn_stats_d->n_kept;
     auto launch = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
@@ -965,7 +966,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     VP_CUDA(cudaMemcpyAsync(&ctx->nn_stats_d->n_kept, &kept, 8, cudaMemcpyHostToDevice, st));
   }
   // rows brought together by the sort (stable LSD passes over the row bits only), cells inside a row by the group kernel
-  VP_TRY(vp_sort_pairs_range(ctx, keys, vals, n, g.lb, row_bits, true, scratch, st));
+  VP_TRY(vp_sort_pairs_range(ctx, keys, vals, n, g.lb, row_bits, scratch, st));
   if (n > 0) {
     {
       vp_stage stage(ctx, "k1d_row_starts", st, 1, double(n) * 4.0 + double(nrows) * 4.0);

@@ -122,9 +122,8 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t* __restrict__ 
   }
 }
 
-// (3) stable scatter.  IOTA: the values are the input positions themselves (first pass of a sort whose slots are the
-// identity): nothing is read for them.
-template <int BITS, bool IOTA>
+// (3) stable scatter
+template <int BITS>
 __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                        uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                        int64_t n, int shift, const uint32_t* __restrict__ hist,
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
     int li = wbase + r * 32 + lane;
     bool ok = li < count;
     key[r] = ok ? kin[tile0 + li] : 0u;
-    val[r] = ok ? (IOTA ? uint32_t(tile0 + li) : vin[tile0 + li]) : 0u;
+    val[r] = ok ? vin[tile0 + li] : 0u;
   }
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
@@ -240,30 +239,20 @@ size_t vp_sort_scratch_bytes(int64_t n) {
 
 template <int BITS>
 static void sort_pass(const uint32_t* ka, const uint32_t* va, uint32_t* kb, uint32_t* vb, int64_t n, int shift, uint32_t* hist,
-                      uint32_t* sums, int nb, bool iota, cudaStream_t st) {
+                      uint32_t* sums, int nb, cudaStream_t st) {
   const int64_t m = int64_t(nb) << BITS;
   const int nchunks = int((m + kScanChunk - 1) / kScanChunk);
   k_tile_hist<BITS><<<nb, kThreads, 0, st>>>(ka, n, shift, hist, nb);
   k_scan_sums<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
   k_scan_top<<<1, kThreads, 0, st>>>(sums, nchunks);
   k_scan_apply<<<nchunks, kThreads, 0, st>>>(hist, m, sums);
-  if (iota) k_scatter<BITS, true><<<nb, kThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nb);
-  else k_scatter<BITS, false><<<nb, kThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nb);
+  k_scatter<BITS><<<nb, kThreads, 0, st>>>(ka, va, kb, vb, n, shift, hist, nb);
 }
 
-__global__ void k_iota(uint32_t* a, int64_t n) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = uint32_t(i);
-}
-
-// Stable sort on key bits [lo, lo + nbits); the other bits travel with the key untouched.  iota_vals: vals[] holds
-// nothing yet and stands for 0, 1, 2, ... (synthesised in the first pass, or written out when there is no pass).
-int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, bool iota_vals, void* scratch,
+// Stable sort on key bits [lo, lo + nbits); the other bits travel with the key untouched.
+int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, void* scratch,
                         cudaStream_t st) {
-  if (n <= 1 || nbits <= 0) {
-    if (iota_vals && n > 0) k_iota<<<unsigned((n + 255) / 256), 256, 0, st>>>(vals, n);
-    return VP_OK;
-  }
+  if (n <= 1 || nbits <= 0) return VP_OK;
   VP_REQUIRE(n < (int64_t(1) << 32), "vp_sort_pairs: n=%lld exceeds 2^32", (long long)n);
   VP_REQUIRE(lo >= 0 && lo + nbits <= 32, "vp_sort_pairs: bit range [%d,%d) outside the key", lo, lo + nbits);
   const int nb = int(sort_nblocks(n));
@@ -281,14 +270,13 @@ int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, 
   const int passes = (nbits + 7) / 8;
   const int digit = passes * 7 >= nbits ? 7 : 8;   // 7-bit digits when they cover the range in as many passes (one ballot less per key)
   // algorithmic bytes: 4 (histogram read) + 16 (pair read + write) per element per pass
-  vp_stage stage(ctx, "k1b_radix_sort", st, 5 * passes, double(n) * (20.0 * passes - (iota_vals ? 4.0 : 0.0)));   // no value read in an iota pass
+  vp_stage stage(ctx, "k1b_radix_sort", st, 5 * passes, double(n) * 20.0 * passes);
   for (int pass = 0; pass < passes; ++pass) {
     // a digit reaching past the range (or past bit 31) only re-sorts bits a later pass / nothing overrides: harmless for LSD
     int shift = lo + pass * digit;
     if (shift + digit > 32) shift = 32 - digit;
-    const bool iota = iota_vals && pass == 0;
-    if (digit == 7) sort_pass<7>(ka, va, kb, vb, n, shift, hist, sums, nb, iota, st);
-    else sort_pass<8>(ka, va, kb, vb, n, shift, hist, sums, nb, iota, st);
+    if (digit == 7) sort_pass<7>(ka, va, kb, vb, n, shift, hist, sums, nb, st);
+    else sort_pass<8>(ka, va, kb, vb, n, shift, hist, sums, nb, st);
     VP_CHECK_LAUNCH();
     uint32_t* t;
     t = ka; ka = kb; kb = t;
@@ -303,5 +291,5 @@ int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, 
 
 int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits, void* scratch,
                        cudaStream_t st) {
-  return vp_sort_pairs_range(ctx, keys, vals, n, 0, bits, false, scratch, st);
+  return vp_sort_pairs_range(ctx, keys, vals, n, 0, bits, scratch, st);
 }
