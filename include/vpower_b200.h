@@ -93,6 +93,13 @@ int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const 
 /* Number of lattice nodes the last vp_nn_grid on this ctx needed the wide (ring >= 2) search for,
  * and the number it could not prove at all (only possible with use_x_keep).  Syncs `stream`. */
 int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_t* n_kept, void* stream);
+/* The cell list vp_nn_grid would build for these arguments -- host arithmetic only, no device, no ctx (useful for sizing
+ * and for checking the key layout at sizes that do not fit a test machine).  info_out[10] = { cells_x, cells_y, cells_z,
+ * yb, lb, nyc, bins, row_bits, scratch_MiB, corner_aligned }: the sort key is (row << lb) | local with
+ * row = cx*nyc + (cy >> yb) < 2^row_bits and local = (cy mod 2^yb)*cells_z + cz < bins <= 2^lb, row_bits + lb <= 32;
+ * scratch_MiB = arena bytes vp_nn_grid_payload needs (MiB, rounded up). */
+int vp_nn_grid_plan(int64_t np, const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz,
+                    const vp_nn_opts* opts, int64_t* info_out);
 
 /* K1 with a payload (whole-path form).  Besides (optionally) nn_idx_d it returns
  *   spay_d   [np] float4 = (vx', vy', vz', m) in CELL-SORTED particle order, v' = (rho*v)/rho, m = rho*lcell3

@@ -1474,6 +1474,25 @@ extern "C" int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t
   return VP_ERR_ARG;
 }
 
+extern "C" int vp_nn_grid_plan(int64_t np, const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz,
+                               const vp_nn_opts* opts, int64_t* info_out) {
+  VP_REQUIRE(qx_h && qy_h && qz_h && info_out, "vp_nn_grid_plan: null argument");
+  VP_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vp_nn_grid_plan: bad sizes");
+  vp_nn_opts o;
+  memset(&o, 0, sizeof o);
+  if (opts) o = *opts;
+  const Grid g = plan_grid(np, qx_h, nx, qy_h, ny, qz_h, nz, o);
+  const uint64_t ncells = uint64_t(g.gx) * g.gy * g.gz, nrows = uint64_t(g.gx) * g.nyc;
+  info_out[0] = g.gx; info_out[1] = g.gy; info_out[2] = g.gz;
+  info_out[3] = g.yb; info_out[4] = g.lb; info_out[5] = g.nyc; info_out[6] = g.bins;
+  info_out[7] = vp_ceil_log2(nrows);
+  info_out[8] = int64_t((nn_scratch(np, true, ncells, nrows, int64_t(nx) * ny * nz).total + (size_t(1) << 20) - 1) >> 20);
+  // corner aligned: cells of the node spacing with every node on a cell corner (the 2x2x2 block then proves radius h)
+  const double sp = nx > 1 ? (qx_h[nx - 1] - qx_h[0]) / (nx - 1) : 0.0;
+  info_out[9] = (g.gx == nx + 1 && nx > 1 && fabs(g.hx - sp) <= 1e-9 * fabs(sp)) ? 1 : 0;
+  return VP_OK;
+}
+
 extern "C" int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_t* n_kept, void* stream) {
   VP_REQUIRE(ctx, "vp_nn_grid_stats: null ctx");
   vp_nn_stats_dev h;

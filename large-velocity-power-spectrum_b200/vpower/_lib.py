@@ -44,6 +44,7 @@ SIGNATURES = {
     "vp_launch_count": (C.c_ulonglong, [_P]),
     "vp_nn_grid": (_I, [_P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _P, C.POINTER(NNOpts), _P]),
     "vp_nn_grid_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _P]),
+    "vp_nn_grid_plan": (_I, [_L, _dp, _I, _dp, _I, _dp, _I, C.POINTER(NNOpts), C.POINTER(_L)]),
     "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
     "vp_fields_sorted": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_slab_bucket": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, _P, _L, C.POINTER(_L), _P]),
@@ -309,6 +310,18 @@ def fields_sorted(nn_pos_t, spay_t, want_v=True, want_p=(False, False, False), w
     _check(load_library().vp_fields_sorted(ctx(), _P(nn_pos_t.data_ptr()), nn_pos_t.numel(), _P(spay_t.data_ptr()), v, p,
                                            _P(e) if e else None, _P(m) if m else None, stream_ptr()))
     return out
+
+
+def nn_grid_plan(np_particles, qx, qy, qz, opts: NNOpts | None = None):
+    """Host-only: the cell list vp_nn_grid would build (no device needed).  -> dict, see include/vpower_b200.h."""
+    qx_a, qx_p = _as_dp(qx)
+    qy_a, qy_p = _as_dp(qy)
+    qz_a, qz_p = _as_dp(qz)
+    out = (_L * 10)()
+    _check(load_library().vp_nn_grid_plan(int(np_particles), qx_p, len(qx_a), qy_p, len(qy_a), qz_p, len(qz_a),
+                                          C.byref(opts) if opts is not None else None, out))
+    names = ("cells_x", "cells_y", "cells_z", "yb", "lb", "nyc", "bins", "row_bits", "scratch_MiB", "corner_aligned")
+    return dict(zip(names, (int(v) for v in out)))
 
 
 def nn_grid_stats():

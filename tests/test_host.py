@@ -220,3 +220,50 @@ def test_boxfield_host_helpers_match_reference_expressions():
     vv, mm = vi._vec_to_vm_grid(vec, 0.5)
     assert np.allclose(vv, v) and np.allclose(mm, rho * 0.125)
 
+
+def test_cell_list_plan_invariants_without_a_device():
+    """vp_nn_grid_plan is host arithmetic: the key layout (row << lb | local) must fit 32 bits, a row of cells must fit the
+    shared-memory counters of the per-row counting sort, and the 1-particle-per-node lattices must come out corner aligned --
+    for every BASELINE configuration (cfg5 cannot be run on one device) and for awkward shapes."""
+    from vpower import _lib
+    kMaxBins = 33 * 1024
+
+    def check(np_particles, qx, qy, qz, opts=None):
+        p = _lib.nn_grid_plan(np_particles, qx, qy, qz, opts)
+        gx, gy, gz = p["cells_x"], p["cells_y"], p["cells_z"]
+        assert gx >= 1 and gy >= 1 and gz >= 1
+        assert p["bins"] == gz << p["yb"] and p["bins"] <= kMaxBins and p["bins"] <= 1 << p["lb"]
+        assert p["lb"] == 0 or p["bins"] > 1 << (p["lb"] - 1)                  # lb is the tight bit width
+        assert p["nyc"] == -(-gy // (1 << p["yb"]))
+        nrows = gx * p["nyc"]
+        assert nrows <= 1 << p["row_bits"] and (p["row_bits"] == 0 or nrows > 1 << (p["row_bits"] - 1))
+        assert p["row_bits"] + p["lb"] <= 32 and nrows << p["lb"] <= 1 << 32   # every key fits u32
+        assert gx * gy * gz < 2 ** 32 - 1
+        return p
+
+    for N, Np in ((64, 1 << 18), (256, 1 << 24), (512, 1 << 27), (1024, 1 << 30)):
+        ax = np.linspace(0.5 / N, 1.0 + 0.5 / N, N)                            # library lattice
+        p = check(Np, ax, ax, ax)
+        assert (p["cells_x"], p["cells_y"], p["cells_z"]) == (N + 1,) * 3 and p["corner_aligned"] == 1
+        assert p["row_bits"] <= 16                                             # two 8-bit radix passes at most
+    p = check(1 << 30, *(np.linspace(0.5 / 1024, 1.0 + 0.5 / 1024, 1024),) * 3)
+    assert p["yb"] == 5 and p["lb"] == 16 and p["nyc"] == 33 and p["row_bits"] == 16 and p["scratch_MiB"] < 150 * 1024
+    # cfg5 (2048^3): one device cannot hold it; a slab of it (8 ranks) must plan fine, the whole lattice gets coarser cells
+    ax5 = np.linspace(0.5 / 2048, 1.0 + 0.5 / 2048, 2048)
+    o = _lib.NNOpts()
+    o.use_x_keep, o.x_keep_lo, o.x_keep_hi = 1, ax5[256] - 4 / 2048, ax5[511] + 4 / 2048
+    o.x_lo_is_domain_edge = o.x_hi_is_domain_edge = 0
+    p = check((1 << 30) + (1 << 26), ax5[256:512], ax5, ax5, o)
+    assert p["cells_y"] == 2049 and p["cells_z"] == 2049 and 256 <= p["cells_x"] <= 280
+    p = check((1 << 31) - 1, ax5, ax5, ax5)
+    assert p["cells_x"] * p["cells_y"] * p["cells_z"] < 2 ** 32 - 1
+    # awkward shapes: a single long line of nodes, a plane, very few / very many particles per node, explicit cell counts
+    line = np.linspace(0.0, 1.0, 100000)
+    check(1000, np.array([0.5]), np.array([0.5]), line)
+    check(1 << 26, np.array([0.5]), np.array([0.5]), line)                      # many cells along z: coarsened to fit
+    check(5, line[:300], line[:200], np.array([0.1, 0.2]))
+    check(1 << 31 - 1, np.linspace(0, 1, 16), np.linspace(0, 1, 16), np.linspace(0, 1, 16))
+    o2 = _lib.NNOpts()
+    o2.cells_x, o2.cells_y, o2.cells_z = 7, 100000, 3
+    check(12345, line[:50], line[:60], line[:70], o2)
+
