@@ -249,7 +249,10 @@ int vp_sort_pairs(vp_ctx* ctx, uint32_t* keys_d, uint32_t* vals_d, int64_t n, in
  *   nsample_h [nbins] u64
  *   rho_h may be NULL (rho = 1: the script path, plain velocity); lcell3 = Lcell^3 (interp.py:273)
  *   momentum_strict: 1 = reference behaviour (vx*m used for all three components, interp.py:523-525)
- * Syncs.
+ * The host arrays (pinned for full PCIe speed, pageable works) are uploaded in 2^24-particle chunks on an internal
+ * copy stream: positions first -- the cell list and the search run while velocity and density follow -- then velocity
+ * and density, packed chunk by chunk into (v', m) records on a high-priority side stream; only the plane gather and
+ * the transforms remain after the last byte.  Syncs.
  */
 int vp_host_particles_to_pk(vp_ctx* ctx, const void* pos_h, const void* vel_h, const void* rho_h, int dtype,
                             int64_t np, const double* qx_h, const double* qy_h, const double* qz_h, int N,
