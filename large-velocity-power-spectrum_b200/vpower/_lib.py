@@ -135,6 +135,16 @@ def launch_count():
     return int(load_library().vp_launch_count(ctx()))
 
 
+def arena_bytes():
+    """Bytes of device scratch the context holds (grow-only high-water mark of the arena)."""
+    return int(load_library().vp_ctx_arena_bytes(ctx()))
+
+
+def trim():
+    """Give the context's scratch arena back to the driver (it is re-grown on demand).  Syncs the device."""
+    _check(load_library().vp_ctx_trim(ctx()))
+
+
 def stream_ptr():
     return _P(_torch().cuda.current_stream().cuda_stream)
 

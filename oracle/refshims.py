@@ -30,6 +30,10 @@ import scipy.fft
 
 REF_ROOT = os.environ.get("VPOWER_REFERENCE", "/root/reference")
 ANN_SAMPLE = os.path.join(REF_ROOT, "ann", "ann_sample")
+# The ELF is an unaudited binary from the public reference tree.  It is executed ONLY when the maintainer regenerates
+# the golden vectors (tests/golden/make_golden.py) and has opted in with VPOWER_ALLOW_REFERENCE_ELF=1, and only if its
+# sha256 is the one that was inspected when the vectors were made.  Nothing on the GPU box, in build() or in pytest runs it.
+ANN_SAMPLE_SHA256 = "5128f74259b161021e7e7766b0a911c1cd5ec6b08fef44361cae30847bff009a"
 
 _snapshots = {}
 _state = {"engine": "oracle", "last_nn": None}
@@ -49,6 +53,14 @@ def run_ann_sample(data, query):
     """Run the reference ELF exactly as vpower/interp.py:1052-1134 would drive it:
     text files written with '%.16f' tab separated; returns (idx0, data_parsed, query_parsed)
     where *_parsed are the doubles the binary actually saw (text round trip)."""
+    import hashlib
+    if os.environ.get("VPOWER_ALLOW_REFERENCE_ELF") != "1":
+        raise RuntimeError("refusing to execute the reference's prebuilt ann/ann_sample: set VPOWER_ALLOW_REFERENCE_ELF=1 "
+                           "(only needed to regenerate tests/golden/reference_golden.npz)")
+    with open(ANN_SAMPLE, "rb") as fh:
+        digest = hashlib.sha256(fh.read()).hexdigest()
+    if digest != ANN_SAMPLE_SHA256:
+        raise RuntimeError(f"{ANN_SAMPLE}: sha256 {digest} is not the pinned {ANN_SAMPLE_SHA256}")
     with tempfile.TemporaryDirectory() as td:
         dp, qp = os.path.join(td, "data.pts"), os.path.join(td, "query.pts")
         np.savetxt(dp, data, delimiter="\t", fmt="%.16f")

@@ -564,6 +564,151 @@ def test_fft_binning_parseval_and_linearity_full_size(lib, orc):
     assert abs((p1.sum() + lo.fields([f.clone()])[0][0] + hi.fields([f.clone()])[0][0]) - want) / want < 1e-5
 
 
+def _spot_check_nn(torch, pos, ax, nn, rs, n_random, n_far, n_sample=1 << 22):
+    """Re-decide lattice nodes independently of the library: particles are binned into 64^3 coarse cells with torch.sort;
+    for every picked node the particles of all coarse cells touching the cube of half-width R = 1.0001 |node - claimed NN|
+    are fetched and the exact f64 argmin (ties -> lowest index) is taken on the host.  Picks: `n_random` uniformly random
+    nodes + the `n_far` nodes with the LARGEST claimed distance out of `n_sample` random ones (the nodes the wide search
+    stages had to settle) + the eight lattice corners.  -> (number of nodes checked, number of wrong answers, max R / h)."""
+    N = len(ax)
+    G = 64
+    lo, hi = float(pos.min().item()), float(pos.max().item())
+    w = (hi - lo) / G * (1 + 1e-6) + 1e-30
+    cid = torch.zeros(pos.shape[0], dtype=torch.int32, device=pos.device)
+    for c in range(3):
+        cid = cid * G + ((pos[:, c] - lo) / w).to(torch.int32).clamp_(0, G - 1)
+    sid, order = torch.sort(cid)
+    del cid
+    starts = torch.searchsorted(sid, torch.arange(G ** 3 + 1, dtype=torch.int32, device=pos.device)).cpu().numpy()
+    del sid
+    axt = torch.from_numpy(ax).to(pos.device)
+    samp = torch.from_numpy(rs.integers(0, N, size=(n_sample, 3))).to(pos.device)
+    got = nn[samp[:, 0], samp[:, 1], samp[:, 2]].long()
+    d = ((axt[samp[:, 0]] - pos[got, 0].double()) ** 2 + (axt[samp[:, 1]] - pos[got, 1].double()) ** 2
+         + (axt[samp[:, 2]] - pos[got, 2].double()) ** 2)
+    far = samp[torch.topk(d, n_far).indices].cpu().numpy()
+    corners = np.array([[a, b, c] for a in (0, N - 1) for b in (0, N - 1) for c in (0, N - 1)])
+    pick = np.concatenate([samp[:n_random].cpu().numpy(), far, corners])
+    h = ax[1] - ax[0]
+    bad, rmax = 0, 0.0
+    for i, j, k in pick:
+        node = np.array([ax[i], ax[j], ax[k]])
+        g = int(nn[i, j, k])
+        pg = pos[g].cpu().numpy().astype(np.float64)
+        dg = ((node[0] - pg[0]) ** 2 + (node[1] - pg[1]) ** 2) + (node[2] - pg[2]) ** 2
+        R = np.sqrt(dg) * 1.0001 + 1e-7
+        rmax = max(rmax, R / h)
+        rng_c = [range(max(0, int((node[c] - R - lo) / w)), min(G - 1, int((node[c] + R - lo) / w)) + 1) for c in range(3)]
+        idx = []
+        for a in rng_c[0]:
+            for b in rng_c[1]:
+                c0, c1 = (a * G + b) * G + rng_c[2][0], (a * G + b) * G + rng_c[2][-1]
+                idx.append(order[starts[c0]:starts[c1 + 1]])          # coarse cells along z are contiguous
+        idx = torch.cat(idx)
+        c = pos[idx].cpu().numpy().astype(np.float64)
+        idx = idx.cpu().numpy()
+        d2 = ((node[0] - c[:, 0]) ** 2 + (node[1] - c[:, 1]) ** 2) + (node[2] - c[:, 2]) ** 2
+        best = idx[np.lexsort((idx, d2))[0]]
+        bad += int(best != g)
+    return len(pick), bad, rmax
+
+
+def test_nn_cfg3_clustered_spot_check(lib, orc):
+    """cfg3 (512^3 lattice, 2^27 particles, half of them in eight Gaussian blobs -- bench.py's generator): cells holding
+    thousands of particles next to half-empty voids, so the long-row path of the cell-list build and the wide stages of the
+    search all carry real load.  No CPU oracle builds a kd-tree of 1.3e8 points in test time: 2600 nodes are re-decided."""
+    import torch
+    import bench
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~40 GB of device memory")
+    wl = bench.WORKLOADS["cfg3"]
+    N = wl["N"]
+    pos, _, _ = bench.synth_range(torch, wl, 0, wl["Np"])
+    ax = orc.lattice_axis_lib(1.0, N)
+    nn = lib.nn_grid(pos, ax, ax, ax)
+    st = lib.nn_grid_stats()
+    assert st["n_unresolved"] == 0 and st["n_kept"] == wl["Np"]
+    assert st["n_wide"] > 100000                       # the exact stage is genuinely exercised
+    lib.trim()
+    n, bad, rmax = _spot_check_nn(torch, pos, ax, nn, np.random.default_rng(3), 1500, 1100)
+    assert n >= 2600 and bad == 0
+    assert rmax > 1.5                                   # nodes in voids were among the picks
+
+
+def test_nn_cfg4_full_size_spot_check(lib, orc):
+    """cfg4 at its own size: 1024^3 lattice, 2^30 uniform-random particles (bench.py's generator).  Exercises the two-pass
+    row sort, the 32-bit slot arithmetic and every search stage at 2^30; 2100 nodes re-decided independently, 1000 of them
+    the farthest-from-their-particle nodes of a 4M sample (what stages B and C settled)."""
+    import torch
+    import bench
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs a whole B200 (~120 GB of device memory)")
+    wl = bench.WORKLOADS["cfg4"]
+    N = wl["N"]
+    pos = torch.empty((wl["Np"], 3), dtype=torch.float32, device="cuda")
+    step = 1 << 27
+    for s in range(0, wl["Np"], step):                 # positions only: the same particle set bench.py times
+        x = torch.stack([bench.hash_uniform_t(torch, wl["seed"], s, s + step, c, "cuda") for c in range(3)], dim=1)
+        pos[s:s + step] = x
+        del x
+    ax = orc.lattice_axis_lib(1.0, N)
+    nn = lib.nn_grid(pos, ax, ax, ax)
+    st = lib.nn_grid_stats()
+    assert st["n_unresolved"] == 0 and st["n_kept"] == wl["Np"]
+    lib.trim()
+    torch.cuda.empty_cache()
+    assert int(nn.min()) >= 0 and int(nn.max()) < wl["Np"]
+    n, bad, rmax = _spot_check_nn(torch, pos, ax, nn, np.random.default_rng(4), 1100, 1000)
+    assert n >= 2100 and bad == 0
+    assert rmax > 1.0                                   # nodes beyond the 2x2x2 proof radius were among the picks
+
+
+def test_cfg2_full_vs_oracle(vp, lib, orc):
+    """BASELINE cfg2 in full against the CPU oracle: 256^3 lattice, 2^24 particles, velocity + momentum spectra through the
+    whole-path C-ABI call (device-resident and host-buffer forms).  Nearest-particle indices and mode counts bit-exact,
+    binned P(k) within 1e-5 of the f64 oracle."""
+    import torch
+    import bench
+    wl = bench.WORKLOADS["cfg2"]
+    N, Np, L = wl["N"], wl["Np"], 1.0
+    pos, vel, rho = bench.synth_range(torch, wl, 0, Np)
+    p64, v64, d64 = (t.cpu().numpy().astype(np.float64) for t in (pos, vel, rho))
+    ax, k, edges, lc3, norm = bench.geometry(N, L)
+    ref_idx = orc.nn_exact_lattice(p64, ax, ax, ax)
+    nn = lib.nn_grid(pos, ax, ax, ax).cpu().numpy()
+    assert np.array_equal(nn, ref_idx)
+    assert lib.nn_grid_stats()["n_unresolved"] == 0
+    v_ref, m_ref, Lcell = orc.ann_interp_to_field(p64, d64, v64, L, N)
+    out, ns = lib.particles_to_pk(pos, vel, rho, ax, ax, ax, N, lc3, norm, k, edges, quantities=wl["quantities"])
+    out_h, ns_h = lib.particles_to_pk(p64.astype(np.float32), v64.astype(np.float32), d64.astype(np.float32), ax, ax, ax, N, lc3,
+                                      norm, k, edges, quantities=wl["quantities"])
+    assert np.array_equal(ns, bench.integer_shell_counts(N))
+    for q in wl["quantities"]:
+        ref = orc.spctrm(v_ref, m_ref, Lcell, q)
+        assert np.array_equal(ns, ref[:, 3].astype(np.int64)) and np.array_equal(ns_h, ns)
+        assert np.max(np.abs(out[q] / ref[:, 2] - 1)) < 1e-5
+        assert np.max(np.abs(out_h[q] / ref[:, 2] - 1)) < 1e-5
+
+
+def test_two_rank_dist_check_under_torchrun():
+    """N>1 on real GPUs: tests/dist_gpu_check.py under torchrun with 2 ranks (NCCL + peer-store exchanges == replicated ==
+    single GPU == CPU oracle).  Needs two visible B200s; the single-GPU test box skips it (the gloo tests in
+    tests/test_dist_cpu.py cover the wiring there)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_gpu_check.py")],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "DIST CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_nn_full_size_spot_check(lib, orc):
     """cfg3 scale (512^3 lattice, 2^27 particles, clustered: voids and sheets).  The CPU oracle cannot build a kd-tree of
     1.3e8 points in test time, so 600 random lattice nodes are re-decided independently: all particles inside a generous

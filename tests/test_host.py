@@ -267,3 +267,36 @@ def test_cell_list_plan_invariants_without_a_device():
     o2.cells_x, o2.cells_y, o2.cells_z = 7, 100000, 3
     check(12345, line[:50], line[:60], line[:70], o2)
 
+
+
+def test_bench_generator_matches_oracle_hash_and_is_rank_count_independent():
+    """bench.py's counter-based particle generator: same integer hash as the oracle's hash_uniform (positions bit-equal to
+    orc.synth_particles), and a rank's index range is a pure function of (seed, index) -- the union over ranks is the same
+    particle set at every GPU count."""
+    import torch
+    import bench
+    import vpower_oracle as orc
+    for seed, stream in ((0, 0), (3, 2), (4, 7)):
+        assert np.array_equal(orc.hash_uniform(seed, 50000, stream), bench.hash_uniform_t(torch, seed, 0, 50000, stream, "cpu").numpy())
+    wl = bench.WORKLOADS["cfg1"]
+    p, v, r = bench.synth_range(torch, wl, 0, 4000, device="cpu")
+    assert np.array_equal(p.numpy(), orc.synth_particles(wl["seed"], wl["Np"], 1.0)[0][:4000])
+    for lo, hi in ((0, 1000), (1000, 4000)):
+        p2, v2, r2 = bench.synth_range(torch, wl, lo, hi, device="cpu", chunk=700)
+        assert torch.equal(p[lo:hi], p2) and torch.equal(v[lo:hi], v2) and torch.equal(r[lo:hi], r2)
+    wl3 = dict(bench.WORKLOADS["cfg3"], Np=1 << 18)
+    pc, vc, rc = bench.synth_range(torch, wl3, 0, 1 << 18, device="cpu")
+    assert float(pc.min()) >= 0.0 and float(pc.max()) < 1.0 and bool(torch.isfinite(vc).all())
+    h = np.histogramdd(pc.numpy(), bins=16, range=[(0, 1)] * 3)[0]
+    assert h.max() > 20 * h.mean()                      # genuinely clustered
+
+
+def test_bench_integer_shell_closed_form():
+    import bench
+    for N in (16, 48, 64):
+        n1 = np.fft.fftfreq(N, 1.0 / N)
+        n2 = (n1[:, None, None] ** 2 + n1[None, :, None] ** 2 + n1[None, None, :] ** 2).ravel()
+        ref = np.bincount(np.floor(np.sqrt(n2) + 0.5).astype(np.int64), minlength=N)[1:N // 2 + 1]
+        assert np.array_equal(bench.integer_shell_counts(N), ref)
+    assert bench.integer_shell_counts(16).tolist()[:8] == [18, 62, 98, 210, 350, 450, 602, 687]      # SURVEY.md 8(c)
+    assert bench.integer_shell_counts(64).sum() == 143457 and bench.integer_shell_counts(256).sum() == 8886577
