@@ -15,8 +15,11 @@
  *     (thread local).  There is NO CPU fallback: without a CUDA device every
  *     compute call fails with VP_ERR_CUDA.
  *   - calls are asynchronous on `stream` unless the comment says "syncs".
- *   - one vp_ctx per device per thread of use; a ctx owns a grow-only device
- *     scratch arena (cudaMalloc) that the calls below carve their temporaries from.
+ *   - a vp_ctx owns a grow-only device scratch arena (cudaMalloc) and a few small tables
+ *     that the calls below carve their temporaries from.  Calls on one ctx are serialised
+ *     by an internal lock, and a call issued on a different stream than the previous call
+ *     of the ctx first waits (on the device) for that call's work -- the scratch is shared.
+ *     For concurrency between streams or threads use one ctx per stream.
  */
 #ifndef VPOWER_B200_H
 #define VPOWER_B200_H
@@ -191,6 +194,9 @@ int vp_pk_dist_p2p_alloc(vp_pk_plan* plan, int ncomp_max, unsigned char* handles
 int vp_pk_dist_p2p_open(vp_pk_plan* plan, const unsigned char* all_handles);
 int vp_pk_dist_local_p2p(vp_pk_plan* plan, float* const* field_d, int ncomp, void* stream);
 int vp_pk_dist_final_p2p(vp_pk_plan* plan, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream);
+/* Teardown: every rank vp_pk_dist_p2p_close (unmaps the peers' receive buffers; syncs), then a barrier across the ranks,
+ * then vp_pk_plan_destroy (frees this rank's exported buffers). */
+int vp_pk_dist_p2p_close(vp_pk_plan* plan);
 
 /* Sharded particle input for the slab decomposition: every particle of this rank's subset is copied into the block of
  * each destination rank d whose kept range lo_h[d] <= x <= hi_h[d] contains it (use -/+ infinity for open ends).
@@ -206,6 +212,10 @@ int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void
  * first row it may write in each destination's buffer, and vp_slab_scatter_p2p stores the rows there directly (own HBM
  * or NVLink peer stores).  The caller separates "all ranks have stored" from "this rank reads" with a stream-ordered
  * barrier across ranks.  Rows of one destination arrive grouped by source rank, in rank order. */
+/* Lifetime of the shared buffers (CUDA leaves freeing an exported allocation that a peer still maps undefined): to grow or
+ * drop them, EVERY rank calls vp_slab_p2p_close (unmaps the peers; syncs the device), the caller runs a barrier across the
+ * ranks, and only then vp_slab_p2p_alloc frees and re-allocates (it refuses while peers are mapped). */
+int vp_slab_p2p_close(vp_ctx* ctx);
 int vp_slab_p2p_alloc(vp_ctx* ctx, size_t bytes, unsigned char* handle_out /* 64 bytes */);
 int vp_slab_p2p_open(vp_ctx* ctx, int nranks, int rank, const unsigned char* all_handles /* [nranks][64] */);
 int vp_slab_p2p_buffer(vp_ctx* ctx, void** ptr_out, size_t* bytes_out);

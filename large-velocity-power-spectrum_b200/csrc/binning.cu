@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_hist(const double* __restrict__ k, cons
 extern "C" int vp_k_magnitude(vp_ctx* ctx, const double* kx_h, const double* ky_h, const double* kz_h, int n, double* out_d,
                               void* stream) {
   VP_REQUIRE(ctx && kx_h && ky_h && kz_h && out_d && n > 0, "vp_k_magnitude: bad argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vp_arena_scope scope(ctx);
@@ -62,6 +63,7 @@ extern "C" int vp_k_magnitude(vp_ctx* ctx, const double* kx_h, const double* ky_
 extern "C" int vp_hist_weighted(vp_ctx* ctx, const double* k_d, const double* w_d, int64_t n, const double* edges_h, int nbins,
                                 double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(ctx && k_d && w_d && edges_h && psum_d && nsample_d && nbins >= 1 && n >= 0, "vp_hist_weighted: bad argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vp_arena_scope scope(ctx);

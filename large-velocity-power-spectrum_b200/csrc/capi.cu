@@ -62,6 +62,8 @@ extern "C" int vp_ctx_destroy(vp_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->pack_stream) cudaStreamDestroy(ctx->pack_stream);
   if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
+  if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
+  if (ctx->ev_tables) cudaEventDestroy(ctx->ev_tables);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
     if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
@@ -114,6 +116,7 @@ void* vp_arena_alloc(vp_ctx* ctx, size_t bytes) {
 
 extern "C" int vp_sort_pairs(vp_ctx* ctx, uint32_t* keys_d, uint32_t* vals_d, int64_t n, int bits, void* stream) {
   VP_REQUIRE(ctx && keys_d && vals_d && n >= 0 && bits >= 0 && bits <= 32, "vp_sort_pairs: bad argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_CUDA(cudaSetDevice(ctx->device));
   size_t sb = vp_sort_scratch_bytes(n);
   vp_arena_scope scope(ctx);

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -47,11 +48,11 @@ struct vp_arena {
 };
 
 struct vp_nn_stats_dev {
-  unsigned long long n_wide;        // nodes sent to the ring>=2 search
+  unsigned long long n_wide;        // nodes sent to the exact stage
   unsigned long long n_unresolved;  // nodes still unproven afterwards
   unsigned long long n_kept;        // particles that survived the x filter
-  unsigned long long pad;
-  unsigned long long row_cursor;    // dynamic row assignment of k_group_permute
+  unsigned long long n_b;           // nodes sent to the wider prefilter stage
+  unsigned long long n_far;         // particles outside the cell grid (clamped into end cells)
 };
 
 // optional per-stage timing with CUDA events on the launching stream (vp_profile_enable / vp_profile_report)
@@ -64,6 +65,14 @@ struct vp_prof_rec {
 
 struct vp_pk_plan;
 struct vp_ctx {
+  // calls on one ctx are serialised by `mu` (threads), and a call on a different stream than the previous one first
+  // waits on the device for `ev_last`, the end of the previous call's work: the arena, the small tables and the stats
+  // block are shared by all calls of the ctx
+  std::recursive_mutex mu;
+  int call_depth = 0;
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false;
   bool prof_on = false;
   std::vector<vp_prof_rec> prof;
   unsigned long long n_launch = 0;        // kernels launched by this ctx since creation
@@ -78,6 +87,7 @@ struct vp_ctx {
   size_t small_cap = 0;
   void* pinned_h = nullptr;               // pinned staging for small host->device tables
   size_t pinned_cap = 0;
+  cudaEvent_t ev_tables = nullptr;        // upload of the pinned tables (the next call waits for it before rewriting them)
   // sharded particle exchange over peer memory (vp_slab_p2p_*): this rank's receive buffer and every peer's, mapped
   void* slab_recv = nullptr;
   size_t slab_recv_bytes = 0;
@@ -88,6 +98,25 @@ struct vp_ctx {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
   cudaStream_t pack_stream = nullptr;     // payload chunks are packed here while the gridding runs on the caller's stream
   cudaEvent_t ev_pack = nullptr;
+};
+
+// Every compute entry point opens one of these first (see vp_ctx::mu).
+struct vp_call_guard {
+  vp_ctx* c;
+  cudaStream_t st;
+  vp_call_guard(vp_ctx* ctx, cudaStream_t s) : c(ctx), st(s) {
+    c->mu.lock();
+    if (c->call_depth++ == 0 && c->last_valid && c->last_stream != st) cudaStreamWaitEvent(st, c->ev_last, 0);
+  }
+  ~vp_call_guard() {
+    if (--c->call_depth == 0) {
+      if (!c->ev_last) cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming);
+      if (c->ev_last && cudaEventRecord(c->ev_last, st) == cudaSuccess) { c->last_stream = st; c->last_valid = true; }
+    }
+    c->mu.unlock();
+  }
+  vp_call_guard(const vp_call_guard&) = delete;
+  vp_call_guard& operator=(const vp_call_guard&) = delete;
 };
 
 // Stack discipline: every entry point opens a vp_arena_scope (restores the offset on exit), calls
@@ -112,6 +141,12 @@ int vp_sort_pairs_impl(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, i
 // stable sort on key bits [lo, lo + nbits) only
 int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int lo, int nbits, void* scratch,
                         cudaStream_t st);
+
+// exclusive prefix sum of m u32 values in place (three kernels); `sums` holds ceil(m/4096)+1 words of scratch
+int vp_scan_exclusive_u32(vp_ctx* ctx, uint32_t* a, int64_t m, uint32_t* sums, cudaStream_t st);
+// planes from (v', m) records addressed through nn_pos: record i at srec + (stride*i + offset) float4
+int vp_fields_from_records(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* srec_d, int stride, int offset,
+                           float* const v_d[3], float* const p_d[3], float* e_d, float* m_d, cudaStream_t st);
 
 // Host-resident particle arrays streamed to the device in chunks (vp_host_particles_to_pk): positions land in a
 // resident device array (the exact search needs them), velocity/density chunks only pass through two staging buffers.

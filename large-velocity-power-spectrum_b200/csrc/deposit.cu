@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) k_deposit(const T* __restrict__ pos, int6
 extern "C" int vp_deposit_ngp(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const double* w_d, int ncomp, int N,
                               double Lbox, double* grid_d, void* stream) {
   VP_REQUIRE(ctx && pos_d && w_d && grid_d, "vp_deposit_ngp: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(np >= 0 && ncomp >= 1 && N >= 1, "vp_deposit_ngp: bad sizes");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VP_CUDA(cudaMemsetAsync(grid_d, 0, sizeof(double) * size_t(N) * N * N * ncomp, st));

@@ -661,6 +661,7 @@ static int pk_fields_generic(vp_pk_plan* pl, float* const* field_d, int ncomp, d
 
 extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && field_d && psum_d && nsample_d, "vp_pk_fields: null argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(ncomp >= 1 && ncomp <= 3, "vp_pk_fields: ncomp must be 1..3");
   VP_REQUIRE(pl->nranks == 1, "vp_pk_fields: plan is distributed over %d ranks; use vp_pk_dist_local/final", pl->nranks);
   VP_CUDA(cudaSetDevice(pl->ctx->device));
@@ -708,6 +709,7 @@ extern "C" int vp_pk_plan_create_dist(vp_ctx* ctx, int N, int nranks, int rank, 
 
 extern "C" int vp_pk_dist_local(vp_pk_plan* pl, float* const* field_d, int ncomp, float* const* send_d, void* stream) {
   VP_REQUIRE(pl && field_d && send_d && ncomp >= 1 && ncomp <= 3, "vp_pk_dist_local: bad argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(pl->pow2, "vp_pk_dist_local: N=%d has no slab path", pl->N);
   VP_CUDA(cudaSetDevice(pl->ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -723,6 +725,7 @@ extern "C" int vp_pk_dist_local(vp_pk_plan* pl, float* const* field_d, int ncomp
 
 extern "C" int vp_pk_dist_final(vp_pk_plan* pl, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && recv_d && psum_d && nsample_d && ncomp >= 1 && ncomp <= 3, "vp_pk_dist_final: bad argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(pl->pow2, "vp_pk_dist_final: N=%d has no slab path", pl->N);
   VP_CUDA(cudaSetDevice(pl->ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -762,6 +765,21 @@ extern "C" int vp_pk_dist_p2p_alloc(vp_pk_plan* pl, int ncomp_max, unsigned char
   return VP_OK;
 }
 
+// Unmap the other ranks' receive buffers.  Teardown order: every rank calls this, the caller runs a barrier across the ranks,
+// and only then vp_pk_plan_destroy() frees this rank's exported buffers.
+extern "C" int vp_pk_dist_p2p_close(vp_pk_plan* pl) {
+  VP_REQUIRE(pl, "vp_pk_dist_p2p_close: null plan");
+  VP_CUDA(cudaSetDevice(pl->ctx->device));
+  VP_CUDA(cudaDeviceSynchronize());
+  if (pl->peer_open) {
+    for (int c = 0; c < 3; ++c)
+      for (int d = 0; d < pl->nranks; ++d)
+        if (d != pl->rank && pl->peer[c][d]) { cudaIpcCloseMemHandle(pl->peer[c][d]); pl->peer[c][d] = nullptr; }
+    pl->peer_open = false;
+  }
+  return VP_OK;
+}
+
 extern "C" int vp_pk_dist_p2p_open(vp_pk_plan* pl, const unsigned char* all_handles) {
   VP_REQUIRE(pl && all_handles && pl->p2p_ncomp > 0, "vp_pk_dist_p2p_open: call vp_pk_dist_p2p_alloc first");
   VP_CUDA(cudaSetDevice(pl->ctx->device));
@@ -781,6 +799,7 @@ extern "C" int vp_pk_dist_p2p_open(vp_pk_plan* pl, const unsigned char* all_hand
 
 extern "C" int vp_pk_dist_local_p2p(vp_pk_plan* pl, float* const* field_d, int ncomp, void* stream) {
   VP_REQUIRE(pl && field_d && ncomp >= 1 && ncomp <= pl->p2p_ncomp, "vp_pk_dist_local_p2p: bad argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(pl->nranks == 1 || pl->peer_open, "vp_pk_dist_local_p2p: peer buffers not opened");
   VP_CUDA(cudaSetDevice(pl->ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -804,6 +823,7 @@ extern "C" int vp_pk_dist_final_p2p(vp_pk_plan* pl, int ncomp, double* psum_d, u
 
 extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) {
   VP_REQUIRE(pl && field_d, "vp_fft_r2c_inplace: null argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   if (!pl->pow2) { vp_set_error("vp_fft_r2c_inplace: N=%d has no packed fast path", pl->N); return VP_ERR_UNSUPPORTED; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VP_TRY(run_z(field_d, pl->N, pl->N, pl, st));
@@ -814,6 +834,7 @@ extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) 
 
 extern "C" int vp_power_cube(vp_pk_plan* pl, float* const* field_d, int ncomp, double* P_d, void* stream) {
   VP_REQUIRE(pl && field_d && P_d && ncomp >= 1 && ncomp <= 3, "vp_power_cube: bad argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_CUDA(cudaSetDevice(pl->ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!pl->pow2) return power_cube_generic(pl, field_d, ncomp, P_d, st);
@@ -830,6 +851,7 @@ extern "C" int vp_power_cube(vp_pk_plan* pl, float* const* field_d, int ncomp, d
 
 extern "C" int vp_fft_unpack_half(vp_pk_plan* pl, const float* packed_d, float* half_d, void* stream) {
   VP_REQUIRE(pl && packed_d && half_d, "vp_fft_unpack_half: null argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   const int N = pl->N;
   size_t n = size_t(N) * N * (N / 2 + 1);
   vp_stage stage(pl->ctx, "unpack_half", static_cast<cudaStream_t>(stream), 1);
@@ -841,6 +863,7 @@ extern "C" int vp_fft_unpack_half(vp_pk_plan* pl, const float* packed_d, float* 
 
 extern "C" int vp_power_bin_full(vp_pk_plan* pl, const double* P_d, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && P_d && psum_d && nsample_d, "vp_power_bin_full: null argument");
+  vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = pl->N;
   VP_CUDA(cudaMemsetAsync(psum_d, 0, sizeof(double) * pl->nbins, st));

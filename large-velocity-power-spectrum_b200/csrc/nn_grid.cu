@@ -1,17 +1,24 @@
-// K1: exact nearest-particle gridding on a sorted cell list.  See include/vpower_b200.h (vp_nn_grid).
+// K1: exact nearest-particle gridding on a cell list.  See include/vpower_b200.h (vp_nn_grid).
 //
-// Pipeline:  keygen + pack (cell key per particle, optional x filter, one packed record per particle)
-//            ->  radix sort of (key, slot) on the ROW bits of the key only (a row = one x plane, a chunk of y, all z)
-//            ->  row starts  ->  one CTA per row: counting sort of the row by cell in shared memory, fused with the
-//                permutation of the packed records into cell order and with the cell-start table
-//            ->  ring-1 search per lattice node (f32 prefilter)  ->  exact f64 search (warp per node, growing ring)
-//                for every node the prefilter could not settle.
+// Cell-list build (no sort; every record moves twice, both times through L2-resident windows -- the measurements behind
+// this are in profiles/r2_ubench_scatter_gather.jsonl: a random scatter of whole 32-byte sectors inside a <= 32 MB
+// window runs at the copy rate, a random gather over the whole array at a quarter of it):
+//   1. k_bin_hist     particles per BUCKET (a bucket = 2^bshift consecutive cells of the linear cell order)
+//   2. k_bin_scatter  every particle's packed 32-byte record is appended to its bucket (one cursor atomic per particle;
+//                        the append frontiers of all buckets together are a few hundred KB, so L2 merges the sectors)
+//   3. k_cell_count      records are now grouped by bucket: per-cell counts with L2-resident atomics
+//   4. exclusive scan    -> the cell-start table
+//   5. k_cell_place      counting-sort placement inside the bucket's window; the record is rewritten in search format
+// Search: a shared-memory staged brick kernel (one CTA = 8 x 8 x 32 lattice nodes, the particles of the covering
+// 9 x 9 x 33 cells staged once, coordinates re-based to the brick so that f32 carries ~2^-16 of a cell), a plus-shaped
+// wider stage for the nodes it cannot prove, and an exact f64 stage (warp per node, growing block) for near ties.
 //
 // Exactness: a candidate is accepted only if its distance is strictly below the distance from the
 // node to every face of the searched cell block behind which unexamined particles can exist.  All
-// distance arithmetic is f64 with the reference's association ((dx*dx+dy*dy)+dz*dz) and no FMA
+// deciding arithmetic is f64 with the reference's association ((dx*dx+dy*dy)+dz*dz) and no FMA
 // contraction (explicit __dmul_rn/__dadd_rn); ties go to the lowest particle index.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -26,26 +33,119 @@ struct Grid {
   double keep_lo, keep_hi;
   int closed_xlo, closed_xhi;  // 1: particles beyond that x face were dropped (face constrains the proof)
   int ps, vs, rs;              // element strides between consecutive particles in pos / vel / rho (3,3,1 when compact)
-  // sort key = (row << lb) | local,  row = cx * nyc + (cy >> yb),  local = (cy & (2^yb - 1)) * gz + cz  (< bins <= 2^lb)
-  int yb, lb, nyc, bins;
+  int bshift;                  // bucket of a cell = linear cell index >> bshift,  linear = (cx*gy + cy)*gz + cz
+  uint32_t nb;                 // number of buckets
 };
 
-// Sorted particle record: position relative to the grid origin rounded to f32 (used only by the f32
-// prefilter; every close call is re-decided in f64 from the caller's array) and the particle index.
+// ---- record formats
+// Bucketed record (between k_bin_scatter and k_cell_place): the position is kept as the cell index plus a 21-bit
+// fixed-point offset inside the cell per axis -- exact cell assignment (f64) travels with the record, and the offset
+// is good to 2^-22 of a cell, far better than an origin-relative f32.
+constexpr int kFixBits = 21;
+constexpr uint32_t kFixMax = (1u << kFixBits) - 1u;
+constexpr uint32_t kFarBit = 0x80000000u;   // idx bit 31: the particle lies outside the cell grid (clamped into an end cell)
+struct __align__(16) RecA { uint32_t u0, u1, cell, idx; };
+struct __align__(32) Rec32 { RecA a; float4 b; };
+// Sorted record (search format), one per particle in cell order: float4 a = (ux, uy, uz32, idx bits) [+ float4 b = (v'x, v'y,
+// v'z, m) with a payload]: ux, uy = offset from the low corner of the particle's cell; uz32 = offset from the low corner of
+// the aligned 32-cell z block the cell lies in (cz & ~31) -- a brick of the search kernel spans exactly one such block
+// plus one cell, so staging re-bases z with one add.  Every consumer knows the cell (it walks the cell table).
 typedef float4 rec_t;
 
-__device__ __forceinline__ int cell_of(double x, double o, double ih, int g) {
-  double f = (x - o) * ih;
-  if (!(f > 0.0)) return 0;
-  if (f >= double(g)) return g - 1;
-  return int(f);
+__device__ __forceinline__ int cell_fix(double x, double o, double ih, int g, uint32_t& fix, bool& far) {
+  const double f = (x - o) * ih;
+  int c;
+  if (!(f > 0.0)) c = 0;
+  else if (f >= double(g)) c = g - 1;
+  else c = int(f);
+  double u = f - double(c);                      // in [0,1) unless the particle was clamped into an end cell (or is NaN)
+  if (!(u >= 0.0)) { far = far || (u < 0.0) || (u != u); u = 0.0; }
+  if (u >= 1.0) { far = true; u = 1.0; }
+  uint32_t q = uint32_t(u * 2097152.0);
+  fix = q > kFixMax ? kFixMax : q;
+  return c;
 }
 
-// Packed particle record written once, in input order, so that the permutation after the sort is ONE random
-// 64-byte access per particle (separate pos/vel/rho arrays would cost three).
-//   a = (x-ox, y-oy, z-oz as f32, particle index)        b = (vx', vy', vz', m)  [only with a payload]
-// with v' = (rho*v)/rho and m = rho*Lcell^3 evaluated in the input dtype (interp.py:199-213,272-273).
-struct __align__(32) rec32_t { float4 a, b; };
+__device__ __forceinline__ void st256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                      uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+               "r"(a6), "r"(a7) : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&a)[8]) {
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "l"(p));
+}
+
+// true: the particle takes part (inside the kept x range of a slab, or no filter)
+template <typename T>
+__device__ __forceinline__ bool load_pos(const T* __restrict__ pos, const Grid& g, int64_t i, double& x, double& y, double& z) {
+  x = pos[size_t(g.ps) * i];
+  y = pos[size_t(g.ps) * i + 1];
+  z = pos[size_t(g.ps) * i + 2];
+  // slab filter: a particle beyond a CLOSED face is dropped; beyond an open (domain-edge) face it is kept and clamped
+  return !(g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi))));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ hist_g) {
+  extern __shared__ uint32_t sh_hist[];
+  for (uint32_t b = threadIdx.x; b < g.nb; b += 256) sh_hist[b] = 0u;
+  __syncthreads();
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < np; i += int64_t(gridDim.x) * 256) {
+    double x, y, z;
+    if (!load_pos(pos, g, i, x, y, z)) continue;
+    uint32_t fx, fy, fz;
+    bool far = false;
+    const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+              cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+    const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+    atomicAdd(&sh_hist[lin >> g.bshift], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < g.nb; b += 256) {
+    const uint32_t c = sh_hist[b];
+    if (c) atomicAdd(hist_g + b, c);
+  }
+}
+
+// exclusive prefix of the bucket histogram -> append cursors; the total is the number of kept particles.  One CTA.
+__global__ void __launch_bounds__(1024) k_bin_offsets(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t nb,
+                                                          vp_nn_stats_dev* __restrict__ stats) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0u;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t b = base + tid;
+    const uint32_t v = b < nb ? hist[b] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t s = wsum[lane];
+      uint32_t is = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) is += t;
+      }
+      wsum[lane] = is - s;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    if (b < nb) cursor[b] = carry + wsum[w] + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) stats->n_kept = carry_s;
+}
 
 template <typename T>
 struct PayloadIn {
@@ -54,314 +154,85 @@ struct PayloadIn {
   T lcell3;
 };
 
-// ITEMS particles per thread: 1 without the slab filter (pure streaming), 8 with it so that the compaction needs
-// only one global atomic per 2048-particle block
-template <typename T, bool PAY, int kKeygenItems>
-__global__ void __launch_bounds__(256) k_keygen_pack(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
-                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                      void* __restrict__ packed, unsigned long long* __restrict__ kept) {
-  // pos / pin.vel / pin.rho point at particle i0 (a chunk); indices and unfiltered slots are global (i0 + local)
-  __shared__ unsigned warp_cnt[8];
-  __shared__ unsigned long long block_base;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t base_i = int64_t(blockIdx.x) * (256 * kKeygenItems);
-  bool ok[kKeygenItems];
-  uint32_t key[kKeygenItems];
-  float4 a[kKeygenItems];
-  unsigned mine = 0;
-#pragma unroll
-  for (int r = 0; r < kKeygenItems; ++r) {
-    const int64_t i = base_i + r * 256 + threadIdx.x;
-    ok[r] = i < np;
-    double x = 0, y = 0, z = 0;
-    if (ok[r]) {
-      x = pos[size_t(g.ps) * i];
-      y = pos[size_t(g.ps) * i + 1];
-      z = pos[size_t(g.ps) * i + 2];
-      // slab filter: a particle beyond a CLOSED face is dropped; beyond an open (domain-edge) face it is kept and clamped
-      if (g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi)))) ok[r] = false;
-    }
-    key[r] = 0;
-    if (ok[r]) {
-      int cx = cell_of(x, g.ox, g.ihx, g.gx), cy = cell_of(y, g.oy, g.ihy, g.gy), cz = cell_of(z, g.oz, g.ihz, g.gz);
-      const uint32_t row = uint32_t(cx) * uint32_t(g.nyc) + (uint32_t(cy) >> g.yb);
-      const uint32_t loc = (uint32_t(cy) & ((1u << g.yb) - 1u)) * uint32_t(g.gz) + uint32_t(cz);
-      key[r] = (row << g.lb) | loc;
-      a[r] = make_float4(float(x - g.ox), float(y - g.oy), float(z - g.oz), __int_as_float(int(i0 + i)));
-      ++mine;
-    }
-  }
-  // output slot: identity without the filter; with it, a block-wide exclusive scan + one atomic per block
-  // (order is irrelevant: the sort follows and ties are decided by particle index)
-  unsigned long long slot0 = 0;
-  if (g.use_keep) {
-    unsigned incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_cnt[w] = incl;
-    __syncthreads();
-    unsigned woff = 0, tot = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q < w) woff += warp_cnt[q];
-      tot += warp_cnt[q];
-    }
-    if (threadIdx.x == 0) block_base = tot ? atomicAdd(kept, (unsigned long long)tot) : 0ull;
-    __syncthreads();
-    slot0 = block_base + woff + incl - mine;
-  }
-  unsigned nth = 0;
-#pragma unroll
-  for (int r = 0; r < kKeygenItems; ++r) {
-    if (!ok[r]) continue;
-    const int64_t i = base_i + r * 256 + threadIdx.x;
-    const int64_t o = g.use_keep ? int64_t(slot0 + nth) : i0 + i;
-    ++nth;
-    keys[o] = key[r];
-    vals[o] = uint32_t(o);
-    if (PAY) {
-      T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
-      T m = pin.lcell3;
-      if (pin.rho) {
-        T rr = pin.rho[size_t(g.rs) * i];
-        vx = (vx * rr) / rr;
-        vy = (vy * rr) / rr;
-        vz = (vz * rr) / rr;
-        m = rr * pin.lcell3;
-      }
-      rec32_t* out = static_cast<rec32_t*>(packed) + o;
-      out->a = a[r];
-      out->b = make_float4(float(vx), float(vy), float(vz), float(m));
-    } else {
-      static_cast<float4*>(packed)[o] = a[r];
-    }
-  }
-}
-
-template <bool PAY>
-__global__ void __launch_bounds__(256) k_permute(const void* __restrict__ packed, const uint32_t* __restrict__ vals, int64_t n,
-                                                  rec_t* __restrict__ spos, float4* __restrict__ spay) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t j = vals[i];
+// One thread per particle: cell + in-cell offset in f64, the record appended to the particle's bucket.
+//   a = (21-bit offsets x|y|z, linear cell, particle index [| far flag])     b = (vx', vy', vz', m)  [only with a payload]
+// with v' = (rho*v)/rho and m = rho*Lcell^3 evaluated in the input dtype (interp.py:199-213,272-273).
+template <typename T, bool PAY>
+__global__ void __launch_bounds__(256) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
+                                                         uint32_t* __restrict__ cursor, void* __restrict__ rec1) {
+  // pos / pin.vel / pin.rho point at particle i0 (a chunk); the stored index is global (i0 + local)
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= np) return;
+  double x, y, z;
+  if (!load_pos(pos, g, i, x, y, z)) return;
+  uint32_t fx, fy, fz;
+  bool far = false;
+  const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+            cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+  const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+  const uint32_t dst = atomicAdd(cursor + (lin >> g.bshift), 1u);
+  const unsigned long long w = (unsigned long long)fx | ((unsigned long long)fy << kFixBits) | ((unsigned long long)fz << (2 * kFixBits));
+  const uint32_t idx = uint32_t(i0 + i) | (far ? kFarBit : 0u);
   if (PAY) {
-    const float4* src = reinterpret_cast<const float4*>(static_cast<const rec32_t*>(packed) + j);
-    const float4 a = __ldg(src), b = __ldg(src + 1);
-    spos[i] = a;
-    spay[i] = b;
+    T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
+    T m = pin.lcell3;
+    if (pin.rho) {
+      const T rr = pin.rho[size_t(g.rs) * i];
+      vx = (vx * rr) / rr;
+      vy = (vy * rr) / rr;
+      vz = (vz * rr) / rr;
+      m = rr * pin.lcell3;
+    }
+    st256(static_cast<Rec32*>(rec1) + dst, uint32_t(w), uint32_t(w >> 32), lin, idx, __float_as_uint(float(vx)),
+          __float_as_uint(float(vy)), __float_as_uint(float(vz)), __float_as_uint(float(m)));
   } else {
-    spos[i] = __ldg(static_cast<const float4*>(packed) + j);
+    static_cast<uint4*>(rec1)[dst] = make_uint4(uint32_t(w), uint32_t(w >> 32), lin, idx);
   }
 }
 
-// row_start[r] = first sorted position whose row (key >> shift) is >= r, for r in [0, nrows]; row_start[nrows] = n.
-// Four consecutive keys per thread (one 16-byte load).
-__global__ void __launch_bounds__(256) k_row_starts(const uint32_t* __restrict__ keys, int64_t n, int shift, uint32_t nrows,
-                                                     uint32_t* __restrict__ start) {
-  const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  const int lane = threadIdx.x & 31;
-  uint32_t k4[4] = {0u, 0u, 0u, 0u};
-  if (i0 + 3 < n) {
-    const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
-    k4[0] = v.x; k4[1] = v.y; k4[2] = v.z; k4[3] = v.w;
+// per-cell counts: T[cell] += 1 (the records of one bucket are contiguous, so the counters in flight are L2 resident)
+template <bool PAY>
+__global__ void __launch_bounds__(256) k_cell_count(const void* __restrict__ rec1, const vp_nn_stats_dev* __restrict__ stats,
+                                                     uint32_t* __restrict__ tab) {
+  const uint32_t n = uint32_t(stats->n_kept);
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t cell = PAY ? static_cast<const Rec32*>(rec1)[i].a.cell : static_cast<const RecA*>(rec1)[i].cell;
+  atomicAdd(tab + cell, 1u);
+}
+
+// counting-sort placement: the record goes to (start of its cell) + (a slot handed out by the cell's cursor), rewritten in
+// search format.  The order of the particles INSIDE a cell is whatever the cursors hand out; no result depends on it.
+struct PlaceGeom {
+  float sx, sy, sz;   // cell size * 2^-21 per axis
+  float hz;
+  uint32_t gz;
+};
+template <bool PAY>
+__global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec1, vp_nn_stats_dev* __restrict__ stats,
+                                                     uint32_t* __restrict__ tab, PlaceGeom pg, void* __restrict__ srec) {
+  const uint32_t n = uint32_t(stats->n_kept);
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r[8];
+  if (PAY) {
+    ld256(static_cast<const Rec32*>(rec1) + i, r);
   } else {
-    for (int u = 0; u < 4; ++u)
-      if (i0 + u < n) k4[u] = keys[i0 + u];
+    const uint4 v = static_cast<const uint4*>(rec1)[i];
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
   }
-  int64_t kp = (i0 == 0 || i0 >= n) ? -1 : int64_t(keys[i0 - 1] >> shift);
-  // almost every warp sees no row boundary at all (2^30 keys, 3e4 rows): leave before the per-key logic
-  bool change = false;
-  {
-    int64_t prev = kp;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (i0 + u < n) {
-        const int64_t k = int64_t(k4[u] >> shift);
-        change |= (k != prev) || (i0 + u == n - 1);
-        prev = k;
-      }
-  }
-  if (!__any_sync(0xffffffffu, change)) return;
-#pragma unroll 1
-  for (int u = 0; u < 4; ++u) {
-    const int64_t i = i0 + u;
-    int64_t lo = 1, hi = 0;  // empty range
-    uint32_t v = 0;
-    if (i < n) {
-      const uint32_t k = k4[u] >> shift;
-      if (int64_t(k) != kp) { lo = kp + 1; hi = k; v = uint32_t(i); }
-      kp = k;
-      if (i == n - 1) {
-        // tail: rows after the last key (done by this thread after its own range)
-        for (int64_t c = lo; c <= hi; ++c) start[c] = v;
-        lo = int64_t(k) + 1; hi = nrows; v = uint32_t(n);
-      }
-    }
-    // long gaps are filled by the whole warp
-    unsigned big = __ballot_sync(0xffffffffu, hi - lo >= 32);
-    while (big) {
-      int src = __ffs(big) - 1;
-      big &= big - 1;
-      int64_t l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
-      uint32_t vv = __shfl_sync(0xffffffffu, v, src);
-      for (int64_t c = l + lane; c <= h; c += 32) start[c] = vv;
-      if (lane == src) { lo = 1; hi = 0; }
-    }
-    for (int64_t c = lo; c <= hi; ++c) start[c] = v;
-  }
-}
-
-// One CTA per SM, rows of cells handed out by a global cursor (a row = one x plane, 2^yb consecutive y, all z: `bins`
-// cells, contiguous in the linear cell order).  The radix sort has brought the row's (key, slot) pairs together; here
-// they are counted per cell in shared memory, the exclusive prefix gives the row's part of the cell-start table, and
-// every slot is written to its place inside the row (taken from the per-cell cursors) in a shared-memory order table
-// that is then copied out coalesced: this finishes the sort without the two radix passes over the low key bits.
-// (Scattering the slots straight to global memory is transaction bound, ~45 G scattered stores/s.  Gathering the packed
-// records in the same kernel was tried and lost: 51 ms against 29 ms for the plain k_permute that follows.)
-//   short rows (len <= ordcap < 65536): 16-bit counters, two per word, + u32 order table   -- the common case
-//   long rows (dense clusters):         32-bit counters, slots scattered to the global array
-// The order of the particles INSIDE a cell is whatever the cursors hand out; no result depends on it (ties are decided
-// by particle index).
-constexpr int kGroupThreads = 1024;
-constexpr int kGroupUnroll = 8;
-constexpr int kMaxBins = 33 * 1024;         // 132 KB of u32 counters: a 32 x 1025 (y, z) tile of the 1024^3 cell grid fits
-constexpr int kGroupSmemMax = 227 * 1024 - 256;   // opt-in dynamic shared memory, minus the static part
-
-template <bool SHORT>
-__device__ __forceinline__ uint32_t group_bump(uint32_t* cnt, uint32_t l) {   // previous value of counter l, then +1
-  if (SHORT) {
-    const uint32_t old = atomicAdd(&cnt[l >> 1], (l & 1u) ? 0x10000u : 1u);
-    return (l & 1u) ? (old >> 16) : (old & 0xffffu);
-  }
-  return atomicAdd(&cnt[l], 1u);
-}
-
-template <bool SHORT>
-__device__ __forceinline__ void group_row(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                          uint32_t* __restrict__ start, uint32_t* __restrict__ ordg, uint32_t* cnt, uint32_t* ord,
-                                          uint32_t* wsum, uint32_t lmask, uint32_t s, uint32_t e, uint32_t used, size_t cell0,
-                                          bool last, uint32_t n) {
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint32_t len = e - s;
-  const uint32_t words = SHORT ? (used + 1) / 2 : used;
-  for (uint32_t l = tid; l < words; l += kGroupThreads) cnt[l] = 0;
-  __syncthreads();
-  for (uint32_t p0 = s; p0 < e; p0 += kGroupThreads * kGroupUnroll) {
-    uint32_t k[kGroupUnroll];
-#pragma unroll
-    for (int u = 0; u < kGroupUnroll; ++u) {
-      const uint32_t p = p0 + u * kGroupThreads + tid;
-      k[u] = p < e ? keys[p] : 0xffffffffu;
-    }
-#pragma unroll
-    for (int u = 0; u < kGroupUnroll; ++u)
-      if (p0 + u * kGroupThreads + tid < e) group_bump<SHORT>(cnt, k[u] & lmask);
-  }
-  __syncthreads();
-  // exclusive scan of the counters: thread t owns words [t*ch, (t+1)*ch)
-  const uint32_t ch = ((words + kGroupThreads - 1) / kGroupThreads) | 1u;   // odd: conflict-free strided scan
-  const uint32_t b0 = min(uint32_t(tid) * ch, words), b1 = min(b0 + ch, words);
-  uint32_t sum = 0;
-  for (uint32_t l = b0; l < b1; ++l) {
-    const uint32_t c = cnt[l];
-    sum += SHORT ? (c & 0xffffu) + (c >> 16) : c;
-  }
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[w] = incl;
-  __syncthreads();
-  if (w == 0) {
-    uint32_t v = wsum[lane], iv = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
-      if (lane >= o) iv += t;
-    }
-    wsum[lane] = iv - v;
-  }
-  __syncthreads();
-  uint32_t run = wsum[w] + incl - sum;   // row-relative
-  for (uint32_t l = b0; l < b1; ++l) {
-    const uint32_t c = cnt[l];
-    if (SHORT) {
-      const uint32_t c0 = c & 0xffffu, c1 = c >> 16;
-      cnt[l] = run | ((run + c0) << 16);
-      run += c0 + c1;
-    } else {
-      cnt[l] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  if (SHORT) {
-    const uint16_t* c16 = reinterpret_cast<const uint16_t*>(cnt);
-    for (uint32_t l = tid; l < used; l += kGroupThreads) start[cell0 + l] = s + c16[l];
-  } else {
-    for (uint32_t l = tid; l < used; l += kGroupThreads) start[cell0 + l] = s + cnt[l];
-  }
-  if (last && tid == 0) start[cell0 + used] = n;
-  __syncthreads();   // the cursors move only after the table has been copied out
-  for (uint32_t p0 = s; p0 < e; p0 += kGroupThreads * kGroupUnroll) {
-    uint32_t k[kGroupUnroll], v[kGroupUnroll];
-#pragma unroll
-    for (int u = 0; u < kGroupUnroll; ++u) {
-      const uint32_t p = p0 + u * kGroupThreads + tid;
-      k[u] = p < e ? keys[p] : 0xffffffffu;
-      v[u] = p < e ? vals[p] : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < kGroupUnroll; ++u) {
-      if (p0 + u * kGroupThreads + tid >= e) continue;
-      const uint32_t d = group_bump<SHORT>(cnt, k[u] & lmask);
-      if (SHORT) ord[d] = v[u];
-      else ordg[s + d] = v[u];
-    }
-  }
-  __syncthreads();
-  if (SHORT) {
-    for (uint32_t t = tid; t < len; t += kGroupThreads) ordg[s + t] = ord[t];
-  }
-  __syncthreads();   // before the next row clears the counters
-}
-
-__global__ void __launch_bounds__(kGroupThreads, 1) k_group_rows(const uint32_t* __restrict__ keys,
-                                                                  const uint32_t* __restrict__ vals,
-                                                                  const uint32_t* __restrict__ row_start,
-                                                                  uint32_t* __restrict__ start, uint32_t* __restrict__ ordg, Grid g,
-                                                                  uint32_t nrows, uint32_t n, uint32_t ordcap,
-                                                                  unsigned long long* __restrict__ cursor) {
-  extern __shared__ __align__(16) uint32_t cnt[];   // counters / cursors (u16 pairs or u32), then the order table of short rows
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t next_row;
-  uint32_t* ord = cnt + ((uint32_t(g.bins) + 1) / 2 + 3 & ~3u);
-  const int tid = threadIdx.x;
-  const uint32_t lmask = (1u << g.lb) - 1u;
-  if (tid == 0) next_row = uint32_t(min(atomicAdd(cursor, 1ull), (unsigned long long)nrows));
-  __syncthreads();
-  uint32_t row = next_row;
-  while (row < nrows) {
-    __syncthreads();   // everybody has read next_row
-    if (tid == 0) next_row = uint32_t(min(atomicAdd(cursor, 1ull), (unsigned long long)nrows));
-    const uint32_t s = row_start[row], e = row_start[row + 1];
-    const uint32_t cx = row / uint32_t(g.nyc), ycb = row - cx * uint32_t(g.nyc);
-    const int y0 = int(ycb << g.yb);
-    const int ny_here = min(1 << g.yb, g.gy - y0);
-    const uint32_t used = uint32_t(ny_here) * uint32_t(g.gz);
-    const size_t cell0 = (size_t(cx) * g.gy + size_t(y0)) * g.gz;
-    const bool last = row == nrows - 1;
-    if (e - s <= ordcap)
-      group_row<true>(keys, vals, start, ordg, cnt, ord, wsum, lmask, s, e, used, cell0, last, n);
-    else
-      group_row<false>(keys, vals, start, ordg, cnt, ord, wsum, lmask, s, e, used, cell0, last, n);
-    row = next_row;   // written before the barriers inside group_row
-  }
+  const uint32_t cell = r[2];
+  const uint32_t dst = atomicAdd(tab + cell, 1u);
+  const unsigned long long w = (unsigned long long)r[0] | ((unsigned long long)r[1] << 32);
+  const uint32_t fx = uint32_t(w) & kFixMax, fy = uint32_t(w >> kFixBits) & kFixMax, fz = uint32_t(w >> (2 * kFixBits)) & kFixMax;
+  const uint32_t cz = cell % pg.gz;
+  const float ux = (float(fx) + 0.5f) * pg.sx, uy = (float(fy) + 0.5f) * pg.sy;
+  const float uz = fmaf(float(cz & 31u), pg.hz, (float(fz) + 0.5f) * pg.sz);
+  if (r[3] & kFarBit) atomicAdd(&stats->n_far, 1ull);
+  if (PAY)
+    st256(static_cast<Rec32*>(srec) + dst, __float_as_uint(ux), __float_as_uint(uy), __float_as_uint(uz), r[3], r[4], r[5], r[6], r[7]);
+  else
+    static_cast<float4*>(srec)[dst] = make_float4(ux, uy, uz, __uint_as_float(r[3]));
 }
 
 __global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
@@ -401,113 +272,287 @@ __device__ __forceinline__ bool proven(const Best& b, double margin) {
 
 struct Lattice {
   const double *qx, *qy, *qz;  // node coordinates
-  const int *cx, *cy, *cz;     // cell of each node coordinate (clamped)
-  // ring-1 tables, precomputed on the host: origin-relative f32 coordinates and, per axis, the distance from the
-  // node to the nearest face of its ring-1 cell block behind which unexamined particles may exist (rounded down,
-  // with the cell-assignment slack already taken off; +inf when the block reaches an open end of the grid)
-  const float *fx, *fy, *fz;
-  const float *mx, *my, *mz;
   // first cell of the node's 2-cell window per axis: [w, w+1] is the pair of cells whose common face is nearest
   // to the node (with the default grid the nodes sit exactly on cell corners, so the 2x2x2 block proves radius h)
   const int *wx, *wy, *wz;
+  // node coordinate minus the low corner of cell w, evaluated in f64 on the host and rounded to f32: every distance
+  // of the f32 prefilter is formed from numbers of the size of a cell
+  const float *rx, *ry, *rz;
+  // per axis, the distance from the node to the nearest face of its 2-cell window behind which unexamined particles may
+  // exist (rounded down, with the cell-assignment slack already taken off; +inf when the window reaches an open end)
+  const float *mx, *my, *mz;
   int nx, ny, nz;
 };
 
-// Stage A of the search, f32 prefilter, one thread per lattice node (consecutive lanes = consecutive z nodes).
-// Candidates: the 2x2x2 cell block around the node (4 cell rows x 2 contiguous cells).  Distances are evaluated in f32
-// on origin-relative coordinates and the two smallest are tracked.  A node is settled here only if (a) the runner-up
-// is farther than the winner by more than a rigorous bound on the f32 error of both and (b) the winner (plus that
-// bound) is strictly inside the proof margin of the block.  Unproven nodes go to stage B (4x4x4 block); proven but
-// ambiguous ones (near ties, exact ties) go straight to the exact f64 kernel.
+// f32 prefilter.  Distances are evaluated in f32 on window-relative coordinates and the two smallest are tracked.  A node
+// is settled by the prefilter only if (a) the runner-up is farther than the winner by more than a rigorous bound on the
+// f32 error of both and (b) the winner (plus that bound) is strictly inside the proof margin of the examined block.
 //
-// f32 error bound: stored coordinate c~ = fl(p-o), query q~ = fl(q-o), d~x = fl(q~-c~):
-//   |d~x - dx| <= 2^-24 (|q-o| + |p-o| + |dx|) <= 2^-23 (E + |dx|) =: eps      (E = grid extent)
-//   |d~^2 - d^2| <= 2 sqrt(3) d eps + 3 eps^2 + 2^-22 d^2
+// Error bound: the stored offset is good to 2^-22 h (fixed point) and every f32 operation that forms a coordinate
+// difference works on numbers below 34 h (brick-relative z) -- at most seven roundings of 2^-24 * 34 h: per axis
+//   |d~x - dx| <= 2e-5 h =: eps,      |d~^2 - d^2| <= 2 sqrt(3) d eps + 3 eps^2 + 2^-22 d^2
 struct Cand {
   float b1, b2;
   int bi;
 };
-__device__ __forceinline__ void scan_row(const rec_t* __restrict__ part, uint32_t s, uint32_t e, float qx, float qy, float qz,
-                                         Cand& c) {
+__device__ __forceinline__ void cand_update(Cand& c, float d, int p) {
+  const bool lt = d < c.b1;
+  c.b2 = fminf(c.b2, lt ? c.b1 : d);
+  c.bi = lt ? p : c.bi;
+  c.b1 = lt ? d : c.b1;
+}
+// records [s, e) of the sorted array (element stride `rs` float4), query relative to the frame the records are stored in
+__device__ __forceinline__ void scan_range(const rec_t* __restrict__ part, int rs, uint32_t s, uint32_t e, float qx, float qy, float qz,
+                                           Cand& c) {
 #pragma unroll 1
   for (uint32_t p = s; p < e; ++p) {
-    const float4 q = __ldg(part + p);
+    const float4 q = __ldg(part + size_t(p) * rs);
     const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
-    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const bool lt = d < c.b1;
-    c.b2 = fminf(c.b2, lt ? c.b1 : d);
-    c.bi = lt ? int(p) : c.bi;
-    c.b1 = lt ? d : c.b1;
+    cand_update(c, fmaf(dz, dz, fmaf(dy, dy, dx * dx)), int(p));
   }
 }
 // 0: settled, 1: proven-or-not but ambiguous / empty -> exact, 2: unambiguous but unproven -> wider block
-__device__ __forceinline__ int judge(const Cand& c, float extent, float margin, float* tol_out) {
+__device__ __forceinline__ int judge(const Cand& c, float eps, float margin) {
   if (c.bi < 0) return 2;
   const float rb = sqrtf(c.b2 < INFINITY ? c.b2 : c.b1);
-  const float eps = 1.5e-7f * (extent + rb);
   const float tol = 8.f * rb * eps + 8.f * eps * eps + 1e-6f * rb * rb;   // >= err(b1) + err(b2)
-  *tol_out = tol;
   const bool proven = (margin == INFINITY) || (margin > 0.f && c.b1 + tol < margin * margin);
   if (!proven) return 2;
   return (c.b2 - c.b1 > tol) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(256) k_search_block2(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
-                                                        Lattice L, float extent, int32_t* __restrict__ nn,
-                                                        int32_t* __restrict__ nn_pos, uint32_t* __restrict__ list_b,
-                                                        uint32_t* __restrict__ list_c, vp_nn_stats_dev* __restrict__ stats) {
+struct SearchOut {
+  int32_t* nn;        // particle index per node (may be null)
+  int32_t* nn_pos;    // sorted position per node (may be null)
+  uint32_t* list_b;   // nodes for the wider stage
+  uint32_t* list_c;   // nodes for the exact stage
+  vp_nn_stats_dev* stats;
+};
+__device__ __forceinline__ void emit(const SearchOut& o, const rec_t* __restrict__ part, int rs, size_t node, int verdict, int pos) {
+  if (verdict == 0) {
+    if (o.nn) o.nn[node] = int(__float_as_uint(__ldg(&part[size_t(pos) * rs].w)) & ~kFarBit);
+    if (o.nn_pos) o.nn_pos[node] = pos;
+  } else if (verdict == 1) {
+    o.list_c[atomicAdd(&o.stats->n_wide, 1ull)] = uint32_t(node);
+  } else {
+    o.list_b[atomicAdd(&o.stats->n_b, 1ull)] = uint32_t(node);
+  }
+}
+
+// true: with particles outside the cell grid (clamped into end cells, their stored offsets saturated) every node whose
+// examined block touches an end cell is decided by the exact stage, which reads the caller's coordinates
+__device__ __forceinline__ bool touches_end(int c0, int c1, int g) { return c0 <= 0 || c1 >= g - 1; }
+
+// Stage A, general form (any lattice / any cell size): one thread per node, the 2x2x2 window cell by cell.
+__global__ void __launch_bounds__(256) k_search_cells2(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
+                                                        Lattice L, float eps, SearchOut out) {
   // block = (z nodes, y rows); grid = (z chunks, y chunks, x)
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int i = blockIdx.z;
   if (k >= L.nz || j >= L.ny) return;
   const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-  const float qx = __ldg(L.fx + i), qy = __ldg(L.fy + j), qz = __ldg(L.fz + k);
   const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
-  const int z1 = min(wz + 1, g.gz - 1);
+  if (out.stats->n_far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
+    out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    return;
+  }
+  const float rx = __ldg(L.rx + i), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
+  const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
   Cand c;
   c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
-  uint32_t rs[4], re[4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int X = wx + a, Y = wy + b;
-      const bool in = X < g.gx && Y < g.gy;
-      const size_t row = in ? (size_t(X) * g.gy + Y) * g.gz : 0;
-      rs[a * 2 + b] = in ? __ldg(start + row + wz) : 0u;
-      re[a * 2 + b] = in ? __ldg(start + row + z1 + 1) : 0u;
-    }
+      if (X >= g.gx || Y >= g.gy) continue;
+      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+      const float qx = rx - float(a) * hx, qy = ry - float(b) * hy;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) scan_row(part, rs[r], re[r], qx, qy, qz, c);
+      for (int zc = 0; zc < 2; ++zc) {
+        const int Z = wz + zc;
+        if (Z >= g.gz) continue;
+        const float qz = rz - float(zc) * hz + float(Z & 31) * hz;
+        scan_range(part, rs, __ldg(start + row + Z), __ldg(start + row + Z + 1), qx, qy, qz, c);
+      }
+    }
   const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
-  float tol;
-  const int verdict = judge(c, extent, m, &tol);
-  if (verdict == 0) {
-    if (nn) nn[node] = __float_as_int(__ldg(&part[c.bi].w));
-    if (nn_pos) nn_pos[node] = c.bi;
-  } else if (verdict == 1) {
-    list_c[atomicAdd(&stats->n_wide, 1ull)] = uint32_t(node);
-  } else {
-    list_b[atomicAdd(&stats->pad, 1ull)] = uint32_t(node);
+  emit(out, part, rs, node, judge(c, eps, m), c.bi);
+}
+
+// Stage A, brick form: the lattice windows are consecutive cells along every axis (node i <-> cells [w0+i, w0+i+1]) and
+// the z windows start on a multiple of 32.  One CTA = kBX x kBY x 32 nodes.  The particles of the covering
+// (kBX+1) x (kBY+1) rows x 33 cells are staged once in shared memory with their coordinates re-based to the low corner of
+// the brick's first cell; a thread then owns the node column (j, k) and walks i, keeping the cell ranges of the two rows it
+// shares with the next node in registers.
+constexpr int kBX = 8, kBY = 8, kBZ = 32;
+constexpr int kBRows = (kBX + 1) * (kBY + 1);
+constexpr int kBCells = kBZ + 2;            // cell boundaries per row: 33 cells + end
+constexpr int kBrickCap = 3584;             // staged particles per brick (mean 2673 at one particle per cell); more -> cell-by-cell form
+constexpr size_t kBrickSmem = size_t(kBrickCap) * 16 + size_t(kBRows) * kBCells * 4 + (3 * size_t(kBRows) + 4) * 4;
+
+__device__ __forceinline__ void scan_smem(const float4* sp, uint32_t s, uint32_t e, float qx, float qy, float qz, Cand& c) {
+#pragma unroll 1
+  for (uint32_t p = s; p < e; ++p) {
+    const float4 q = sp[p];
+    const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
+    cand_update(c, fmaf(dz, dz, fmaf(dy, dy, dx * dx)), int(p));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_search_brick(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
+                                                       Lattice L, float eps, SearchOut out) {
+  extern __shared__ __align__(16) unsigned char brick_smem[];
+  float4* sp = reinterpret_cast<float4*>(brick_smem);                                       // [kBrickCap] staged particles
+  // smem index of the first staged particle of cell (row, z); last entry of a row = end
+  uint32_t (*cofs)[kBCells] = reinterpret_cast<uint32_t (*)[kBCells]>(brick_smem + size_t(kBrickCap) * 16);
+  uint32_t* seg_s = reinterpret_cast<uint32_t*>(cofs + kBRows);
+  uint32_t* seg_last = seg_s + kBRows;
+  uint32_t* seg_off = seg_last + kBRows;                                                    // [kBRows + 1]
+  __shared__ int fallback;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int k0 = blockIdx.x * kBZ, j0 = blockIdx.y * kBY, i0 = blockIdx.z * kBX;
+  const int X0 = __ldg(L.wx + i0), Y0 = __ldg(L.wy + j0), Z0 = __ldg(L.wz + k0);   // first cell of the brick
+  const int Zend = min(Z0 + kBZ, g.gz - 1);                                         // last staged cell along z
+  const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
+
+  // ---- stage: row segments -> shared memory
+  if (tid < kBRows) {
+    const int X = X0 + tid / (kBY + 1), Y = Y0 + tid % (kBY + 1);
+    uint32_t s = 0, e = 0, l = 0xffffffffu;
+    if (X < g.gx && Y < g.gy) {
+      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+      s = __ldg(start + row + Z0);
+      e = __ldg(start + row + Zend + 1);
+      if (Z0 + kBZ <= Zend) l = __ldg(start + row + Z0 + kBZ);   // first record of the 33rd cell (next 32-cell z block)
+    }
+    seg_s[tid] = s;
+    seg_last[tid] = l;
+    seg_off[tid] = e - s;
+  }
+  __syncthreads();
+  if (w == 0) {   // exclusive prefix of the kBRows segment lengths
+    uint32_t carry = 0;
+    for (int base = 0; base < kBRows; base += 32) {
+      const int r = base + lane;
+      const uint32_t v = r < kBRows ? seg_off[r] : 0u;
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (r < kBRows) seg_off[r] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      seg_off[kBRows] = carry;
+      fallback = carry > uint32_t(kBrickCap);
+    }
+  }
+  __syncthreads();
+  const bool fb = fallback != 0;
+  if (!fb) {
+    for (int t = tid; t < kBRows * kBCells; t += 256) {
+      const int r = t / kBCells, z = t - r * kBCells;
+      const int X = X0 + r / (kBY + 1), Y = Y0 + r % (kBY + 1);
+      uint32_t v = seg_off[r];
+      if (X < g.gx && Y < g.gy) {
+        const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+        v += __ldg(start + row + min(Z0 + z, Zend + 1)) - seg_s[r];
+      }
+      cofs[r][z] = v;
+    }
+    for (int r = w; r < kBRows; r += 8) {
+      const uint32_t s = seg_s[r], len = seg_off[r + 1] - seg_off[r], off = seg_off[r], last = seg_last[r];
+      const float bx = float(r / (kBY + 1)) * hx, by = float(r % (kBY + 1)) * hy;
+      for (uint32_t p = lane; p < len; p += 32) {
+        const float4 q = __ldg(part + size_t(s + p) * rs);
+        sp[off + p] = make_float4(q.x + bx, q.y + by, (s + p >= last) ? q.z + float(kBZ) * hz : q.z, __int_as_float(int(s + p)));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- search: thread (j = warp, k = lane), i = 0 .. kBX-1
+  const int j = j0 + w, k = k0 + lane;
+  if (j >= L.ny || k >= L.nz) return;
+  const bool far = out.stats->n_far != 0;
+  const float ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
+  const float my = __ldg(L.my + j), mz = __ldg(L.mz + k);
+  const int wy = Y0 + w, wz = Z0 + lane;
+  if (fb) {
+    // crowded brick: same arithmetic from global memory, cell by cell
+    for (int ii = 0; ii < kBX; ++ii) {
+      const int i = i0 + ii;
+      if (i >= L.nx) break;
+      const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
+      const int wx = X0 + ii;
+      if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
+        out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+        continue;
+      }
+      const float rx = __ldg(L.rx + i);
+      Cand c;
+      c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int X = wx + a, Y = wy + b;
+          if (X >= g.gx || Y >= g.gy) continue;
+          const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+          for (int zc = 0; zc < 2; ++zc) {
+            const int Z = wz + zc;
+            if (Z >= g.gz) continue;
+            scan_range(part, rs, __ldg(start + row + Z), __ldg(start + row + Z + 1), rx - float(a) * hx, ry - float(b) * hy,
+                       rz - float(zc) * hz + float(Z & 31) * hz, c);
+          }
+        }
+      emit(out, part, rs, node, judge(c, eps, fminf(__ldg(L.mx + i), fminf(my, mz))), c.bi);
+    }
+    return;
+  }
+  const float qy = ry + float(w) * hy, qz = rz + float(lane) * hz;   // brick-relative node coordinates
+  const int r0 = w;                                                    // row index of (ii, w): ii*(kBY+1) + w
+  uint32_t s0 = cofs[r0][lane], e0 = cofs[r0][lane + 2], s1 = cofs[r0 + 1][lane], e1 = cofs[r0 + 1][lane + 2];
+  for (int ii = 0; ii < kBX; ++ii) {
+    const int i = i0 + ii;
+    if (i >= L.nx) break;
+    const int rn = (ii + 1) * (kBY + 1) + w;
+    const uint32_t s2 = cofs[rn][lane], e2 = cofs[rn][lane + 2], s3 = cofs[rn + 1][lane], e3 = cofs[rn + 1][lane + 2];
+    const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
+    const int wx = X0 + ii;
+    if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
+      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    } else {
+      const float qx = __ldg(L.rx + i) + float(ii) * hx;
+      Cand c;
+      c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+      scan_smem(sp, s0, e0, qx, qy, qz, c);
+      scan_smem(sp, s1, e1, qx, qy, qz, c);
+      scan_smem(sp, s2, e2, qx, qy, qz, c);
+      scan_smem(sp, s3, e3, qx, qy, qz, c);
+      const int verdict = judge(c, eps, fminf(__ldg(L.mx + i), fminf(my, mz)));
+      emit(out, part, rs, node, verdict, c.bi >= 0 ? __float_as_int(sp[c.bi].w) : -1);
+    }
+    s0 = s2; e0 = e2; s1 = s3; e1 = e3;
   }
 }
 
 // Stage B: the nodes stage A could not prove, one thread per listed node, the 32-cell union of the three 4x2x2 bars
 // through the window (proves sqrt(2) h with corner-aligned nodes), same f32 prefilter and verdict.  What is still
 // unproven or ambiguous goes to the exact kernel.
-__global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
-                                                        Lattice L, float extent, int32_t* __restrict__ nn,
-                                                        int32_t* __restrict__ nn_pos, const uint32_t* __restrict__ list_b,
-                                                        uint32_t* __restrict__ list_c, vp_nn_stats_dev* __restrict__ stats) {
-  const unsigned long long nb = stats->pad;
+__global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
+                                                        Lattice L, float eps, SearchOut out) {
+  const unsigned long long nb = out.stats->n_b;
+  const bool far = out.stats->n_far != 0;
+  const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
   for (unsigned long long t = (unsigned long long)(blockIdx.x) * blockDim.x + threadIdx.x; t < nb;
        t += (unsigned long long)(gridDim.x) * blockDim.x) {
-    const uint32_t node = list_b[t];
+    const uint32_t node = out.list_b[t];
     const int k = int(node % uint32_t(L.nz));
     const uint32_t u = node / uint32_t(L.nz);
     const int j = int(u % uint32_t(L.ny)), i = int(u / uint32_t(L.ny));
-    const float qx = L.fx[i], qy = L.fy[j], qz = L.fz[k];
     // examined region = union of the three 4x2x2 bars through the 2x2x2 window (32 cells instead of 64):
     //   central rows (x, y both inside the window): 4 cells along z;  rows one step outside in x OR y: 2 cells
     const int wx = L.wx[i], wy = L.wy[j], wz = L.wz[k];
@@ -515,6 +560,11 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
     const int x0 = max(wx - 1, 0), x1 = min(wx + 2, g.gx - 1);
     const int y0 = max(wy - 1, 0), y1 = min(wy + 2, g.gy - 1);
     const int z0 = max(wz - 1, 0), z1 = min(wz + 2, g.gz - 1);
+    if (far && (touches_end(x0, x1, g.gx) || touches_end(y0, y1, g.gy) || touches_end(z0, z1, g.gz))) {
+      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = node;
+      continue;
+    }
+    const float rx = L.rx[i], ry = L.ry[j], rz = L.rz[k];
     Cand c;
     c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
     for (int X = x0; X <= x1; ++X)
@@ -523,7 +573,9 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
         if (!xin && !yin) continue;                                  // corner rows are not part of the union
         const size_t row = (size_t(X) * g.gy + Y) * g.gz;
         const int a = (xin && yin) ? z0 : wz, b = (xin && yin) ? z1 : wz1;
-        scan_row(part, __ldg(start + row + a), __ldg(start + row + b + 1), qx, qy, qz, c);
+        const float qx = rx - float(X - wx) * hx, qy = ry - float(Y - wy) * hy;
+        for (int Z = a; Z <= b; ++Z)
+          scan_range(part, rs, __ldg(start + row + Z), __ldg(start + row + Z + 1), qx, qy, rz - float(Z - wz) * hz + float(Z & 31) * hz, c);
       }
     // nearest unexamined point: beyond a 4-cell bar end along one axis, or outside the 2-cell window along two axes
     const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
@@ -540,12 +592,12 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
     const double md = fmin(m4, diag);
     float m = INFINITY;
     if (md != INFINITY) m = md > 0.0 ? __double2float_rd(md * (1.0 - 1.0 / 1048576.0)) : 0.f;
-    float tol;
-    if (judge(c, extent, m, &tol) == 0) {
-      if (nn) nn[node] = __float_as_int(__ldg(&part[c.bi].w));
-      if (nn_pos) nn_pos[node] = c.bi;
+    const int verdict = judge(c, eps, m);
+    if (verdict == 0) {
+      if (out.nn) out.nn[node] = int(__float_as_uint(__ldg(&part[size_t(c.bi) * rs].w)) & ~kFarBit);
+      if (out.nn_pos) out.nn_pos[node] = c.bi;
     } else {
-      list_c[atomicAdd(&stats->n_wide, 1ull)] = node;
+      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = node;
     }
   }
 }
@@ -554,7 +606,7 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
 // as the node's 2x2x2 window and is widened (1, 3, 7, ... cells per side) until the proof holds (or every kept
 // particle has been examined).
 template <typename T>
-__global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ part, const uint32_t* __restrict__ start,
+__global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start,
                                                        const T* __restrict__ pos, Grid g, Lattice L, int32_t* __restrict__ nn,
                                                        int32_t* __restrict__ nn_pos, const uint32_t* __restrict__ list,
                                                        vp_nn_stats_dev* __restrict__ stats) {
@@ -598,7 +650,7 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
         const uint32_t c2 = c1 + __shfl_sync(0xffffffffu, e - s, 2), c3 = c2 + __shfl_sync(0xffffffffu, e - s, 3);
         for (uint32_t t = lane; t < c3; t += 32) {
           const uint32_t p = t < c0 ? s0 + t : (t < c1 ? s1 + (t - c0) : (t < c2 ? s2 + (t - c1) : s3 + (t - c2)));
-          const int id = __float_as_int(__ldg(&part[p].w));
+          const int id = int(__float_as_uint(__ldg(&part[size_t(p) * rs].w)) & ~kFarBit);
           const int before = b.idx;
           const size_t pb = size_t(g.ps) * size_t(id);
           consider(b, qx, qy, qz, double(pos[pb]), double(pos[pb + 1]), double(pos[pb + 2]), id);
@@ -610,7 +662,7 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
           size_t row = (size_t(X) * g.gy + Y) * g.gz;
           uint32_t s = __ldg(start + row + z0), e = __ldg(start + row + z1 + 1);
           for (uint32_t p = s; p < e; ++p) {
-            const int id = __float_as_int(__ldg(&part[p].w));
+            const int id = int(__float_as_uint(__ldg(&part[size_t(p) * rs].w)) & ~kFarBit);
             const int before = b.idx;
             const size_t pb = size_t(g.ps) * size_t(id);
             consider(b, qx, qy, qz, double(pos[pb]), double(pos[pb + 1]), double(pos[pb + 2]), id);
@@ -643,13 +695,14 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
   }
 }
 
-// fields from the SORTED payload: node -> sorted position of its nearest particle -> (v', m)
-__global__ void __launch_bounds__(256) k_fields_sorted(const int32_t* __restrict__ nn_pos, int64_t n, const float4* __restrict__ spay,
-                                                        float* vx, float* vy, float* vz, float* px, float* py, float* pz, float* e,
-                                                        float* mo) {
+// fields from the SORTED records: node -> sorted position of its nearest particle -> (v', m) (second half of the record)
+// (stride, offset in float4 units: 2, 1 for the sorted 32-byte records; 1, 0 for a plain [np] float4 payload array)
+__global__ void __launch_bounds__(256) k_fields_sorted(const int32_t* __restrict__ nn_pos, int64_t n, const float4* __restrict__ srec,
+                                                        int stride, int offset, float* vx, float* vy, float* vz, float* px, float* py,
+                                                        float* pz, float* e, float* mo) {
   int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const float4 w = __ldg(spay + nn_pos[t]);
+  const float4 w = __ldg(srec + size_t(stride) * size_t(nn_pos[t]) + offset);
   if (vx) vx[t] = w.x;
   if (vy) vy[t] = w.y;
   if (vz) vz[t] = w.z;
@@ -720,6 +773,8 @@ AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, 
   return a;
 }
 
+constexpr uint32_t kMaxBuckets = 16384;   // 64 KB of shared-memory counters in k_bin_hist
+
 Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, const double* qz, int nz,
                const vp_nn_opts& o) {
   int gx = o.cells_x, gy = o.cells_y, gz = o.cells_z;
@@ -748,19 +803,8 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
       corner_x = false;
     }
   }
-  // key layout: the widest y chunk whose (y, z) tile of cells fits the shared-memory counters of k_group_permute;
-  // the grid is coarsened until a z row fits the counters and (row << lb | local) fits 32 bits
-  int yb = 0, lb = 0, nyc = 1;
-  for (;;) {
-    bool fits = gz <= kMaxBins;
-    if (fits) {
-      yb = 0;
-      while ((int64_t(2) << yb) * gz <= kMaxBins && (1 << yb) < gy) ++yb;
-      lb = vp_ceil_log2(uint64_t(gz) << yb);
-      nyc = (gy + (1 << yb) - 1) >> yb;
-      fits = (uint64_t(gx) * uint64_t(nyc)) <= (uint64_t(1) << (32 - lb)) && double(gx) * gy * gz < 4294967295.0;
-    }
-    if (fits) break;
+  // the linear cell index must fit 32 bits: coarsen until it does
+  while (double(gx) * gy * gz >= 4294967295.0) {
     gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
     corner_x = corner_y = corner_z = false;
   }
@@ -785,34 +829,47 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
   g.ps = o.row_stride > 0 ? o.row_stride : 3;
   g.vs = o.row_stride > 0 ? o.row_stride : 3;
   g.rs = o.row_stride > 0 ? o.row_stride : 1;
-  g.yb = yb; g.lb = lb; g.nyc = nyc; g.bins = gz << yb;
+  // buckets of 2^bshift consecutive cells holding ~2^17 particles on average (a 4 MB window of records: the counting
+  // sort inside it runs out of L2), at most kMaxBuckets of them
+  const uint64_t ncells = uint64_t(gx) * gy * gz;
+  const double cells_per_bucket = double(ncells) * 131072.0 / double(np > 0 ? np : 1);
+  int bshift = 0;
+  while (bshift < 31 && double(uint64_t(1) << bshift) * 1.4142135623730951 < cells_per_bucket) ++bshift;   // nearest power of two
+  if (const char* ev = getenv("VP_BUCKET_SHIFT")) bshift = atoi(ev);
+  if (bshift < 0) bshift = 0;
+  if (bshift > 31) bshift = 31;
+  while (bshift < 31 && ((ncells + (uint64_t(1) << bshift) - 1) >> bshift) > kMaxBuckets) ++bshift;
+  g.bshift = bshift;
+  g.nb = uint32_t((ncells + (uint64_t(1) << bshift) - 1) >> bshift);
+  if (g.nb < 1) g.nb = 1;
   return g;
 }
 
+size_t vp_scan_scratch_bytes_local(int64_t m) { return vp_align256(size_t((m + 4095) / 4096 + 1) * 4); }
+
 struct NNScratch {
-  size_t keys, packed, spos, start, rows, tail, total;
+  size_t rec1, srec, tab, small, tail, total;
 };
-NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint64_t nrows, int64_t nnodes) {
+NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint32_t nb, int64_t nnodes) {
   NNScratch s;
-  s.keys = vp_align256(size_t(np) * 4);
-  s.packed = vp_align256(size_t(np) * (pay ? sizeof(rec32_t) : sizeof(float4)));
-  s.spos = vp_align256(size_t(np) * sizeof(rec_t));
-  s.start = vp_align256((ncells + 1) * 4);
-  s.rows = vp_align256((nrows + 1) * 4);
-  size_t b_wide = 2 * vp_align256(size_t(nnodes) * 4), b_sort = vp_sort_scratch_bytes(np);
-  s.tail = b_sort > b_wide ? b_sort : b_wide;  // the sort scratch is dead once the records are permuted; the two node lists reuse it
-  s.total = 2 * s.keys + s.packed + s.spos + s.start + s.rows + s.tail + 2048;
+  s.rec1 = vp_align256(size_t(np) * (pay ? sizeof(Rec32) : sizeof(RecA)));
+  s.srec = pay ? 0 : vp_align256(size_t(np) * sizeof(rec_t));   // with a payload the sorted records are the caller's spay array
+  s.tab = vp_align256((ncells + 8) * 4);
+  s.small = 2 * vp_align256(size_t(nb + 1) * 4) + vp_scan_scratch_bytes_local(int64_t(ncells) + 1);
+  const size_t b_lists = 2 * vp_align256(size_t(nnodes) * 4);
+  s.tail = s.rec1 > b_lists ? s.rec1 : b_lists;   // the bucketed records are dead once placed; the two node lists reuse them
+  s.total = s.tail + s.srec + s.tab + s.small + 4096;
   return s;
 }
 
-// Optional payload travelling with the particles (whole-path use): sorted (v', m) records and the sorted position
-// of every node's nearest particle, so that the field kernel reads the payload almost sequentially.
+// Optional payload travelling with the particles (whole-path use): sorted 32-byte records (search half + (v', m) half) and
+// the sorted position of every node's nearest particle, so that the field kernel reads the payload almost sequentially.
 template <typename T>
 struct NNPayload {
   const T* vel = nullptr;
   const T* rho = nullptr;
   double lcell3 = 1.0;
-  float4* spay_out = nullptr;    // [np]
+  float4* srec_out = nullptr;    // [np] x 2 float4
   int32_t* nn_pos_out = nullptr;  // [nnodes]
 };
 
@@ -824,51 +881,52 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
   VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
   const bool has_pay = pay != nullptr;
-  if (has_pay) VP_REQUIRE(pay->vel && pay->spay_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
+  if (has_pay) VP_REQUIRE(pay->vel && pay->srec_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
   vp_nn_opts o;
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
   const Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
   const int gx = g.gx, gy = g.gy, gz = g.gz;
   const uint64_t ncells = uint64_t(gx) * gy * gz;
-  const uint64_t nrows = uint64_t(gx) * g.nyc;
-  const int row_bits = vp_ceil_log2(nrows);
 
   // ---- lattice tables (host -> pinned -> device)
   const size_t nt = size_t(nx) + ny + nz;
-  const size_t off_c = vp_align256(nt * 8), off_f = off_c + vp_align256(nt * 4), off_m = off_f + vp_align256(nt * 4);
-  const size_t off_w = off_m + vp_align256(nt * 4);
-  const size_t tab_bytes = off_w + vp_align256(nt * 4);
-  if (ctx->pinned_cap < tab_bytes) {
-    if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
-    VP_CUDA(cudaMallocHost(&ctx->pinned_h, tab_bytes));
-    ctx->pinned_cap = tab_bytes;
-  }
-  if (ctx->small_cap < tab_bytes) {
+  const size_t off_w = vp_align256(nt * 8), off_r = off_w + vp_align256(nt * 4), off_m = off_r + vp_align256(nt * 4);
+  const size_t tab_bytes = off_m + vp_align256(nt * 4);
+  if (ctx->pinned_cap < tab_bytes || ctx->small_cap < tab_bytes) {
     VP_CUDA(cudaStreamSynchronize(st));
-    if (ctx->small_d) cudaFree(ctx->small_d);
-    VP_CUDA(cudaMalloc(&ctx->small_d, tab_bytes));
-    ctx->small_cap = tab_bytes;
+    if (ctx->pinned_cap < tab_bytes) {
+      if (ctx->pinned_h) cudaFreeHost(ctx->pinned_h);
+      VP_CUDA(cudaMallocHost(&ctx->pinned_h, tab_bytes));
+      ctx->pinned_cap = tab_bytes;
+    }
+    if (ctx->small_cap < tab_bytes) {
+      if (ctx->small_d) cudaFree(ctx->small_d);
+      VP_CUDA(cudaMalloc(&ctx->small_d, tab_bytes));
+      ctx->small_cap = tab_bytes;
+    }
   }
-  VP_CUDA(cudaStreamSynchronize(st));  // the pinned block may still be in flight from a previous call
+  // the pinned block may still be in flight from the previous call's upload: wait for that copy only
+  if (ctx->ev_tables) VP_CUDA(cudaEventSynchronize(ctx->ev_tables));
+  else VP_CUDA(cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming));
   char* hb = static_cast<char*>(ctx->pinned_h);
   double* hq = reinterpret_cast<double*>(hb);
-  int* hc = reinterpret_cast<int*>(hb + off_c);
-  float* hf = reinterpret_cast<float*>(hb + off_f);
-  float* hm = reinterpret_cast<float*>(hb + off_m);
   int* hw = reinterpret_cast<int*>(hb + off_w);
+  float* hr = reinterpret_cast<float*>(hb + off_r);
+  float* hm = reinterpret_cast<float*>(hb + off_m);
+  bool consecutive = true;
   auto fill_axis = [&](const double* q, int n, int at, double o_, double h_, double ih, int gg, bool closed_lo, bool closed_hi) {
     for (int i = 0; i < n; ++i) {
       double f = (q[i] - o_) * ih;
       int c = !(f > 0.0) ? 0 : (f >= double(gg) ? gg - 1 : int(f));
       hq[at + i] = q[i];
-      hc[at + i] = c;
-      hf[at + i] = float(q[i] - o_);
       // 2-cell window [w, w+1]: the neighbour on the side of the nearer face of cell c
       int w = (f - double(c) < 0.5) ? c - 1 : c;
       if (w > gg - 2) w = gg - 2;
       if (w < 0) w = 0;
       hw[at + i] = w;
+      if (i > 0 && w != hw[at + i - 1] + 1) consecutive = false;
+      hr[at + i] = float(q[i] - (o_ + double(w) * h_));
       // same expression as the device axis_margin() for the block [c0, c1]
       const int c0 = w, c1 = w + 1 > gg - 1 ? gg - 1 : w + 1;
       double m = INFINITY;
@@ -888,135 +946,149 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   fill_axis(qx, nx, 0, g.ox, g.hx, g.ihx, gx, g.closed_xlo != 0, g.closed_xhi != 0);
   fill_axis(qy, ny, nx, g.oy, g.hy, g.ihy, gy, false, false);
   fill_axis(qz, nz, nx + ny, g.oz, g.hz, g.ihz, gz, false, false);
+  // brick kernel: consecutive windows on every axis, z windows starting on a 32-cell boundary, node inside its window
+  bool brick = consecutive && (hw[nx + ny] % 32 == 0) && gx >= 2 && gy >= 2 && gz >= 2 && !getenv("VP_NO_BRICK");
+  for (size_t t = 0; t < nt && brick; ++t) {
+    const double hh = t < size_t(nx) ? g.hx : (t < size_t(nx + ny) ? g.hy : g.hz);
+    if (!(hr[t] >= -0.5f * float(hh) && hr[t] <= 2.5f * float(hh))) brick = false;   // keeps the f32 error bound of the brick frame
+  }
   VP_CUDA(cudaMemcpyAsync(ctx->small_d, ctx->pinned_h, tab_bytes, cudaMemcpyHostToDevice, st));
+  VP_CUDA(cudaEventRecord(ctx->ev_tables, st));
   const char* db = reinterpret_cast<const char*>(ctx->small_d);
   Lattice L;
   L.qx = reinterpret_cast<const double*>(db); L.qy = L.qx + nx; L.qz = L.qy + ny;
-  L.cx = reinterpret_cast<const int*>(db + off_c); L.cy = L.cx + nx; L.cz = L.cy + ny;
-  L.fx = reinterpret_cast<const float*>(db + off_f); L.fy = L.fx + nx; L.fz = L.fy + ny;
-  L.mx = reinterpret_cast<const float*>(db + off_m); L.my = L.mx + nx; L.mz = L.my + ny;
   L.wx = reinterpret_cast<const int*>(db + off_w); L.wy = L.wx + nx; L.wz = L.wy + ny;
+  L.rx = reinterpret_cast<const float*>(db + off_r); L.ry = L.rx + nx; L.rz = L.ry + ny;
+  L.mx = reinterpret_cast<const float*>(db + off_m); L.my = L.mx + nx; L.mz = L.my + ny;
   L.nx = nx; L.ny = ny; L.nz = nz;
 
   // ---- scratch
-  const NNScratch sc = nn_scratch(np, has_pay, ncells, nrows, nnodes);
+  const NNScratch sc = nn_scratch(np, has_pay, ncells, g.nb, nnodes);
   vp_arena_scope scope(ctx);
   VP_TRY(vp_arena_reserve(ctx, sc.total));
-  uint32_t* keys = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
-  uint32_t* vals = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.keys));
-  void* packed = vp_arena_alloc(ctx, sc.packed);
-  rec_t* spos = static_cast<rec_t*>(vp_arena_alloc(ctx, sc.spos));
-  uint32_t* start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.start));
-  uint32_t* row_start = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.rows));
-  void* scratch = vp_arena_alloc(ctx, sc.tail);
-  VP_REQUIRE(keys && vals && packed && spos && start && row_start && scratch, "vp_nn_grid: arena carve failed");
-  uint32_t* node_list = static_cast<uint32_t*>(scratch);                                      // -> exact kernel
-  uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> 4x4x4 stage
+  void* rec1 = vp_arena_alloc(ctx, sc.tail);
+  rec_t* srec = has_pay ? reinterpret_cast<rec_t*>(pay->srec_out) : static_cast<rec_t*>(vp_arena_alloc(ctx, sc.srec ? sc.srec : 256));
+  uint32_t* xtab = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.tab));
+  uint32_t* hist = static_cast<uint32_t*>(vp_arena_alloc(ctx, vp_align256(size_t(g.nb + 1) * 4)));
+  uint32_t* cursor = static_cast<uint32_t*>(vp_arena_alloc(ctx, vp_align256(size_t(g.nb + 1) * 4)));
+  uint32_t* sums = static_cast<uint32_t*>(vp_arena_alloc(ctx, vp_scan_scratch_bytes_local(int64_t(ncells) + 1)));
+  VP_REQUIRE(rec1 && srec && xtab && hist && cursor && sums, "vp_nn_grid: arena carve failed");
+  uint32_t* node_list = static_cast<uint32_t*>(rec1);                                           // -> exact kernel
+  uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> wider stage
+  const int rs = has_pay ? 2 : 1;     // float4 stride of the sorted records
 
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
-  int64_t n = np;
+  VP_CUDA(cudaMemsetAsync(xtab, 0, (ncells + 8) * 4, st));
+  VP_CUDA(cudaMemsetAsync(hist, 0, size_t(g.nb + 1) * 4, st));
+  // counts / cursors live at xtab + 4 (16-byte aligned for the scan); after the placement cursor c holds the start of cell
+  // c + 1, so the start table is the same array read from xtab + 3 (entry 0 = the zero in front of the counters)
+  uint32_t* tab = xtab + 4;
   if (np > 0) {
-    // read pos (+vel, rho), write key, slot and the packed record
     const double es = sizeof(T);
-    vp_stage stage(ctx, "k1a_keygen_pack", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 8.0 + 32.0 : 3 * es + 8.0 + 16.0));
-    unsigned long long* kept_d = &ctx->nn_stats_d->n_kept;
-    auto launch = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
+    const size_t hist_smem = size_t(g.nb) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * 4)));
+      attr_done = true;
+    }
+    auto launch_hist = [&](const T* p, int64_t n_c) {
+      int64_t nb64 = (n_c + 255) / 256;
+      const int64_t cap = int64_t(ctx->sm_count) * 8;
+      k_bin_hist<T><<<unsigned(nb64 < cap ? nb64 : cap), 256, hist_smem, st>>>(p, n_c, g, hist);
+    };
+    auto launch_scatter = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
       pin.vel = v;
       pin.rho = r;
       pin.lcell3 = T(has_pay ? pay->lcell3 : 1.0);
-      if (o.use_x_keep) {
-        const unsigned nb = unsigned((n_c + 256 * 8 - 1) / (256 * 8));
-        if (has_pay) k_keygen_pack<T, true, 8><<<nb, 256, 0, st>>>(p, pin, n_c, i0, g, keys, vals, packed, kept_d);
-        else k_keygen_pack<T, false, 8><<<nb, 256, 0, st>>>(p, pin, n_c, i0, g, keys, vals, packed, kept_d);
-      } else {
-        const unsigned nb = unsigned((n_c + 255) / 256);
-        if (has_pay) k_keygen_pack<T, true, 1><<<nb, 256, 0, st>>>(p, pin, n_c, i0, g, keys, vals, packed, kept_d);
-        else k_keygen_pack<T, false, 1><<<nb, 256, 0, st>>>(p, pin, n_c, i0, g, keys, vals, packed, kept_d);
-      }
+      const unsigned nbk = unsigned((n_c + 255) / 256);
+      if (has_pay) k_bin_scatter<T, true><<<nbk, 256, 0, st>>>(p, pin, n_c, i0, g, cursor, rec1);
+      else k_bin_scatter<T, false><<<nbk, 256, 0, st>>>(p, pin, n_c, i0, g, cursor, rec1);
     };
     if (host_pos) {
-      // positions arrive from the host in chunks (copy stream); keys + records of chunk c are made while chunk c+1 moves
+      // positions arrive from the host in chunks (copy stream); the bucket histogram of chunk c is taken while chunk c+1 moves
       VP_REQUIRE(!has_pay && o.row_stride == 0 && !o.use_x_keep, "vp_nn_grid: host position streaming is the plain compact form");
       VP_TRY(vp_host_streams(ctx));
       const int64_t chunk = host_pos->chunk;
       T* posd = const_cast<T*>(pos);
       VP_CUDA(cudaEventRecord(ctx->ev_used[0], st));   // order the copy stream after everything already queued on st
       VP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+      vp_stage stage(ctx, "k1a_bin_hist", st, int((np + chunk - 1) / chunk), double(np) * 3 * es);
       int c = 0;
       for (int64_t i0 = 0; i0 < np; i0 += chunk, ++c) {
         const int64_t n_c = np - i0 < chunk ? np - i0 : chunk;
         VP_CUDA(cudaMemcpyAsync(posd + 3 * i0, static_cast<const T*>(host_pos->pos_h) + 3 * i0, size_t(n_c) * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
         VP_CUDA(cudaEventRecord(ctx->ev_h2d[c & 1], ctx->copy_stream));
         VP_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[c & 1], 0));
-        launch(posd + 3 * i0, nullptr, nullptr, n_c, i0);
+        launch_hist(posd + 3 * i0, n_c);
       }
     } else {
-      launch(pos, has_pay ? pay->vel : nullptr, has_pay ? pay->rho : nullptr, np, 0);
+      vp_stage stage(ctx, "k1a_bin_hist", st, 1, double(np) * 3 * es);
+      launch_hist(pos, np);
+    }
+    k_bin_offsets<<<1, 1024, 0, st>>>(hist, cursor, g.nb, ctx->nn_stats_d);
+    ctx->n_launch += 1;
+    {
+      // read pos (+vel, rho), write one record
+      vp_stage stage(ctx, "k1b_bin_scatter", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 32.0 : 3 * es + 16.0));
+      launch_scatter(pos, has_pay ? pay->vel : nullptr, has_pay ? pay->rho : nullptr, np, 0);
+    }
+    const unsigned nbk = unsigned((np + 255) / 256);
+    {
+      // the cell index of every record read (one sector), one counter bumped
+      vp_stage stage(ctx, "k1c_cell_count", st, 1, double(np) * (has_pay ? 32.0 : 16.0) + double(ncells) * 4.0);
+      if (has_pay) k_cell_count<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab);
+      else k_cell_count<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab);
+    }
+    VP_TRY(vp_scan_exclusive_u32(ctx, tab, int64_t(ncells) + 1, sums, st));
+    {
+      // record read, cursor bumped, record written in cell order
+      vp_stage stage(ctx, "k1e_cell_place", st, 1, double(np) * (has_pay ? 64.0 : 32.0) + double(ncells) * 4.0);
+      PlaceGeom pg;
+      pg.sx = float(g.hx / 2097152.0); pg.sy = float(g.hy / 2097152.0); pg.sz = float(g.hz / 2097152.0);
+      pg.hz = float(g.hz);
+      pg.gz = uint32_t(gz);
+      if (has_pay) k_cell_place<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec);
+      else k_cell_place<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec);
     }
     VP_CHECK_LAUNCH();
   }
-  if (o.use_x_keep) {
-    unsigned long long kept = 0;
-    VP_CUDA(cudaMemcpyAsync(&kept, &ctx->nn_stats_d->n_kept, 8, cudaMemcpyDeviceToHost, st));
-    VP_CUDA(cudaStreamSynchronize(st));  // documented: the filtered form syncs once
-    n = int64_t(kept);
-  } else {
-    unsigned long long kept = (unsigned long long)np;
-    VP_CUDA(cudaMemcpyAsync(&ctx->nn_stats_d->n_kept, &kept, 8, cudaMemcpyHostToDevice, st));
-  }
-  // rows brought together by the sort (stable LSD passes over the row bits only), cells inside a row by the group kernel
-  VP_TRY(vp_sort_pairs_range(ctx, keys, vals, n, g.lb, row_bits, scratch, st));
-  if (n > 0) {
-    {
-      vp_stage stage(ctx, "k1d_row_starts", st, 1, double(n) * 4.0 + double(nrows) * 4.0);
-      k_row_starts<<<unsigned((n + 1023) / 1024), 256, 0, st>>>(keys, n, g.lb, uint32_t(nrows), row_start);
-    }
-    uint32_t* svals = static_cast<uint32_t*>(scratch);          // first alternate buffer of the finished sort
-    {
-      // key read twice (count, place), slot read and written, cell table written
-      vp_stage stage(ctx, "k1c_group_rows", st, 1, double(n) * 16.0 + double(ncells) * 4.0);
-      const size_t ord_off = (((size_t(g.bins) + 1) / 2 + 3) & ~size_t(3)) * 4;      // bytes of the packed 16-bit counters
-      const uint32_t room = uint32_t((kGroupSmemMax - ord_off) / 4);
-      const uint32_t ordcap = room < 65535u ? room : 65535u;    // a short row's cursors fit 16 bits
-      size_t smem = ord_off + size_t(ordcap) * 4;
-      if (smem < size_t(g.bins) * 4) smem = size_t(g.bins) * 4;   // long rows: 32-bit counters
-      const unsigned nb = unsigned(nrows < uint64_t(ctx->sm_count) ? nrows : uint64_t(ctx->sm_count));
-      unsigned long long* cursor = &ctx->nn_stats_d->row_cursor;   // zeroed with the stats block above
-      VP_CUDA(cudaFuncSetAttribute(k_group_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kGroupSmemMax));
-      k_group_rows<<<nb, kGroupThreads, smem, st>>>(keys, vals, row_start, start, svals, g, uint32_t(nrows), uint32_t(n), ordcap,
-                                                    cursor);
-    }
-    {
-      // slot read, one packed record gathered, sorted records written
-      vp_stage stage(ctx, "k1c_permute", st, 1, double(n) * (4.0 + (has_pay ? 64.0 : 32.0)));
-      const unsigned nb = unsigned((n + 255) / 256);
-      if (has_pay) k_permute<true><<<nb, 256, 0, st>>>(packed, svals, n, spos, pay->spay_out);
-      else k_permute<false><<<nb, 256, 0, st>>>(packed, svals, n, spos, nullptr);
-    }
-  } else {
-    k_fill_u32<<<unsigned((ncells + 1 + 255) / 256), 256, 0, st>>>(start, int64_t(ncells + 1), 0u);
-  }
-  VP_CHECK_LAUNCH();
+  const uint32_t* start = xtab + 3;
   int32_t* nn_pos = has_pay ? pay->nn_pos_out : nullptr;
-  const float extent = float(fmax(fmax(g.gx * g.hx, g.gy * g.hy), g.gz * g.hz));
+  const float hmax = float(fmax(fmax(g.hx, g.hy), g.hz));
+  const float eps = 2e-5f * hmax;
+  SearchOut so;
+  so.nn = nn; so.nn_pos = nn_pos; so.list_b = list_b; so.list_c = node_list; so.stats = ctx->nn_stats_d;
   {
     // sorted records read once + cell starts read once + one index written per node
-    vp_stage stage(ctx, "k1e_search_block2", st, 1, double(n) * sizeof(rec_t) + double(ncells) * 4.0 + double(nnodes) * 4.0);
-    // block = (z nodes, y rows), one x plane per blockIdx.z: no integer division in the kernel
-    int bx = nz >= 256 ? 256 : ((nz + 31) / 32) * 32;
-    int by = 256 / bx;
-    dim3 block(bx, by, 1), grid((nz + bx - 1) / bx, (ny + by - 1) / by, nx);
-    VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
-    k_search_block2<<<grid, block, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, list_b, node_list, ctx->nn_stats_d);
+    vp_stage stage(ctx, brick ? "k1f_search_brick" : "k1f_search_cells2", st, 1,
+                   double(np) * (has_pay ? 32.0 : 16.0) + double(ncells) * 4.0 + double(nnodes) * 4.0);
+    if (brick) {
+      dim3 grid((nz + kBZ - 1) / kBZ, (ny + kBY - 1) / kBY, (nx + kBX - 1) / kBX);
+      VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
+      static bool brick_attr = false;
+      if (!brick_attr) {
+        VP_CUDA(cudaFuncSetAttribute(k_search_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBrickSmem)));
+        brick_attr = true;
+      }
+      k_search_brick<<<grid, 256, kBrickSmem, st>>>(srec, rs, start, g, L, eps, so);
+    } else {
+      // block = (z nodes, y rows), one x plane per blockIdx.z: no integer division in the kernel
+      int bx = nz >= 256 ? 256 : ((nz + 31) / 32) * 32;
+      int by = 256 / bx;
+      dim3 block(bx, by, 1), grid((nz + bx - 1) / bx, (ny + by - 1) / by, nx);
+      VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
+      k_search_cells2<<<grid, block, 0, st>>>(srec, rs, start, g, L, eps, so);
+    }
   }
   {
-    vp_stage stage(ctx, "k1e_search_block4", st, 1);
-    k_search_block4<<<ctx->sm_count * 8, 256, 0, st>>>(spos, start, g, L, extent, nn, nn_pos, list_b, node_list, ctx->nn_stats_d);
+    vp_stage stage(ctx, "k1g_search_block4", st, 1);
+    k_search_block4<<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
   }
   {
-    vp_stage stage(ctx, "k1f_search_exact", st, 1);
-    k_search_exact<T><<<ctx->sm_count * 8, 256, 0, st>>>(spos, start, pos, g, L, nn, nn_pos, node_list, ctx->nn_stats_d);
+    vp_stage stage(ctx, "k1h_search_exact", st, 1);
+    k_search_exact<T><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, pos, g, L, nn, nn_pos, node_list, ctx->nn_stats_d);
   }
   VP_CHECK_LAUNCH();
   return VP_OK;
@@ -1030,7 +1102,7 @@ int nn_payload_typed(vp_ctx* ctx, const void* pos, const void* vel, const void* 
   pay.vel = static_cast<const T*>(vel);
   pay.rho = static_cast<const T*>(rho);
   pay.lcell3 = lcell3;
-  pay.spay_out = reinterpret_cast<float4*>(spay);
+  pay.srec_out = reinterpret_cast<float4*>(spay);
   pay.nn_pos_out = nn_pos;
   return nn_grid_typed<T>(ctx, static_cast<const T*>(pos), np, qx, nx, qy, ny, qz, nz, nn_idx, &pay, opts, st);
 }
@@ -1224,8 +1296,10 @@ int slab_scatter_p2p_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho
 }  // namespace
 
 // ---- sharded particle exchange fused into the bucketing kernel (peer stores over NVLink)
-extern "C" int vp_slab_p2p_alloc(vp_ctx* ctx, size_t bytes, unsigned char* handle_out) {
-  VP_REQUIRE(ctx && handle_out && bytes > 0, "vp_slab_p2p_alloc: bad argument");
+// Teardown order of an IPC-shared buffer (CUDA: freeing an exported allocation while another process still has it mapped is
+// undefined):  every rank vp_slab_p2p_close()  ->  barrier across the ranks (caller)  ->  vp_slab_p2p_alloc() may free.
+extern "C" int vp_slab_p2p_close(vp_ctx* ctx) {
+  VP_REQUIRE(ctx, "vp_slab_p2p_close: null ctx");
   VP_CUDA(cudaSetDevice(ctx->device));
   VP_CUDA(cudaDeviceSynchronize());
   if (ctx->slab_open) {
@@ -1233,6 +1307,14 @@ extern "C" int vp_slab_p2p_alloc(vp_ctx* ctx, size_t bytes, unsigned char* handl
       if (d != ctx->slab_rank && ctx->slab_peer[d]) { cudaIpcCloseMemHandle(ctx->slab_peer[d]); ctx->slab_peer[d] = nullptr; }
     ctx->slab_open = false;
   }
+  return VP_OK;
+}
+
+extern "C" int vp_slab_p2p_alloc(vp_ctx* ctx, size_t bytes, unsigned char* handle_out) {
+  VP_REQUIRE(ctx && handle_out && bytes > 0, "vp_slab_p2p_alloc: bad argument");
+  VP_REQUIRE(!ctx->slab_open, "vp_slab_p2p_alloc: peers are still mapped -- vp_slab_p2p_close() on every rank, then a barrier, first");
+  VP_CUDA(cudaSetDevice(ctx->device));
+  VP_CUDA(cudaDeviceSynchronize());
   if (ctx->slab_recv) { VP_CUDA(cudaFree(ctx->slab_recv)); ctx->slab_recv = nullptr; }
   VP_CUDA(cudaMalloc(&ctx->slab_recv, bytes));
   ctx->slab_recv_bytes = bytes;
@@ -1277,6 +1359,7 @@ static SlabRanges make_ranges(const double* lo_h, const double* hi_h, int nranks
 extern "C" int vp_slab_count(vp_ctx* ctx, const void* pos_d, int dtype, int64_t np, const double* lo_h, const double* hi_h,
                              int nranks, int64_t* counts_h, void* stream) {
   VP_REQUIRE(ctx && pos_d && lo_h && hi_h && counts_h && nranks >= 1 && nranks <= 16 && np >= 0, "vp_slab_count: bad argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_CUDA(cudaSetDevice(ctx->device));
   const SlabRanges R = make_ranges(lo_h, hi_h, nranks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1289,6 +1372,7 @@ extern "C" int vp_slab_count(vp_ctx* ctx, const void* pos_d, int dtype, int64_t 
 extern "C" int vp_slab_scatter_p2p(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
                                    const double* lo_h, const double* hi_h, int nranks, const int64_t* first_row_h, void* stream) {
   VP_REQUIRE(ctx && pos_d && vel_d && lo_h && hi_h && first_row_h, "vp_slab_scatter_p2p: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(ctx->slab_open && ctx->slab_nranks == nranks, "vp_slab_scatter_p2p: peer buffers not opened for %d ranks", nranks);
   VP_CUDA(cudaSetDevice(ctx->device));
   const SlabRanges R = make_ranges(lo_h, hi_h, nranks);
@@ -1307,6 +1391,7 @@ extern "C" int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d,
                               const double* lo_h, const double* hi_h, int nranks, void* rows_d, int64_t cap_rows, int64_t* counts_h,
                               void* stream) {
   VP_REQUIRE(ctx && pos_d && vel_d && lo_h && hi_h && rows_d && counts_h, "vp_slab_bucket: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(nranks >= 1 && nranks <= 16 && np >= 0, "vp_slab_bucket: 1..16 ranks supported");
   VP_CUDA(cudaSetDevice(ctx->device));
   SlabRanges R;
@@ -1423,7 +1508,7 @@ size_t vp_nn_grid_scratch_bytes_tables(int64_t np, int pos_dtype, const double* 
   if (opts) o = *opts;
   Grid g = plan_grid(np, qx, nx, qy, ny, qz, nz, o);
   (void)pos_dtype;
-  return nn_scratch(np, true, uint64_t(g.gx) * g.gy * g.gz, uint64_t(g.gx) * g.nyc, int64_t(nx) * ny * nz).total + 4096;
+  return nn_scratch(np, true, uint64_t(g.gx) * g.gy * g.gz, g.nb, int64_t(nx) * ny * nz).total + 4096;
 }
 
 extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
@@ -1431,6 +1516,7 @@ extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* ve
                                   double lcell3, int32_t* nn_idx_d, int32_t* nn_pos_d, float* spay_d, const vp_nn_opts* opts,
                                   void* stream) {
   VP_REQUIRE(ctx && pos_d && vel_d && qx_h && qy_h && qz_h && nn_pos_d && spay_d, "vp_nn_grid_payload: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vp_nn_grid_payload: bad sizes");
   VP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1444,17 +1530,22 @@ extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* ve
 
 extern "C" int vp_fields_sorted(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, float* const v_d[3],
                                 float* const p_d[3], float* e_d, float* m_d, void* stream) {
+  return vp_fields_from_records(ctx, nn_pos_d, n_nodes, spay_d, 2, 1, v_d, p_d, e_d, m_d, static_cast<cudaStream_t>(stream));
+}
+
+int vp_fields_from_records(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, int stride, int offset,
+                           float* const v_d[3], float* const p_d[3], float* e_d, float* m_d, cudaStream_t st) {
   VP_REQUIRE(ctx && nn_pos_d && spay_d, "vp_fields_sorted: null argument");
+  vp_call_guard guard(ctx, st);
   if (n_nodes == 0) return VP_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* v[3] = {v_d ? v_d[0] : nullptr, v_d ? v_d[1] : nullptr, v_d ? v_d[2] : nullptr};
   float* p[3] = {p_d ? p_d[0] : nullptr, p_d ? p_d[1] : nullptr, p_d ? p_d[2] : nullptr};
   int nplanes = (e_d != nullptr) + (m_d != nullptr);
   for (int c = 0; c < 3; ++c) nplanes += (v[c] != nullptr) + (p[c] != nullptr);
   // per node: sorted position read, 16-byte payload record read, 4 B written per plane
   vp_stage stage(ctx, "k3_fields_sorted", st, 1, double(n_nodes) * (4.0 + 16.0 + 4.0 * nplanes));
-  k_fields_sorted<<<unsigned((n_nodes + 255) / 256), 256, 0, st>>>(nn_pos_d, n_nodes, reinterpret_cast<const float4*>(spay_d), v[0],
-                                                                   v[1], v[2], p[0], p[1], p[2], e_d, m_d);
+  k_fields_sorted<<<unsigned((n_nodes + 255) / 256), 256, 0, st>>>(nn_pos_d, n_nodes, reinterpret_cast<const float4*>(spay_d), stride,
+                                                                   offset, v[0], v[1], v[2], p[0], p[1], p[2], e_d, m_d);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
@@ -1463,6 +1554,7 @@ extern "C" int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t
                           const double* qy_h, int ny, const double* qz_h, int nz, int32_t* nn_idx_d,
                           const vp_nn_opts* opts, void* stream) {
   VP_REQUIRE(ctx && pos_d && qx_h && qy_h && qz_h && nn_idx_d, "vp_nn_grid: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vp_nn_grid: bad sizes");
   VP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1482,11 +1574,11 @@ extern "C" int vp_nn_grid_plan(int64_t np, const double* qx_h, int nx, const dou
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
   const Grid g = plan_grid(np, qx_h, nx, qy_h, ny, qz_h, nz, o);
-  const uint64_t ncells = uint64_t(g.gx) * g.gy * g.gz, nrows = uint64_t(g.gx) * g.nyc;
+  const uint64_t ncells = uint64_t(g.gx) * g.gy * g.gz;
   info_out[0] = g.gx; info_out[1] = g.gy; info_out[2] = g.gz;
-  info_out[3] = g.yb; info_out[4] = g.lb; info_out[5] = g.nyc; info_out[6] = g.bins;
-  info_out[7] = vp_ceil_log2(nrows);
-  info_out[8] = int64_t((nn_scratch(np, true, ncells, nrows, int64_t(nx) * ny * nz).total + (size_t(1) << 20) - 1) >> 20);
+  info_out[3] = g.bshift; info_out[4] = g.nb; info_out[5] = 0; info_out[6] = 0;
+  info_out[7] = 0;
+  info_out[8] = int64_t((nn_scratch(np, true, ncells, g.nb, int64_t(nx) * ny * nz).total + (size_t(1) << 20) - 1) >> 20);
   // corner aligned: cells of the node spacing with every node on a cell corner (the 2x2x2 block then proves radius h)
   const double sp = nx > 1 ? (qx_h[nx - 1] - qx_h[0]) / (nx - 1) : 0.0;
   info_out[9] = (g.gx == nx + 1 && nx > 1 && fabs(g.hx - sp) <= 1e-9 * fabs(sp)) ? 1 : 0;
@@ -1495,6 +1587,7 @@ extern "C" int vp_nn_grid_plan(int64_t np, const double* qx_h, int nx, const dou
 
 extern "C" int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_t* n_kept, void* stream) {
   VP_REQUIRE(ctx, "vp_nn_grid_stats: null ctx");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   vp_nn_stats_dev h;
   VP_CUDA(cudaMemcpyAsync(&h, ctx->nn_stats_d, sizeof h, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
   VP_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -1507,6 +1600,7 @@ extern "C" int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresol
 extern "C" int vp_gather_rows(vp_ctx* ctx, const int32_t* idx_d, int64_t n, const void* src_d, int row_bytes, void* dst_d,
                               void* stream) {
   VP_REQUIRE(ctx && idx_d && src_d && dst_d, "vp_gather_rows: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(row_bytes > 0 && row_bytes % 4 == 0, "vp_gather_rows: row_bytes must be a multiple of 4");
   if (n == 0) return VP_OK;
   int rw = row_bytes / 4;
@@ -1522,6 +1616,7 @@ extern "C" int vp_build_fields(vp_ctx* ctx, const int32_t* nn_idx_d, int64_t n_n
                                int dtype, double lcell3, float* const v_d[3], float* const p_d[3], float* e_d, float* m_d,
                                void* stream) {
   VP_REQUIRE(ctx && nn_idx_d && vel_d, "vp_build_fields: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
   if (n_nodes == 0) return VP_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* v[3] = {v_d ? v_d[0] : nullptr, v_d ? v_d[1] : nullptr, v_d ? v_d[2] : nullptr};

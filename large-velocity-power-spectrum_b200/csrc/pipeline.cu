@@ -36,6 +36,19 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
                     const double* edges_h, int nbins, int qmask, int strict, double* psum_h, uint64_t* nsample_h,
                     cudaStream_t st) {
   VP_REQUIRE(ctx && pos && vel && qx && qy && qz && k_h && edges_h && psum_h && nsample_h, "particles_to_pk: null argument");
+  vp_call_guard guard(ctx, st);
+  // an early error return must not leave H2D / pack work queued on the side streams into arena memory that the scope
+  // below has already released
+  struct SideDrain {
+    vp_ctx* c;
+    bool armed = false, ok = false;
+    ~SideDrain() {
+      if (armed && !ok) {
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        if (c->pack_stream) cudaStreamSynchronize(c->pack_stream);
+      }
+    }
+  } drain{ctx};
   VP_REQUIRE(dtype == VP_F32 || dtype == VP_F64, "particles_to_pk: bad dtype");
   VP_REQUIRE((qmask & 7) != 0 && np > 0 && N > 0, "particles_to_pk: nothing to do");
   VP_CUDA(cudaSetDevice(ctx->device));
@@ -52,7 +65,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   const int64_t chunk = np < (int64_t(1) << 24) ? np : (int64_t(1) << 24);
   size_t own = 0;
   if (on_host) own += vp_align256(size_t(np) * 3 * es) + vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 1024;
-  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * 16) + vp_align256(size_t(nbins) * 16) + 8192;
+  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * (on_host ? 16 : 32)) + vp_align256(size_t(nbins) * 16) + 8192;
   size_t inner = vp_nn_grid_scratch_bytes_tables(np, dtype, qx, N, qy, N, qz, N, nullptr);
   size_t inner2 = vp_pk_fields_scratch_bytes(plan);
   vp_arena_scope scope(ctx);
@@ -65,7 +78,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
     VP_REQUIRE(pos_res, "particles_to_pk: arena carve failed");
   }
   int32_t* nn_pos = static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4));
-  float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * 16));
+  float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * (on_host ? 16 : 32)));   // host path: (v', m) in input order; device path: sorted 32-byte records
   float* planes[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < nplanes; ++i) {
     planes[i] = static_cast<float*>(vp_arena_alloc(ctx, n3 * 4));
@@ -84,6 +97,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
     hc.pos_h = pos; hc.vel_h = vel; hc.rho_h = rho; hc.chunk = chunk;
     void* staging = vp_arena_alloc(ctx, vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 512);
     VP_REQUIRE(staging, "particles_to_pk: arena carve failed (staging)");
+    drain.armed = true;
     VP_TRY(vp_host_fork(ctx, st));
     VP_TRY(vp_nn_grid_host_pos(ctx, &hc, pos_res, dtype, np, qx, N, qy, N, qz, N, nn_pos, st));
     VP_TRY(vp_pack_payload_host(ctx, &hc, dtype, np, lcell3, staging, spay, st));
@@ -96,7 +110,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   if (want_v) { v3[0] = planes[at++]; v3[1] = planes[at++]; v3[2] = planes[at++]; }
   if (want_p) { p3[0] = planes[at++]; if (!strict) { p3[1] = planes[at++]; p3[2] = planes[at++]; } }
   if (want_e) e1 = planes[at++];
-  VP_TRY(vp_fields_sorted(ctx, nn_pos, int64_t(n3), spay, v3, p3, e1, nullptr, st));
+  VP_TRY(vp_fields_from_records(ctx, nn_pos, int64_t(n3), spay, on_host ? 1 : 2, on_host ? 0 : 1, v3, p3, e1, nullptr, st));
 
   std::vector<double> hp(nbins);
   auto one = [&](float** f, int nc, double scale, int row) -> int {
@@ -110,6 +124,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   if (want_v) VP_TRY(one(v3, 3, norm, 0));
   if (want_p) VP_TRY(one(p3, strict ? 1 : 3, strict ? 3.0 * norm : norm, 1));  // strict: three identical components
   if (want_e) VP_TRY(one(&e1, 1, norm, 2));
+  drain.ok = true;
   return VP_OK;
 }
 

@@ -226,6 +226,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
 
 }  // namespace
 
+int vp_scan_exclusive_u32(vp_ctx* ctx, uint32_t* a, int64_t m, uint32_t* sums, cudaStream_t st) {
+  if (m <= 0) return VP_OK;
+  const int64_t nchunks64 = (m + kScanChunk - 1) / kScanChunk;
+  VP_REQUIRE(nchunks64 < (int64_t(1) << 31), "vp_scan: too many elements");
+  const int nchunks = int(nchunks64);
+  vp_stage stage(ctx, "k1d_cell_scan", st, 3, double(m) * 12.0);   // read twice, written once
+  k_scan_sums<<<nchunks, kThreads, 0, st>>>(a, m, sums);
+  k_scan_top<<<1, kThreads, 0, st>>>(sums, nchunks);
+  k_scan_apply<<<nchunks, kThreads, 0, st>>>(a, m, sums);
+  VP_CHECK_LAUNCH();
+  return VP_OK;
+}
+
 static inline int64_t sort_nblocks(int64_t n) { return (n + kTile - 1) / kTile; }
 
 size_t vp_sort_scratch_bytes(int64_t n) {

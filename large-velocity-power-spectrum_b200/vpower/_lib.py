@@ -48,6 +48,7 @@ SIGNATURES = {
     "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
     "vp_fields_sorted": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_slab_bucket": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, _P, _L, C.POINTER(_L), _P]),
+    "vp_slab_p2p_close": (_I, [_P]),
     "vp_slab_p2p_alloc": (_I, [_P, C.c_size_t, C.c_char_p]),
     "vp_slab_p2p_open": (_I, [_P, _I, _I, C.c_char_p]),
     "vp_slab_p2p_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "vp_pk_dist_final": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
     "vp_pk_dist_p2p_alloc": (_I, [_P, _I, C.c_char_p]),
     "vp_pk_dist_p2p_open": (_I, [_P, C.c_char_p]),
+    "vp_pk_dist_p2p_close": (_I, [_P]),
     "vp_pk_dist_local_p2p": (_I, [_P, C.POINTER(_P), _I, _P]),
     "vp_pk_dist_final_p2p": (_I, [_P, _I, _P, _P, _P]),
     "vp_pk_fields": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P]),
@@ -201,8 +203,8 @@ def slab_bucket(pos_t, vel_t, rho_t, lo, hi):
     w = 7 if rho_t is not None else 6
     lo_a, lop = _as_dp(lo)
     hi_a, hip = _as_dp(hi)
-    cap = n + n // 2 + 1024          # halo duplicates; grown on demand
-    while True:
+    cap = n + n // 2 + 1024          # halo duplicates; if that is too small the call reports the exact need in `counts`
+    for attempt in range(2):
         rows = torch.empty((cap, w), dtype=pos_t.dtype, device=pos_t.device)
         counts = (_L * P)()
         rc = load_library().vp_slab_bucket(ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()),
@@ -210,9 +212,10 @@ def slab_bucket(pos_t, vel_t, rho_t, lo, hi):
                                            _P(rows.data_ptr()), cap, counts, stream_ptr())
         if rc == 0:
             break
-        if cap > 3 * n + 4096:
+        need = sum(int(c) for c in counts)
+        if attempt == 1 or need <= cap:          # a real error (CUDA, arguments), not the capacity
             _check(rc)
-        cap *= 2
+        cap = need                               # wide halos can send a particle to every rank: up to P * n rows
     counts = [int(c) for c in counts]
     return rows[:sum(counts)], counts
 
@@ -237,6 +240,9 @@ class SlabExchangeP2P:
         if need_bytes <= self.cap_bytes:
             return
         cap = int(need_bytes * 1.15) + (1 << 20)
+        # an exported buffer may only be freed once no peer maps it any more: unmap everywhere, barrier, then re-allocate
+        _check(load_library().vp_slab_p2p_close(ctx()))
+        dist.barrier(group=self.group)
         buf = C.create_string_buffer(64)
         _check(load_library().vp_slab_p2p_alloc(ctx(), cap, buf))
         mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
@@ -247,7 +253,8 @@ class SlabExchangeP2P:
         self.cap_bytes = cap
 
     def exchange(self, pos_t, vel_t, rho_t, lo, hi):
-        """-> torch tensor [rows, 7|6] aliasing this rank's receive buffer (all particles of its slab + halo)."""
+        """-> torch tensor [rows, 7|6] ALIASING this rank's receive buffer (all particles of its slab + halo).  It is valid
+        until the next exchange() on this object (which overwrites, and may re-allocate, the buffer): clone it to keep it."""
         torch = _torch()
         import torch.distributed as dist
         P = self.nranks
@@ -280,7 +287,8 @@ class SlabExchangeP2P:
 
 
 def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):
-    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, spay[np,4] f32 in cell order).
+    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, srec[np,8] f32 = the cell-sorted 32-byte records:
+    floats 0..3 the search half, floats 4..7 the payload (v'x, v'y, v'z, m)).
     With opts.row_stride > 0 the three tensors are column views of one interleaved row tensor."""
     torch = _torch()
     assert pos_t.is_cuda and vel_t.dtype == pos_t.dtype
@@ -292,7 +300,7 @@ def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts
     shape = (len(qx_a), len(qy_a), len(qz_a))
     nn_idx = torch.empty(shape, dtype=torch.int32, device=pos_t.device) if want_idx else None
     nn_pos = torch.empty(shape, dtype=torch.int32, device=pos_t.device)
-    spay = torch.empty((pos_t.shape[0], 4), dtype=torch.float32, device=pos_t.device)
+    spay = torch.empty((pos_t.shape[0], 8), dtype=torch.float32, device=pos_t.device)
     _check(load_library().vp_nn_grid_payload(
         ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()), _P(rho_t.data_ptr()) if rho_t is not None else None,
         _dtype_code(pos_t), pos_t.shape[0], qx_p, shape[0], qy_p, shape[1], qz_p, shape[2], float(lcell3),
@@ -330,7 +338,7 @@ def nn_grid_plan(np_particles, qx, qy, qz, opts: NNOpts | None = None):
     out = (_L * 10)()
     _check(load_library().vp_nn_grid_plan(int(np_particles), qx_p, len(qx_a), qy_p, len(qy_a), qz_p, len(qz_a),
                                           C.byref(opts) if opts is not None else None, out))
-    names = ("cells_x", "cells_y", "cells_z", "yb", "lb", "nyc", "bins", "row_bits", "scratch_MiB", "corner_aligned")
+    names = ("cells_x", "cells_y", "cells_z", "bucket_shift", "n_buckets", "r5", "r6", "r7", "scratch_MiB", "corner_aligned")
     return dict(zip(names, (int(v) for v in out)))
 
 
@@ -447,6 +455,18 @@ class PkPlan:
         ns = torch.empty(self.nbins, dtype=torch.int64, device=recv[0].device)
         _check(load_library().vp_pk_dist_final(self._h, rp, len(recv), _P(psum.data_ptr()), _P(ns.data_ptr()), stream_ptr()))
         return psum, ns
+
+    def close(self, group=None):
+        """Collective teardown of a plan with peer-mapped receive buffers: unmap the peers on every rank, barrier, free."""
+        if not self._h:
+            return
+        if getattr(self, "p2p", False) and self.nranks > 1:
+            import torch.distributed as dist
+            _check(load_library().vp_pk_dist_p2p_close(self._h))
+            if dist.is_initialized():
+                dist.barrier(group=group)
+        load_library().vp_pk_plan_destroy(self._h)
+        self._h = None
 
     def __del__(self):
         try:

@@ -48,6 +48,10 @@ class CudaBackend:
             self.plan.p2p_setup(group)
             self.slab_x = _lib.SlabExchangeP2P(nranks, rank, group)
 
+    def close(self, group=None):
+        """Collective: release the peer-mapped buffers in the order CUDA IPC requires (unmap everywhere, barrier, free)."""
+        self.plan.close(group)
+
     def grid_slab(self, pos, vel, rho, ax_loc, ax, lcell3, keep):
         lo, hi, open_lo, open_hi = keep
         o = _lib.NNOpts()

@@ -222,32 +222,30 @@ def test_boxfield_host_helpers_match_reference_expressions():
 
 
 def test_cell_list_plan_invariants_without_a_device():
-    """vp_nn_grid_plan is host arithmetic: the key layout (row << lb | local) must fit 32 bits, a row of cells must fit the
-    shared-memory counters of the per-row counting sort, and the 1-particle-per-node lattices must come out corner aligned --
-    for every BASELINE configuration (cfg5 cannot be run on one device) and for awkward shapes."""
+    """vp_nn_grid_plan is host arithmetic: the linear cell index must fit 32 bits, the buckets of 2^bucket_shift consecutive
+    cells must cover the grid with at most 16384 of them (the shared-memory histogram of the first pass), and the
+    1-particle-per-node lattices must come out corner aligned -- for every BASELINE configuration (cfg5 cannot be run on one
+    device) and for awkward shapes."""
     from vpower import _lib
-    kMaxBins = 33 * 1024
 
     def check(np_particles, qx, qy, qz, opts=None):
         p = _lib.nn_grid_plan(np_particles, qx, qy, qz, opts)
         gx, gy, gz = p["cells_x"], p["cells_y"], p["cells_z"]
         assert gx >= 1 and gy >= 1 and gz >= 1
-        assert p["bins"] == gz << p["yb"] and p["bins"] <= kMaxBins and p["bins"] <= 1 << p["lb"]
-        assert p["lb"] == 0 or p["bins"] > 1 << (p["lb"] - 1)                  # lb is the tight bit width
-        assert p["nyc"] == -(-gy // (1 << p["yb"]))
-        nrows = gx * p["nyc"]
-        assert nrows <= 1 << p["row_bits"] and (p["row_bits"] == 0 or nrows > 1 << (p["row_bits"] - 1))
-        assert p["row_bits"] + p["lb"] <= 32 and nrows << p["lb"] <= 1 << 32   # every key fits u32
-        assert gx * gy * gz < 2 ** 32 - 1
+        ncells = gx * gy * gz
+        assert ncells < 2 ** 32 - 1
+        assert 1 <= p["n_buckets"] <= 16384 and 0 <= p["bucket_shift"] <= 31
+        assert p["n_buckets"] == -(-ncells // (1 << p["bucket_shift"]))           # the buckets cover every cell
         return p
 
     for N, Np in ((64, 1 << 18), (256, 1 << 24), (512, 1 << 27), (1024, 1 << 30)):
         ax = np.linspace(0.5 / N, 1.0 + 0.5 / N, N)                            # library lattice
         p = check(Np, ax, ax, ax)
         assert (p["cells_x"], p["cells_y"], p["cells_z"]) == (N + 1,) * 3 and p["corner_aligned"] == 1
-        assert p["row_bits"] <= 16                                             # two 8-bit radix passes at most
+        # about 2^17 particles per bucket: the counting sort inside a bucket's window of records runs out of L2
+        assert Np <= (1 << 18) or 1 << 16 <= Np / p["n_buckets"] <= 1 << 18
     p = check(1 << 30, *(np.linspace(0.5 / 1024, 1.0 + 0.5 / 1024, 1024),) * 3)
-    assert p["yb"] == 5 and p["lb"] == 16 and p["nyc"] == 33 and p["row_bits"] == 16 and p["scratch_MiB"] < 150 * 1024
+    assert p["bucket_shift"] == 17 and p["n_buckets"] == 8217 and p["scratch_MiB"] < 150 * 1024
     # cfg5 (2048^3): one device cannot hold it; a slab of it (8 ranks) must plan fine, the whole lattice gets coarser cells
     ax5 = np.linspace(0.5 / 2048, 1.0 + 0.5 / 2048, 2048)
     o = _lib.NNOpts()
