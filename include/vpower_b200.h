@@ -224,6 +224,17 @@ int vp_slab_count(vp_ctx* ctx, const void* pos_d, int dtype, int64_t np, const d
 int vp_slab_scatter_p2p(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
                         const double* lo_h, const double* hi_h, int nranks, const int64_t* first_row_h, void* stream);
 
+/* Snapshot preamble on the device, in place (the two O(Np) host passes of the reference between reading the snapshot and
+ * gridding it):
+ *   do_shift: pos[:, c] -= min(pos[:, c])                GasParticles.shift_to_origin (vpower/interp.py:169-175),
+ *                                                         scripts/parallel_optimized.py:278-282
+ *   do_bulk : v[:, c] -= sum(m * v[:, c]) / sum(m)       GasParticles.remove_bulk_velocity (vpower/interp.py:178-182),
+ *                                                         scripts/parallel_optimized.py:284-288
+ * pos_d, vel_d [np,3], mass_d [np] of `dtype`.  The minimum is exact; the mass-weighted sums are accumulated in f64 (numpy
+ * accumulates pairwise in the array dtype).  min_h[3] / bulk_h[3] (may be NULL) receive what was subtracted.  Syncs. */
+int vp_snapshot_preamble(vp_ctx* ctx, void* pos_d, void* vel_d, const void* mass_d, int dtype, int64_t np, int do_shift,
+                         int do_bulk, double* min_h, double* bulk_h, void* stream);
+
 /* Test/diagnostic entry points */
 /* In-place 3-D r2c transform only.  Output layout: [N][N][N/2] complex64 where entry (x,y,0) packs
  * (Re F(x,y,0), Re F_zNyquist-line ...) -- see DESIGN.md "half-spectrum layout"; use

@@ -143,7 +143,7 @@ int vp_sort_pairs_range(vp_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, 
                         cudaStream_t st);
 
 // exclusive prefix sum of m u32 values in place (three kernels); `sums` holds ceil(m/4096)+1 words of scratch
-int vp_scan_exclusive_u32(vp_ctx* ctx, uint32_t* a, int64_t m, uint32_t* sums, cudaStream_t st);
+int vp_scan_exclusive_u32(vp_ctx* ctx, uint32_t* a, int64_t m, uint32_t* sums, cudaStream_t st, const char* stage_name);
 // planes from (v', m) records addressed through nn_pos: record i at srec + (stride*i + offset) float4
 int vp_fields_from_records(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* srec_d, int stride, int offset,
                            float* const v_d[3], float* const p_d[3], float* e_d, float* m_d, cudaStream_t st);

@@ -23,6 +23,10 @@ struct vp_pk_plan {
   double* thr = nullptr;      // nbins+1 thresholds on the squared magnitude
   float2* plane0 = nullptr;   // [3][N][N] x-pass output of the kz=0 column
   float inv_kf = 0.f;
+  double e0 = 0.0, inv_de = 1.0;                 // linear estimate of the shell of |k|: (|k| - e0) * inv_de
+  unsigned long long* ns_tiles = nullptr;        // mode counts of the x-pass tiles (geometry only; filled on first use)
+  bool ns_valid = false;
+  int ns_kz_offset = 0, ns_NZ = 0;
   // slab decomposition (one process per GPU): this rank owns x planes [rank*N/nranks, ...) before the exchange
   // and half-spectrum columns kz in [rank*kzc, (rank+1)*kzc) after it
   int nranks = 1, rank = 0;
@@ -36,15 +40,6 @@ struct vp_pk_plan {
 };
 
 namespace {
-
-// 8-byte asynchronous global -> shared copy (LDGSTS); each thread only ever reads back what it copied itself,
-// so its own wait_group is the only synchronisation the prefetch needs.
-__device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* gsrc) {
-  unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------ z pass: N reals -> N/2 packed complex
 template <int R2, int R3>
@@ -83,14 +78,19 @@ __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const f
 }
 
 // ------------------------------------------------------------------ y pass: lines strided by NZ, C columns per CTA
-// Destination of the y pass.  base[d] + (xoff + x_local)*N*kzc + ky*kzc + (kz - d*kzc):
-//   single GPU, in place      : base[0] = the field itself, xoff = 0, kzc = N/2
-//   NCCL exchange             : base[d] = send buffer block d ([dest][x_local][ky][kzc]), xoff = 0
-//   peer-to-peer (fused)      : base[d] = rank d's receive buffer mapped through CUDA IPC, xoff = rank*N/nranks --
+// Destination of the y pass, two layouts of the half spectrum:
+//   row-major  (tile_major = 0):  base[d] + (xoff + x_local)*N*kzc + ky*kzc + (kz - d*kzc)
+//   tile-major (tile_major = 1):  base[d] + (((xoff + x_local)*(kzc/C) + zt_local)*N + ky)*C + c -- the C columns of a tile stay
+//       together, so everything one CTA stores for one x is ONE contiguous block of N*C*8 bytes (a warp store = 256
+//       contiguous bytes instead of four 64-byte pieces): the form used when the store crosses NVLink.
+//   single GPU, in place      : base[0] = the field itself, xoff = 0, kzc = N/2, row-major (a CTA writes where it read)
+//   NCCL exchange             : base[d] = send buffer block d ([dest][x_local][ky][kzc]), xoff = 0, row-major
+//   peer-to-peer (fused)      : base[d] = rank d's receive buffer mapped through CUDA IPC, xoff = rank*N/nranks, tile-major --
 //                               the tile is stored over NVLink where the x pass of rank d will read it
 struct YDest {
   float2* base[16];
   int xoff;
+  int tile_major;
 };
 
 template <int R2, int R3, int C>
@@ -108,152 +108,145 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * NZ];
   F::run(v, t, sm + c, tw);
   const int kz0 = zt * C, d = kz0 / kzc;
-  float2* ob = dst.base[d] + (size_t(dst.xoff) + x) * L * kzc + (kz0 - d * kzc) + c;
+  float2* ob;
+  int sky;
+  if (dst.tile_major) {
+    ob = dst.base[d] + ((size_t(dst.xoff) + x) * (kzc / C) + (kz0 - d * kzc) / C) * (size_t(L) * C) + c;
+    sky = C;
+  } else {
+    ob = dst.base[d] + (size_t(dst.xoff) + x) * L * kzc + (kz0 - d * kzc) + c;
+    sky = kzc;
+  }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * kzc] = v[j];
+  for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * sky] = v[j];
 }
 
-// ------------------------------------------------------------------ x pass fused with |F|^2 and shell binning
+// ------------------------------------------------------------------ x pass with |F|^2, then shell binning
 struct FieldSet {
   float2* f[3];
   int n;
+  int tile_major;   // layout of the half spectrum the x pass reads (see YDest)
 };
 
-// Binning inside the x pass: the |F|^2 tile [C columns][L rows] sits in shared memory; rows kx and -kx are folded.
-// For a column the shell index is monotone in |kx|, so the rows of shell b form one contiguous segment
-// [r0(b), r0(b+1)).  Work item = (shell b, column c): lanes of a group of C consecutive threads take the C columns
-// of one shell, sum their segments, and reduce across the group with shuffles; the group leader keeps the running
-// f64 sum and the mode count of that shell in registers for the whole kernel.  No atomics until the final flush.
-constexpr int kMaxSlots = 8;  // shells per group leader
+// x pass of 1..3 components of one (ky, kz-tile): the sum over components of |F|^2 is collected in a shared-memory tile
+// [C columns][L rows] and written out with rows kx and -kx folded together, tile-major and column-major inside the tile:
+//   P[((ky * tiles_z + zt) * C + c) * NRP + r],  r = 0 .. L/2  (NRP = L/2+1 rounded up to a multiple of 32; padding unwritten)
+// so that the binning kernel reads 32 consecutive rows of ONE column per warp -- along a column the shell index never
+// decreases, which is what its segmented reduction relies on.  The transform itself is never written back.
+template <int L>
+__host__ __device__ constexpr int nrp_of() { return ((L / 2 + 1) + 31) / 32 * 32; }
 
-// smallest row r in [0, nr] with  wrow[r] + zc >= thr  (nr = number of rows when none qualifies)
-__device__ __forceinline__ int first_row_at_or_above(const double* wrow, int nr, double zc, double thr, double base2,
-                                                     float inv_kf) {
-  double d = thr - zc - base2;
-  int r = 0;
-  if (d > 0.0) {
-    float rf = sqrtf(float(d)) * inv_kf;
-    r = rf >= float(nr) ? nr : int(rf);
-  }
-  while (r > 0 && __dadd_rn(wrow[r - 1], zc) >= thr) --r;
-  while (r < nr && __dadd_rn(wrow[r], zc) < thr) ++r;
-  return r;
-}
-
-template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
-__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 256 ? 2 : 1)) k_fft_x_bin(FieldSet fs, int NZ, const float2* __restrict__ tw,
-                                                         const double* __restrict__ kk2, const double* __restrict__ thr_g,
-                                                         int nbins, float inv_kf, float2* __restrict__ plane0, int kz_offset,
-                                                         double* __restrict__ psum_g, unsigned long long* __restrict__ cnt_g) {
+template <int R2, int R3, int C>
+__global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_x_pow(FieldSet fs, int NZ, const float2* __restrict__ tw,
+                                                                                       float2* __restrict__ plane0, int kz_offset,
+                                                                                       float* __restrict__ P) {
   using F = LineFFT<R2, R3, C>;
-  constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1;
-  constexpr int NG = NT / C;                                       // shell groups per sweep
-  extern __shared__ float2 sm[];                                   // exchange area, later the |F|^2 tile
-  float* pt = reinterpret_cast<float*>(sm);                        // [C][PP]
-  double* wrow = reinterpret_cast<double*>(sm + XS);               // [NR]   kx^2 + ky^2
-  double* kz2 = wrow + NR;                                         // [C]
-  double* thr = kz2 + C;                                           // [nbins+1]
-  static_assert(size_t(C) * PP * 4 <= size_t(XS) * 8, "P tile must fit in the exchange area");
-  static_assert(C <= 32 && (C & (C - 1)) == 0, "a shell group must sit inside one warp");
-
+  constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1, NRP = nrp_of<L>();
+  extern __shared__ float2 sm[];                                   // exchange area
+  float* pt = reinterpret_cast<float*>(sm + XS);                   // [C][PP] sum over components of |F|^2
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
   const int tiles_z = NZ / C;
-  const int ntiles = L * tiles_z;
+  const int ky = blockIdx.x / tiles_z, zt = blockIdx.x % tiles_z;
   const size_t xstride = size_t(L) * NZ;
-  float2* pre = reinterpret_cast<float2*>(thr + nbins + 1 + ((nbins + 1) & 1));   // [16][NT] prefetch slots (thread private)
-
-  for (int i = tid; i <= nbins; i += NT) thr[i] = thr_g[i];
-  double acc[SLOTS];
-  unsigned cnt[SLOTS];   // per-CTA mode counts stay far below 2^32 (<= tiles per CTA * 2*NR*C)
+  for (int comp = 0; comp < fs.n; ++comp) {
+    const float2* base = fs.f[comp] + (fs.tile_major ? (size_t(zt) * L + ky) * C : size_t(ky) * NZ + size_t(zt) * C) + c;
+    float2 v[16];
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s) { acc[s] = 0.0; cnt[s] = 0u; }
-
-  // software pipeline over the sequence (tile, component): the next item's 16 strided elements are copied
-  // global -> shared with cp.async while the current item is transformed and binned
-  auto prefetch = [&](int tile, int comp) {
-    if (!PREFETCH) return;
-    const int ky = tile / tiles_z, zt = tile % tiles_z;
-    const float2* base = fs.f[comp] + size_t(ky) * NZ + zt * C + c;
+    for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+    if (comp) __syncthreads();  // previous component's last exchange reads are done
+    F::run(v, t, sm + c, tw);
+    if (kz_offset + zt * C + c == 0) {
+      float2* pl = plane0 + (size_t(comp) * L + ky) * L;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) cp_async8(pre + j * NT + tid, base + size_t(j * T + t) * xstride);
-    cp_async_commit();
-  };
-  if (int(blockIdx.x) < ntiles) prefetch(blockIdx.x, 0);
-
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int ky = tile / tiles_z, zt = tile % tiles_z;
-    float p[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) p[j] = 0.f;
-    for (int comp = 0; comp < fs.n; ++comp) {
-      float2 v[16];
-      if (PREFETCH) {
-        cp_async_wait_all();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = pre[j * NT + tid];
-      } else {
-        const float2* base = fs.f[comp] + size_t(ky) * NZ + zt * C + c;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
-      }
-      if (comp + 1 < fs.n) prefetch(tile, comp + 1);
-      else if (tile + int(gridDim.x) < ntiles) prefetch(tile + gridDim.x, 0);
-      __syncthreads();  // previous user of the exchange area is done
-      F::run(v, t, sm + c, tw);
-      if (kz_offset + zt * C + c == 0) {
-        float2* pl = plane0 + (size_t(comp) * L + ky) * L;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pl[F::kout(j, t)] = v[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) p[j] += v[j].x * v[j].x + v[j].y * v[j].y;
+      for (int j = 0; j < 16; ++j) pl[F::kout(j, t)] = v[j];
     }
-    __syncthreads();
+    float* col = pt + c * PP;
+    if (comp == 0) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) pt[c * PP + F::kout(j, t)] = p[j];
-    const double ky2 = kk2[ky];
-    for (int r = tid; r < NR; r += NT) wrow[r] = __dadd_rn(kk2[r], ky2);
-    if (tid < C) kz2[tid] = kk2[kz_offset + zt * C + tid];
-    __syncthreads();
-
-    const double zc = kz2[c];
-    const double smin = __dadd_rn(wrow[0], zc), smax = __dadd_rn(wrow[NR - 1], zc);
-    const bool col_on = (kz_offset + zt * C + c) != 0;   // the packed kz=0 column is binned by k_plane_bin
-    const float* col = pt + c * PP;
+      for (int j = 0; j < 16; ++j) col[F::kout(j, t)] = v[j].x * v[j].x + v[j].y * v[j].y;
+    } else {
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int b = t + s * NG;                   // shell of this group in sweep s (uniform across the group)
-      float a = 0.f;
-      unsigned n = 0;
-      if (b < nbins && col_on) {
-        const double tlo = thr[b], thi = thr[b + 1];
-        if (smin < thi && smax >= tlo) {
-          const int r0 = first_row_at_or_above(wrow, NR, zc, tlo, ky2, inv_kf);
-          const int r1 = first_row_at_or_above(wrow, NR, zc, thi, ky2, inv_kf);
-          for (int r = r0; r < r1; ++r) {
-            float q = col[r];
-            if (r > 0 && r < L / 2) { q += col[L - r]; n += 2; } else n += 1;
-            a += q;
-          }
-        }
-      }
-#pragma unroll
-      for (int o = C / 2; o; o >>= 1) {            // all lanes take part (full-warp shuffles)
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        n += __shfl_xor_sync(0xffffffffu, n, o);
-      }
-      acc[s] += double(a);
-      cnt[s] += n;
+      for (int j = 0; j < 16; ++j) col[F::kout(j, t)] += v[j].x * v[j].x + v[j].y * v[j].y;   // same thread, same slots
     }
   }
-  if (c == 0) {
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int b = t + s * NG;
-      if (b < nbins && cnt[s]) {
-        atomicAdd(psum_g + b, 2.0 * acc[s]);   // Hermitian partner of every kz in [1, N/2-1]
-        atomicAdd(cnt_g + b, 2ull * (unsigned long long)cnt[s]);
+  __syncthreads();
+  float* out = P + size_t(blockIdx.x) * (C * NRP);
+  for (int i = tid; i < C * NRP; i += NT) {
+    const int cc = i / NRP, r = i - cc * NRP;
+    if (r < NR) {
+      float q = pt[cc * PP + r];
+      if (r > 0 && r < L / 2) q += pt[cc * PP + L - r];
+      out[i] = q;
+    }
+  }
+}
+
+// Shell binning of the folded power tiles.  A warp takes 32 consecutive rows of one column: |k|^2 = (kx^2 + ky^2) + kz^2 in
+// f64 with numpy's association, the shell from a float estimate corrected against the f64 thresholds (identical decisions
+// to numpy.histogram on sqrt(s), see sq_threshold), then a segmented warp reduction over runs of equal shell and ONE
+// read-modify-write per run into the warp's private f64 accumulators in shared memory -- no atomics until the final flush.
+// COUNT: accumulate the number of modes (1 or 2 per folded row) instead of the power -- geometry only, done once per plan.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_bin_tiles(const float* __restrict__ P, int L, int C, int NRP, int tiles_z, int ntiles,
+                                                   const double* __restrict__ kk2, const double* __restrict__ thr_g, int nbins,
+                                                   double e0, double inv_de, int kz_offset, double* __restrict__ psum_g,
+                                                   unsigned long long* __restrict__ cnt_g) {
+  extern __shared__ double bsm[];
+  double* thr = bsm;                                   // [nbins + 1]
+  const int nwarps = blockDim.x >> 5;
+  double* acc = bsm + (nbins + 2);                     // [nwarps][nbins]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i <= nbins; i += blockDim.x) thr[i] = thr_g[i];
+  for (int i = tid; i < nwarps * nbins; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  double* my = acc + size_t(w) * nbins;
+  const int NR = L / 2 + 1;
+  const int chunks_per_col = NRP / 32;
+  const uint32_t ncols = uint32_t(ntiles) * uint32_t(C);
+  // a warp takes whole columns (tile, c): the column geometry is decoded once, then its rows in chunks of 32
+  for (uint32_t colid = blockIdx.x * nwarps + w; colid < ncols; colid += gridDim.x * nwarps) {
+    const uint32_t tile = colid / uint32_t(C), c = colid - tile * uint32_t(C);
+    const uint32_t ky = tile / uint32_t(tiles_z), zt = tile - ky * uint32_t(tiles_z);
+    const int kz = kz_offset + int(zt) * C + int(c);
+    if (kz == 0) continue;                               // the packed kz = 0 column is binned by k_plane_bin
+    const double kyz2a = __ldg(kk2 + ky), kz2 = __ldg(kk2 + kz);
+    const float* col = COUNT ? nullptr : P + size_t(colid) * NRP;
+    for (int rc = 0; rc < chunks_per_col; ++rc) {
+      const int r = rc * 32 + lane;
+      int b = -1;
+      float v = 0.f;
+      if (r < NR) {
+        const double s = __dadd_rn(__dadd_rn(__ldg(kk2 + r), kyz2a), kz2);
+        int e = int((sqrtf(float(s)) - float(e0)) * float(inv_de));   // estimate of the shell; corrected below against the exact thresholds
+        e = e < 0 ? 0 : (e > nbins ? nbins : e);
+        while (e < nbins + 1 && thr[e] <= s) ++e;        // e = number of thresholds <= s ...
+        while (e > 0 && thr[e - 1] > s) --e;
+        b = e - 1;                                        // ... minus one: -1 below the first edge, nbins beyond the last
+        if (b >= nbins) b = -1;
+        if (b >= 0) v = COUNT ? ((r > 0 && r < L / 2) ? 2.f : 1.f) : col[r];
       }
+      // runs of equal shell (never decreasing along a column): inclusive segmented scan, the last lane of a run holds its sum
+      const int prev = __shfl_up_sync(0xffffffffu, b, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != b);
+      const int seg0 = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float tv = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane - d >= seg0) v += tv;
+      }
+      const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+      if (tail && b >= 0) my[b] += double(v);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nbins; i += blockDim.x) {
+    double a = 0.0;
+    for (int q = 0; q < nwarps; ++q) a += acc[size_t(q) * nbins + i];
+    if (a != 0.0) {
+      // Hermitian partner of every kz in [1, N/2-1]
+      if (COUNT) atomicAdd(cnt_g + i, 2ull * (unsigned long long)(a + 0.5));
+      else atomicAdd(psum_g + i, 2.0 * a);
     }
   }
 }
@@ -410,45 +403,63 @@ int launch_y(const float2* data, const YDest& dst, int N, int nx, int kzc, const
   return VP_OK;
 }
 
-template <int R2, int R3, int C, int SLOTS, bool PREFETCH>
-int launch_x_bin_sp(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, size_t smem, double* psum, unsigned long long* cnt,
-                    cudaStream_t st) {
-  using F = LineFFT<R2, R3, C>;
-  constexpr int NT = F::T * C;
-  auto kern = k_fft_x_bin<R2, R3, C, SLOTS, PREFETCH>;
-  VP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int occ = 1;
-  VP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-  if (occ < 1) occ = 1;
-  VP_REQUIRE(NZ % C == 0, "fft x pass: %d columns is not a multiple of the tile width %d", NZ, C);
-  int ntiles = N * (NZ / C);
-  int grid = pl->ctx->sm_count * occ;
-  if (grid > ntiles) grid = ntiles;
-  vp_stage stage(pl->ctx, "k4c_fft_x_bin", st, 1, 8.0 * double(N) * N * NZ * fs.n);   // 8 B/mode read, nothing written
-  kern<<<grid, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->kk2, pl->thr, pl->nbins, pl->inv_kf, pl->plane0, kz_offset, psum, cnt);
-  VP_CHECK_LAUNCH();
-  return VP_OK;
-}
-
-template <int R2, int R3, int C, int SLOTS>
-int launch_x_bin_s(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
-  using F = LineFFT<R2, R3, C>;
-  constexpr int NT = F::T * C;
-  const size_t base = size_t(xsize<F::L, C>()) * sizeof(float2) +
-                      (size_t(F::L / 2 + 1) + C + pl->nbins + 1 + ((pl->nbins + 1) & 1)) * sizeof(double);
-  const size_t pre = size_t(16) * NT * sizeof(float2);
-  if (base + pre <= size_t(200) * 1024) return launch_x_bin_sp<R2, R3, C, SLOTS, true>(fs, N, NZ, kz_offset, pl, base + pre, psum, cnt, st);
-  return launch_x_bin_sp<R2, R3, C, SLOTS, false>(fs, N, NZ, kz_offset, pl, base, psum, cnt, st);
-}
-
 template <int R2, int R3, int C>
-int launch_x_bin(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+int launch_x_pow(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   using F = LineFFT<R2, R3, C>;
-  constexpr int NG = F::T;   // shell groups per sweep
-  const int need = (pl->nbins + NG - 1) / NG;
-  VP_REQUIRE(need <= 4 * kMaxSlots, "vp_pk_fields: nbins=%d exceeds %d for N=%d", pl->nbins, 4 * kMaxSlots * NG, N);
-  if (need <= kMaxSlots) return launch_x_bin_s<R2, R3, C, kMaxSlots>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-  return launch_x_bin_s<R2, R3, C, 4 * kMaxSlots>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+  constexpr int NT = F::T * C, NRP = nrp_of<F::L>();
+  vp_ctx* ctx = pl->ctx;
+  VP_REQUIRE(NZ % C == 0, "fft x pass: %d columns is not a multiple of the tile width %d", NZ, C);
+  const int tiles_z = NZ / C, ntiles = N * tiles_z;
+  const size_t pbytes = size_t(ntiles) * C * NRP * sizeof(float);
+  vp_arena_scope scope(ctx);
+  VP_TRY(vp_arena_reserve(ctx, pbytes + 1024));
+  float* P = static_cast<float*>(vp_arena_alloc(ctx, pbytes));
+  VP_REQUIRE(P, "fft x pass: arena carve failed");
+  const size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2) + size_t(C) * (F::L + 4) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x_pow<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  {
+    // 8 B/mode read per component, the folded power tile written (4 B per pair of modes)
+    vp_stage stage(ctx, "k4c_fft_x_pow", st, 1, 8.0 * double(N) * N * NZ * fs.n + 4.0 * double(N) * NZ * (N / 2 + 1));
+    k_fft_x_pow<R2, R3, C><<<ntiles, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->plane0, kz_offset, P);
+    VP_CHECK_LAUNCH();
+  }
+  // binning: per-warp f64 accumulators in shared memory
+  const int nbins = pl->nbins;
+  const int nwarps = nbins <= 2048 ? 8 : 4;
+  const size_t bsmem = (size_t(nbins) + 2 + size_t(nwarps) * nbins) * sizeof(double);
+  VP_REQUIRE(bsmem <= size_t(200) * 1024, "vp_pk_fields: nbins=%d is more than the binning kernel holds in shared memory", nbins);
+  static bool battr = false;
+  if (!battr) {
+    VP_CUDA(cudaFuncSetAttribute(k_bin_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(cudaFuncSetAttribute(k_bin_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    battr = true;
+  }
+  int per_sm = int((size_t(220) * 1024) / (bsmem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const long long ncols = (long long)ntiles * C;
+  long long grid = (long long)ctx->sm_count * per_sm;
+  if (grid > (ncols + nwarps - 1) / nwarps) grid = (ncols + nwarps - 1) / nwarps;
+  if (!pl->ns_valid || pl->ns_kz_offset != kz_offset || pl->ns_NZ != NZ) {
+    // mode counts of the tiles: geometry only -- once per plan
+    if (!pl->ns_tiles) VP_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl->ns_tiles), sizeof(unsigned long long) * nbins));
+    VP_CUDA(cudaMemsetAsync(pl->ns_tiles, 0, sizeof(unsigned long long) * nbins, st));
+    vp_stage stage(ctx, "k5_bin_counts", st, 1);
+    k_bin_tiles<true><<<unsigned(grid), nwarps * 32, bsmem, st>>>(nullptr, N, C, NRP, tiles_z, ntiles, pl->kk2, pl->thr, nbins, pl->e0,
+                                                                pl->inv_de, kz_offset, nullptr, pl->ns_tiles);
+    VP_CHECK_LAUNCH();
+    pl->ns_valid = true;
+    pl->ns_kz_offset = kz_offset;
+    pl->ns_NZ = NZ;
+  }
+  VP_CUDA(cudaMemcpyAsync(cnt, pl->ns_tiles, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToDevice, st));
+  {
+    vp_stage stage(ctx, "k5_bin_tiles", st, 1, 4.0 * double(N) * NZ * (N / 2 + 1));
+    k_bin_tiles<false><<<unsigned(grid), nwarps * 32, bsmem, st>>>(P, N, C, NRP, tiles_z, ntiles, pl->kk2, pl->thr, nbins, pl->e0,
+                                                                 pl->inv_de, kz_offset, psum, nullptr);
+    VP_CHECK_LAUNCH();
+  }
+  return VP_OK;
 }
 
 int run_z(float* d, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
@@ -480,16 +491,19 @@ YDest ydest_blocks(float2* out, int nranks, int nx, int N, int kzc) {
   YDest d;
   for (int r = 0; r < 16; ++r) d.base[r] = r < nranks ? out + size_t(r) * nx * N * kzc : nullptr;
   d.xoff = 0;
+  d.tile_major = 0;
   return d;
 }
-int run_x_bin(FieldSet fs, int N, int NZ, int kz_offset, const vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
+// x pass + |F|^2 (k_fft_x_pow) and shell binning (k_bin_tiles).  psum is accumulated into (the caller zeroes it); cnt is
+// overwritten with the mode counts of this rank's tiles.
+int run_x_bin(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_x_bin<4, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 128: return launch_x_bin<8, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 256: return launch_x_bin<16, 1, 16>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 512: return launch_x_bin<16, 2, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 1024: return launch_x_bin<16, 4, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 2048: return launch_x_bin<16, 8, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 64: return launch_x_pow<4, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 128: return launch_x_pow<8, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 256: return launch_x_pow<16, 1, 16>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 512: return launch_x_pow<16, 2, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 1024: return launch_x_pow<16, 4, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 2048: return launch_x_pow<16, 8, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
   }
   vp_set_error("fft x pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
@@ -577,6 +591,8 @@ extern "C" int vp_pk_plan_create(vp_ctx* ctx, int N, const double* k_h, const do
   for (int j = 0; j < nbins; ++j) thr[j] = sq_threshold(edges_h[j], false);
   thr[nbins] = sq_threshold(edges_h[nbins], true);
   p->inv_kf = (N > 1 && fabs(k_h[1]) > 0) ? float(1.0 / fabs(k_h[1])) : 1.f;
+  p->e0 = edges_h[0];
+  p->inv_de = double(nbins) / (edges_h[nbins] - edges_h[0]);
   std::vector<float2> twf(N), twh(N / 2 > 0 ? N / 2 : 1);
   for (int m = 0; m < N; ++m) twf[m] = make_float2(float(cos(2.0 * M_PI * m / N)), float(-sin(2.0 * M_PI * m / N)));
   for (int m = 0; m < N / 2; ++m)
@@ -604,6 +620,7 @@ extern "C" int vp_pk_plan_destroy(vp_pk_plan* p) {
   if (p->kk2) cudaFree(p->kk2);
   if (p->thr) cudaFree(p->thr);
   if (p->plane0) cudaFree(p->plane0);
+  if (p->ns_tiles) cudaFree(p->ns_tiles);
   for (int c = 0; c < 3; ++c) {
     if (p->peer_open)
       for (int d = 0; d < p->nranks; ++d)
@@ -615,7 +632,7 @@ extern "C" int vp_pk_plan_destroy(vp_pk_plan* p) {
 }
 
 size_t vp_pk_fields_scratch_bytes(const vp_pk_plan* pl) {
-  if (pl->pow2) return 0;
+  if (pl->pow2) return vp_align256(size_t(pl->N) * (pl->N / 2) * (((pl->N / 2 + 1) + 31) / 32 * 32) * sizeof(float)) + 8192;   // folded power tiles
   const size_t n3 = size_t(pl->N) * pl->N * pl->N;
   return vp_align256(n3 * sizeof(float2)) + vp_align256(n3 * sizeof(double)) + vp_align256(sizeof(double2) * pl->N) + 16384;
 }
@@ -672,6 +689,7 @@ extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, do
   VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
   FieldSet fs;
   fs.n = ncomp;
+  fs.tile_major = 0;
   for (int c = 0; c < 3; ++c) fs.f[c] = nullptr;
   for (int c = 0; c < ncomp; ++c) {
     VP_REQUIRE(field_d[c], "vp_pk_fields: null field %d", c);
@@ -723,7 +741,11 @@ extern "C" int vp_pk_dist_local(vp_pk_plan* pl, float* const* field_d, int ncomp
   return VP_OK;
 }
 
+static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int tile_major, double* psum_d, uint64_t* nsample_d, void* stream);
 extern "C" int vp_pk_dist_final(vp_pk_plan* pl, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
+  return dist_final_impl(pl, recv_d, ncomp, 0, psum_d, nsample_d, stream);
+}
+static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int tile_major, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && recv_d && psum_d && nsample_d && ncomp >= 1 && ncomp <= 3, "vp_pk_dist_final: bad argument");
   vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(pl->pow2, "vp_pk_dist_final: N=%d has no slab path", pl->N);
@@ -734,6 +756,7 @@ extern "C" int vp_pk_dist_final(vp_pk_plan* pl, float* const* recv_d, int ncomp,
   VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
   FieldSet fs;
   fs.n = ncomp;
+  fs.tile_major = tile_major;
   for (int c = 0; c < 3; ++c) fs.f[c] = c < ncomp ? reinterpret_cast<float2*>(recv_d[c]) : nullptr;
   VP_TRY(run_x_bin(fs, N, pl->kzc, pl->rank * pl->kzc, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
   if (pl->rank == 0) {   // the packed kz=0 column (planes kz=0 and kz=N/2) lives on rank 0
@@ -810,6 +833,7 @@ extern "C" int vp_pk_dist_local_p2p(vp_pk_plan* pl, float* const* field_d, int n
     YDest dst;
     for (int d = 0; d < 16; ++d) dst.base[d] = d < pl->nranks ? pl->peer[c][d] : nullptr;
     dst.xoff = pl->rank * nx;
+    dst.tile_major = 1;
     VP_TRY(run_y(reinterpret_cast<const float2*>(field_d[c]), dst, N, nx, pl->kzc, pl, st));
   }
   return VP_OK;
@@ -818,7 +842,7 @@ extern "C" int vp_pk_dist_local_p2p(vp_pk_plan* pl, float* const* field_d, int n
 extern "C" int vp_pk_dist_final_p2p(vp_pk_plan* pl, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && ncomp >= 1 && ncomp <= pl->p2p_ncomp, "vp_pk_dist_final_p2p: bad argument");
   float* r[3] = {reinterpret_cast<float*>(pl->recv[0]), reinterpret_cast<float*>(pl->recv[1]), reinterpret_cast<float*>(pl->recv[2])};
-  return vp_pk_dist_final(pl, r, ncomp, psum_d, nsample_d, stream);
+  return dist_final_impl(pl, r, ncomp, 1, psum_d, nsample_d, stream);   // the peer stores arrive tile-major (see YDest)
 }
 
 extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) {

@@ -46,8 +46,8 @@ constexpr uint32_t kFixMax = (1u << kFixBits) - 1u;
 constexpr uint32_t kFarBit = 0x80000000u;   // idx bit 31: the particle lies outside the cell grid (clamped into an end cell)
 struct __align__(16) RecA { uint32_t u0, u1, cell, idx; };
 struct __align__(32) Rec32 { RecA a; float4 b; };
-// Sorted record (search format), one per particle in cell order: float4 a = (ux, uy, uz32, idx bits) [+ float4 b = (v'x, v'y,
-// v'z, m) with a payload]: ux, uy = offset from the low corner of the particle's cell; uz32 = offset from the low corner of
+// Sorted records (search format), one per particle in cell order, two arrays: spos float4 = (ux, uy, uz32, idx bits) and, with a
+// payload, spay float4 = (v'x, v'y, v'z, m): ux, uy = offset from the low corner of the particle's cell; uz32 = offset from the low corner of
 // the aligned 32-cell z block the cell lies in (cz & ~31) -- a brick of the search kernel spans exactly one such block
 // plus one cell, so staging re-bases z with one add.  Every consumer knows the cell (it walks the cell table).
 typedef float4 rec_t;
@@ -86,39 +86,55 @@ __device__ __forceinline__ bool load_pos(const T* __restrict__ pos, const Grid& 
   return !(g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi))));
 }
 
+// Bucket pass.  Particles are taken in TILES of kBinTile consecutive particles; tile t appends to SUB-STREAM t % kSub of each
+// bucket (kSub independent append cursors per bucket keep the per-address atomic rate low; the sub-streams of a bucket are
+// laid out one after the other, so downstream a bucket is still one contiguous run of records).
+// Part 1 (k_bin_hist): particles per (bucket, sub-stream) -- persistent CTAs, shared-memory counters, one flush per CTA.
+constexpr int kBinTile = 4096;
+constexpr int kSub = 8;
 template <typename T>
-__global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ hist_g) {
-  extern __shared__ uint32_t sh_hist[];
-  for (uint32_t b = threadIdx.x; b < g.nb; b += 256) sh_hist[b] = 0u;
+__global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ hist_g,
+                                                   uint32_t tile0) {
+  extern __shared__ uint32_t sh_hist[];         // [nb][kSub]
+  const uint32_t nh = g.nb * kSub;
+  for (uint32_t b = threadIdx.x; b < nh; b += 256) sh_hist[b] = 0u;
   __syncthreads();
-  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < np; i += int64_t(gridDim.x) * 256) {
-    double x, y, z;
-    if (!load_pos(pos, g, i, x, y, z)) continue;
-    uint32_t fx, fy, fz;
-    bool far = false;
-    const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
-              cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
-    const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
-    atomicAdd(&sh_hist[lin >> g.bshift], 1u);
+  const int64_t ntiles = (np + kBinTile - 1) / kBinTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t sub = uint32_t((tile0 + tile) % kSub);
+    const int64_t base = tile * kBinTile;
+#pragma unroll 4
+    for (int r = 0; r < kBinTile / 256; ++r) {
+      const int64_t i = base + r * 256 + threadIdx.x;
+      if (i >= np) break;
+      double x, y, z;
+      if (!load_pos(pos, g, i, x, y, z)) continue;
+      uint32_t fx, fy, fz;
+      bool far = false;
+      const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+                cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+      const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+      atomicAdd(&sh_hist[(lin >> g.bshift) * kSub + sub], 1u);
+    }
   }
   __syncthreads();
-  for (uint32_t b = threadIdx.x; b < g.nb; b += 256) {
+  for (uint32_t b = threadIdx.x; b < nh; b += 256) {
     const uint32_t c = sh_hist[b];
     if (c) atomicAdd(hist_g + b, c);
   }
 }
 
-// exclusive prefix of the bucket histogram -> append cursors; the total is the number of kept particles.  One CTA.
-__global__ void __launch_bounds__(1024) k_bin_offsets(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t nb,
-                                                          vp_nn_stats_dev* __restrict__ stats) {
+// exclusive prefix of the (bucket, sub-stream) histogram -> append cursors; the total is the number of kept particles.  One CTA.
+__global__ void __launch_bounds__(1024) k_bin_offsets(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t n,
+                                                       vp_nn_stats_dev* __restrict__ stats) {
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) carry_s = 0u;
   __syncthreads();
-  for (uint32_t base = 0; base < nb; base += 1024) {
+  for (uint32_t base = 0; base < n; base += 1024) {
     const uint32_t b = base + tid;
-    const uint32_t v = b < nb ? hist[b] : 0u;
+    const uint32_t v = b < n ? hist[b] : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -128,18 +144,18 @@ __global__ void __launch_bounds__(1024) k_bin_offsets(const uint32_t* __restrict
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
     if (w == 0) {
-      const uint32_t s = wsum[lane];
-      uint32_t is = s;
+      const uint32_t sv = wsum[lane];
+      uint32_t is = sv;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, is, o);
         if (lane >= o) is += t;
       }
-      wsum[lane] = is - s;
+      wsum[lane] = is - sv;
     }
     __syncthreads();
     const uint32_t carry = carry_s;
-    if (b < nb) cursor[b] = carry + wsum[w] + incl - v;
+    if (b < n) cursor[b] = carry + wsum[w] + incl - v;
     __syncthreads();
     if (tid == 1023) carry_s = carry + wsum[31] + incl;
     __syncthreads();
@@ -157,36 +173,62 @@ struct PayloadIn {
 // One thread per particle: cell + in-cell offset in f64, the record appended to the particle's bucket.
 //   a = (21-bit offsets x|y|z, linear cell, particle index [| far flag])     b = (vx', vy', vz', m)  [only with a payload]
 // with v' = (rho*v)/rho and m = rho*Lcell^3 evaluated in the input dtype (interp.py:199-213,272-273).
+// Part 2 (k_bin_scatter): one CTA of 1024 threads per tile, four particles per thread held in registers.  The tile's
+// particles are ranked per bucket with shared-memory atomics, every touched bucket claims ONE contiguous run of slots from
+// its sub-stream cursor, and the records go straight from registers to their slots: all records of a run are written
+// within the same few microseconds, and temporally adjacent tiles append adjacent runs, so L2 assembles whole lines.
 template <typename T, bool PAY>
-__global__ void __launch_bounds__(256) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
-                                                         uint32_t* __restrict__ cursor, void* __restrict__ rec1) {
+__global__ void __launch_bounds__(1024) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
+                                                       uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
   // pos / pin.vel / pin.rho point at particle i0 (a chunk); the stored index is global (i0 + local)
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= np) return;
-  double x, y, z;
-  if (!load_pos(pos, g, i, x, y, z)) return;
-  uint32_t fx, fy, fz;
-  bool far = false;
-  const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
-            cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
-  const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
-  const uint32_t dst = atomicAdd(cursor + (lin >> g.bshift), 1u);
-  const unsigned long long w = (unsigned long long)fx | ((unsigned long long)fy << kFixBits) | ((unsigned long long)fz << (2 * kFixBits));
-  const uint32_t idx = uint32_t(i0 + i) | (far ? kFarBit : 0u);
-  if (PAY) {
-    T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
-    T m = pin.lcell3;
-    if (pin.rho) {
-      const T rr = pin.rho[size_t(g.rs) * i];
-      vx = (vx * rr) / rr;
-      vy = (vy * rr) / rr;
-      vz = (vz * rr) / rr;
-      m = rr * pin.lcell3;
+  extern __shared__ uint32_t sh_cnt[];          // [nb] particles of this tile per bucket, then the first slot of its run
+  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) sh_cnt[b] = 0u;
+  __syncthreads();
+  constexpr int kItems = kBinTile / 1024;
+  const uint32_t sub = (tile0 + blockIdx.x) % kSub;
+  const int64_t base = int64_t(blockIdx.x) * kBinTile;
+  uint32_t ra[kItems][4], rb[kItems][4], bkt[kItems], rank[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int64_t i = base + r * 1024 + threadIdx.x;
+    bkt[r] = 0xffffffffu;
+    double x, y, z;
+    if (i >= np || !load_pos(pos, g, i, x, y, z)) continue;
+    uint32_t fx, fy, fz;
+    bool far = false;
+    const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+              cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+    const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+    bkt[r] = lin >> g.bshift;
+    rank[r] = atomicAdd(&sh_cnt[bkt[r]], 1u);
+    const unsigned long long w = (unsigned long long)fx | ((unsigned long long)fy << kFixBits) | ((unsigned long long)fz << (2 * kFixBits));
+    ra[r][0] = uint32_t(w); ra[r][1] = uint32_t(w >> 32); ra[r][2] = lin; ra[r][3] = uint32_t(i0 + i) | (far ? kFarBit : 0u);
+    if (PAY) {
+      T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
+      T m = pin.lcell3;
+      if (pin.rho) {
+        const T rr = pin.rho[size_t(g.rs) * i];
+        vx = (vx * rr) / rr;
+        vy = (vy * rr) / rr;
+        vz = (vz * rr) / rr;
+        m = rr * pin.lcell3;
+      }
+      rb[r][0] = __float_as_uint(float(vx)); rb[r][1] = __float_as_uint(float(vy)); rb[r][2] = __float_as_uint(float(vz));
+      rb[r][3] = __float_as_uint(float(m));
     }
-    st256(static_cast<Rec32*>(rec1) + dst, uint32_t(w), uint32_t(w >> 32), lin, idx, __float_as_uint(float(vx)),
-          __float_as_uint(float(vy)), __float_as_uint(float(vz)), __float_as_uint(float(m)));
-  } else {
-    static_cast<uint4*>(rec1)[dst] = make_uint4(uint32_t(w), uint32_t(w >> 32), lin, idx);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) {
+    const uint32_t c = sh_cnt[b];
+    if (c) sh_cnt[b] = atomicAdd(cursor + b * kSub + sub, c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    if (bkt[r] == 0xffffffffu) continue;
+    const uint32_t dst = sh_cnt[bkt[r]] + rank[r];
+    if (PAY) st256(static_cast<Rec32*>(rec1) + dst, ra[r][0], ra[r][1], ra[r][2], ra[r][3], rb[r][0], rb[r][1], rb[r][2], rb[r][3]);
+    else static_cast<uint4*>(rec1)[dst] = make_uint4(ra[r][0], ra[r][1], ra[r][2], ra[r][3]);
   }
 }
 
@@ -210,7 +252,8 @@ struct PlaceGeom {
 };
 template <bool PAY>
 __global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec1, vp_nn_stats_dev* __restrict__ stats,
-                                                     uint32_t* __restrict__ tab, PlaceGeom pg, void* __restrict__ srec) {
+                                                     uint32_t* __restrict__ tab, PlaceGeom pg, float4* __restrict__ spos,
+                                                     float4* __restrict__ spay) {
   const uint32_t n = uint32_t(stats->n_kept);
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= n) return;
@@ -229,10 +272,10 @@ __global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec
   const float ux = (float(fx) + 0.5f) * pg.sx, uy = (float(fy) + 0.5f) * pg.sy;
   const float uz = fmaf(float(cz & 31u), pg.hz, (float(fz) + 0.5f) * pg.sz);
   if (r[3] & kFarBit) atomicAdd(&stats->n_far, 1ull);
-  if (PAY)
-    st256(static_cast<Rec32*>(srec) + dst, __float_as_uint(ux), __float_as_uint(uy), __float_as_uint(uz), r[3], r[4], r[5], r[6], r[7]);
-  else
-    static_cast<float4*>(srec)[dst] = make_float4(ux, uy, uz, __uint_as_float(r[3]));
+  // search half and payload half go to separate arrays: the search streams 16-byte records (a 32-byte stride halves what
+  // L1 holds and made it 2x slower), the field kernel reads whole 16-byte payload records
+  spos[dst] = make_float4(ux, uy, uz, __uint_as_float(r[3]));
+  if (PAY) spay[dst] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
 }
 
 __global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
@@ -343,42 +386,127 @@ __device__ __forceinline__ void emit(const SearchOut& o, const rec_t* __restrict
 // examined block touches an end cell is decided by the exact stage, which reads the caller's coordinates
 __device__ __forceinline__ bool touches_end(int c0, int c1, int g) { return c0 <= 0 || c1 >= g - 1; }
 
-// Stage A, general form (any lattice / any cell size): one thread per node, the 2x2x2 window cell by cell.
-__global__ void __launch_bounds__(256) k_search_cells2(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
-                                                        Lattice L, float eps, SearchOut out) {
-  // block = (z nodes, y rows); grid = (z chunks, y chunks, x)
+// Records of cells [za, zb] (zb - za <= 31) of one cell row.  Their z offsets are relative to the 32-cell block of their own
+// cell, so the range is cut where it enters the next block: each piece is one contiguous run of records with a single
+// query offset  rz + (wz - block base) * hz  (rz = node z relative to the low corner of cell wz).
+__device__ __forceinline__ void scan_zcells(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, size_t row,
+                                            int za, int zb, int wz, float qx, float qy, float rz, float hz, Cand& c) {
+  const int zs = min(zb, za | 31);
+  const uint32_t s0 = __ldg(start + row + za), s1 = __ldg(start + row + zs + 1);
+  scan_range(part, rs, s0, s1, qx, qy, rz + float(wz - (za & ~31)) * hz, c);
+  if (zs < zb) scan_range(part, rs, s1, __ldg(start + row + zb + 1), qx, qy, rz + float(wz - ((zs + 1) & ~31)) * hz, c);
+}
+
+// Stage B, warp-cooperative: the node stage A could not prove is re-decided by its whole warp on the 32-cell union of the
+// three 4x2x2 bars through the window (proves sqrt(2) h with corner-aligned nodes) -- ONE CELL PER LANE, the per-lane
+// (winner, runner-up) pairs merged with shuffles, the same verdict.  Every lane of the warp must call this with the same
+// (i, j, k).  What is still unproven or ambiguous goes to the exact kernel.
+__device__ __forceinline__ void warp_plus32(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, const Grid& g,
+                                            const Lattice& L, float eps, const SearchOut& out, int lane, int i, int j, int k, bool far) {
+  const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
+  const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
+  const int wx1 = min(wx + 1, g.gx - 1), wy1 = min(wy + 1, g.gy - 1), wz1 = min(wz + 1, g.gz - 1);
+  const int x0 = max(wx - 1, 0), x1 = min(wx + 2, g.gx - 1);
+  const int y0 = max(wy - 1, 0), y1 = min(wy + 2, g.gy - 1);
+  const int z0 = max(wz - 1, 0), z1 = min(wz + 2, g.gz - 1);
+  if (far && (touches_end(x0, x1, g.gx) || touches_end(y0, y1, g.gy) || touches_end(z0, z1, g.gz))) {
+    if (lane == 0) out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    return;
+  }
+  // lanes 0..15: the four central rows x 4 cells along z;  lanes 16..31: the eight rows one step outside in x OR y x 2 cells
+  int X, Y, Z;
+  if (lane < 16) {
+    X = wx + (lane >> 3); Y = wy + ((lane >> 2) & 1); Z = wz - 1 + (lane & 3);
+  } else {
+    const int m = lane - 16, r8 = m >> 1;      // r8: (-1,0) (-1,1) (2,0) (2,1) (0,-1) (1,-1) (0,2) (1,2)
+    const int dx = r8 < 4 ? ((r8 & 2) ? 2 : -1) : (r8 & 1);
+    const int dy = r8 < 4 ? (r8 & 1) : ((r8 & 2) ? 2 : -1);
+    X = wx + dx; Y = wy + dy; Z = wz + (m & 1);
+  }
+  Cand c;
+  c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+  if (X >= 0 && X < g.gx && Y >= 0 && Y < g.gy && Z >= 0 && Z < g.gz) {
+    const size_t cell = (size_t(X) * g.gy + Y) * g.gz + Z;
+    scan_range(part, rs, __ldg(start + cell), __ldg(start + cell + 1), __ldg(L.rx + i) - float(X - wx) * float(g.hx),
+               __ldg(L.ry + j) - float(Y - wy) * float(g.hy), __ldg(L.rz + k) + float(wz - (Z & ~31)) * float(g.hz), c);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob1 = __shfl_xor_sync(0xffffffffu, c.b1, o), ob2 = __shfl_xor_sync(0xffffffffu, c.b2, o);
+    const int obi = __shfl_xor_sync(0xffffffffu, c.bi, o);
+    const bool lt = ob1 < c.b1;
+    c.b2 = fminf(fminf(c.b2, ob2), lt ? c.b1 : ob1);
+    c.bi = lt ? obi : c.bi;
+    c.b1 = lt ? ob1 : c.b1;
+  }
+  // nearest unexamined point: beyond a 4-cell bar end along one axis, or outside the 2-cell window along two axes
+  const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
+  const double m4 = fmin(axis_margin(qxd, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
+                         fmin(axis_margin(qyd, g.oy, g.hy, y0, y1, g.gy, false, false),
+                              axis_margin(qzd, g.oz, g.hz, z0, z1, g.gz, false, false)));
+  const double a2 = axis_margin(qxd, g.ox, g.hx, wx, wx1, g.gx, g.closed_xlo, g.closed_xhi);
+  const double b2 = axis_margin(qyd, g.oy, g.hy, wy, wy1, g.gy, false, false);
+  const double c2 = axis_margin(qzd, g.oz, g.hz, wz, wz1, g.gz, false, false);
+  const double lo1 = fmin(a2, fmin(b2, c2));
+  const double lo2 = (lo1 == a2) ? fmin(b2, c2) : ((lo1 == b2) ? fmin(a2, c2) : fmin(a2, b2));   // two smallest of (a2, b2, c2)
+  const double diag = (lo2 == INFINITY) ? INFINITY : sqrt(lo1 * lo1 + lo2 * lo2);
+  const double md = fmin(m4, diag);
+  float m = INFINITY;
+  if (md != INFINITY) m = md > 0.0 ? __double2float_rd(md * (1.0 - 1.0 / 1048576.0)) : 0.f;
+  if (lane == 0) {
+    if (judge(c, eps, m) == 0) {
+      if (out.nn) out.nn[node] = int(__float_as_uint(__ldg(&part[size_t(c.bi) * rs].w)) & ~kFarBit);
+      if (out.nn_pos) out.nn_pos[node] = c.bi;
+    } else {
+      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    }
+  }
+}
+
+// Stage A + B (any lattice / any cell size): one thread per node (consecutive lanes = consecutive z nodes), the 2x2x2 window
+// as 4 cell rows x 2 contiguous cells; the nodes of a warp that this cannot prove are then taken one after the other by
+// the whole warp (warp_plus32).
+__global__ void __launch_bounds__(256) k_search_rows(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
+                                                      Lattice L, float eps, SearchOut out) {
+  // block = (z nodes, y rows), blockDim.x a multiple of 32: a warp = 32 consecutive z nodes of one (i, j); grid = (z chunks, y chunks, x)
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int i = blockIdx.z;
-  if (k >= L.nz || j >= L.ny) return;
-  const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-  const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
-  if (out.stats->n_far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
-    out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
-    return;
-  }
-  const float rx = __ldg(L.rx + i), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
-  const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
-  Cand c;
-  c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+  const int lane = threadIdx.x & 31;
+  if (j >= L.ny) return;                       // uniform per warp
+  const bool valid = k < L.nz;
+  const bool far = out.stats->n_far != 0;
+  int verdict = -1;
+  if (valid) {
+    const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
+    const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
+    if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
+      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    } else {
+      const float rx = __ldg(L.rx + i), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
+      const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
+      const int z1 = min(wz + 1, g.gz - 1);
+      Cand c;
+      c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int X = wx + a, Y = wy + b;
-      if (X >= g.gx || Y >= g.gy) continue;
-      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
-      const float qx = rx - float(a) * hx, qy = ry - float(b) * hy;
-#pragma unroll
-      for (int zc = 0; zc < 2; ++zc) {
-        const int Z = wz + zc;
-        if (Z >= g.gz) continue;
-        const float qz = rz - float(zc) * hz + float(Z & 31) * hz;
-        scan_range(part, rs, __ldg(start + row + Z), __ldg(start + row + Z + 1), qx, qy, qz, c);
-      }
+        for (int b = 0; b < 2; ++b) {
+          const int X = wx + a, Y = wy + b;
+          if (X >= g.gx || Y >= g.gy) continue;
+          scan_zcells(part, rs, start, (size_t(X) * g.gy + Y) * g.gz, wz, z1, wz, rx - float(a) * hx, ry - float(b) * hy, rz, hz, c);
+        }
+      const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
+      verdict = judge(c, eps, m);
+      if (verdict != 2) emit(out, part, rs, node, verdict, c.bi);
     }
-  const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
-  emit(out, part, rs, node, judge(c, eps, m), c.bi);
+  }
+  unsigned need = __ballot_sync(0xffffffffu, verdict == 2);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    warp_plus32(part, rs, start, g, L, eps, out, lane, i, j, k - lane + src, far);
+  }
 }
 
 // Stage A, brick form: the lattice windows are consecutive cells along every axis (node i <-> cells [w0+i, w0+i+1]) and
@@ -500,13 +628,8 @@ __global__ void __launch_bounds__(256) k_search_brick(const rec_t* __restrict__ 
         for (int b = 0; b < 2; ++b) {
           const int X = wx + a, Y = wy + b;
           if (X >= g.gx || Y >= g.gy) continue;
-          const size_t row = (size_t(X) * g.gy + Y) * g.gz;
-          for (int zc = 0; zc < 2; ++zc) {
-            const int Z = wz + zc;
-            if (Z >= g.gz) continue;
-            scan_range(part, rs, __ldg(start + row + Z), __ldg(start + row + Z + 1), rx - float(a) * hx, ry - float(b) * hy,
-                       rz - float(zc) * hz + float(Z & 31) * hz, c);
-          }
+          scan_zcells(part, rs, start, (size_t(X) * g.gy + Y) * g.gz, wz, min(wz + 1, g.gz - 1), wz, rx - float(a) * hx,
+                      ry - float(b) * hy, rz, hz, c);
         }
       emit(out, part, rs, node, judge(c, eps, fminf(__ldg(L.mx + i), fminf(my, mz))), c.bi);
     }
@@ -573,9 +696,7 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
         if (!xin && !yin) continue;                                  // corner rows are not part of the union
         const size_t row = (size_t(X) * g.gy + Y) * g.gz;
         const int a = (xin && yin) ? z0 : wz, b = (xin && yin) ? z1 : wz1;
-        const float qx = rx - float(X - wx) * hx, qy = ry - float(Y - wy) * hy;
-        for (int Z = a; Z <= b; ++Z)
-          scan_range(part, rs, __ldg(start + row + Z), __ldg(start + row + Z + 1), qx, qy, rz - float(Z - wz) * hz + float(Z & 31) * hz, c);
+        scan_zcells(part, rs, start, row, a, b, wz, rx - float(X - wx) * hx, ry - float(Y - wy) * hy, rz, hz, c);
       }
     // nearest unexamined point: beyond a 4-cell bar end along one axis, or outside the 2-cell window along two axes
     const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
@@ -773,7 +894,7 @@ AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, 
   return a;
 }
 
-constexpr uint32_t kMaxBuckets = 16384;   // 64 KB of shared-memory counters in k_bin_hist
+constexpr uint32_t kMaxBuckets = 2048;    // 8 KB of shared-memory counters / cursors per CTA of the bucket pass
 
 Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, const double* qz, int nz,
                const vp_nn_opts& o) {
@@ -829,10 +950,12 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
   g.ps = o.row_stride > 0 ? o.row_stride : 3;
   g.vs = o.row_stride > 0 ? o.row_stride : 3;
   g.rs = o.row_stride > 0 ? o.row_stride : 1;
-  // buckets of 2^bshift consecutive cells holding ~2^17 particles on average (a 4 MB window of records: the counting
-  // sort inside it runs out of L2), at most kMaxBuckets of them
+  // buckets of 2^bshift consecutive cells holding ~2^20 particles on average (a 32 MB window of records: the counting
+  // sort inside it still runs out of L2, profiles/r2_ubench_scatter_gather.jsonl), at most kMaxBuckets of them
   const uint64_t ncells = uint64_t(gx) * gy * gz;
-  const double cells_per_bucket = double(ncells) * 131072.0 / double(np > 0 ? np : 1);
+  int blog = 20;
+  if (const char* ev = getenv("VP_BUCKET_LOG2")) blog = atoi(ev);
+  const double cells_per_bucket = double(ncells) * double(uint64_t(1) << blog) / double(np > 0 ? np : 1);
   int bshift = 0;
   while (bshift < 31 && double(uint64_t(1) << bshift) * 1.4142135623730951 < cells_per_bucket) ++bshift;   // nearest power of two
   if (const char* ev = getenv("VP_BUCKET_SHIFT")) bshift = atoi(ev);
@@ -848,28 +971,29 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
 size_t vp_scan_scratch_bytes_local(int64_t m) { return vp_align256(size_t((m + 4095) / 4096 + 1) * 4); }
 
 struct NNScratch {
-  size_t rec1, srec, tab, small, tail, total;
+  size_t rec1, spos, tab, hist, sums, tail, total;
 };
 NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint32_t nb, int64_t nnodes) {
   NNScratch s;
   s.rec1 = vp_align256(size_t(np) * (pay ? sizeof(Rec32) : sizeof(RecA)));
-  s.srec = pay ? 0 : vp_align256(size_t(np) * sizeof(rec_t));   // with a payload the sorted records are the caller's spay array
+  s.spos = vp_align256(size_t(np) * sizeof(rec_t) + 256);
   s.tab = vp_align256((ncells + 8) * 4);
-  s.small = 2 * vp_align256(size_t(nb + 1) * 4) + vp_scan_scratch_bytes_local(int64_t(ncells) + 1);
+  s.hist = 2 * vp_align256((size_t(nb) * kSub + 1) * 4);          // (bucket, sub-stream) histogram and cursors
+  s.sums = vp_scan_scratch_bytes_local(int64_t(ncells) + 1);
   const size_t b_lists = 2 * vp_align256(size_t(nnodes) * 4);
   s.tail = s.rec1 > b_lists ? s.rec1 : b_lists;   // the bucketed records are dead once placed; the two node lists reuse them
-  s.total = s.tail + s.srec + s.tab + s.small + 4096;
+  s.total = s.tail + s.spos + s.tab + s.hist + s.sums + 4096;
   return s;
 }
 
-// Optional payload travelling with the particles (whole-path use): sorted 32-byte records (search half + (v', m) half) and
-// the sorted position of every node's nearest particle, so that the field kernel reads the payload almost sequentially.
+// Optional payload travelling with the particles (whole-path use): sorted (v', m) records and the sorted position of every
+// node's nearest particle, so that the field kernel reads the payload almost sequentially.
 template <typename T>
 struct NNPayload {
   const T* vel = nullptr;
   const T* rho = nullptr;
   double lcell3 = 1.0;
-  float4* srec_out = nullptr;    // [np] x 2 float4
+  float4* spay_out = nullptr;    // [np] float4
   int32_t* nn_pos_out = nullptr;  // [nnodes]
 };
 
@@ -881,7 +1005,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
   VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
   const bool has_pay = pay != nullptr;
-  if (has_pay) VP_REQUIRE(pay->vel && pay->srec_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
+  if (has_pay) VP_REQUIRE(pay->vel && pay->spay_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
   vp_nn_opts o;
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
@@ -947,7 +1071,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   fill_axis(qy, ny, nx, g.oy, g.hy, g.ihy, gy, false, false);
   fill_axis(qz, nz, nx + ny, g.oz, g.hz, g.ihz, gz, false, false);
   // brick kernel: consecutive windows on every axis, z windows starting on a 32-cell boundary, node inside its window
-  bool brick = consecutive && (hw[nx + ny] % 32 == 0) && gx >= 2 && gy >= 2 && gz >= 2 && !getenv("VP_NO_BRICK");
+  bool brick = consecutive && (hw[nx + ny] % 32 == 0) && gx >= 2 && gy >= 2 && gz >= 2 && getenv("VP_SEARCH_BRICK");   // measured slower than k_search_rows
   for (size_t t = 0; t < nt && brick; ++t) {
     const double hh = t < size_t(nx) ? g.hx : (t < size_t(nx + ny) ? g.hy : g.hz);
     if (!(hr[t] >= -0.5f * float(hh) && hr[t] <= 2.5f * float(hh))) brick = false;   // keeps the f32 error bound of the brick frame
@@ -967,48 +1091,49 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   vp_arena_scope scope(ctx);
   VP_TRY(vp_arena_reserve(ctx, sc.total));
   void* rec1 = vp_arena_alloc(ctx, sc.tail);
-  rec_t* srec = has_pay ? reinterpret_cast<rec_t*>(pay->srec_out) : static_cast<rec_t*>(vp_arena_alloc(ctx, sc.srec ? sc.srec : 256));
+  rec_t* srec = static_cast<rec_t*>(vp_arena_alloc(ctx, sc.spos));
+  float4* spay = has_pay ? pay->spay_out : nullptr;
   uint32_t* xtab = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.tab));
-  uint32_t* hist = static_cast<uint32_t*>(vp_arena_alloc(ctx, vp_align256(size_t(g.nb + 1) * 4)));
-  uint32_t* cursor = static_cast<uint32_t*>(vp_arena_alloc(ctx, vp_align256(size_t(g.nb + 1) * 4)));
-  uint32_t* sums = static_cast<uint32_t*>(vp_arena_alloc(ctx, vp_scan_scratch_bytes_local(int64_t(ncells) + 1)));
-  VP_REQUIRE(rec1 && srec && xtab && hist && cursor && sums, "vp_nn_grid: arena carve failed");
+  uint32_t* hist = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.hist));
+  uint32_t* sums = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.sums));
+  VP_REQUIRE(rec1 && srec && xtab && hist && sums, "vp_nn_grid: arena carve failed");
+  uint32_t* cursor = hist + vp_align256((size_t(g.nb) * kSub + 1) * 4) / 4;
   uint32_t* node_list = static_cast<uint32_t*>(rec1);                                           // -> exact kernel
   uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> wider stage
-  const int rs = has_pay ? 2 : 1;     // float4 stride of the sorted records
+  const int rs = 1;                   // float4 stride of the sorted search records
 
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
   VP_CUDA(cudaMemsetAsync(xtab, 0, (ncells + 8) * 4, st));
-  VP_CUDA(cudaMemsetAsync(hist, 0, size_t(g.nb + 1) * 4, st));
+  VP_CUDA(cudaMemsetAsync(hist, 0, (size_t(g.nb) * kSub + 1) * 4, st));
   // counts / cursors live at xtab + 4 (16-byte aligned for the scan); after the placement cursor c holds the start of cell
   // c + 1, so the start table is the same array read from xtab + 3 (entry 0 = the zero in front of the counters)
   uint32_t* tab = xtab + 4;
   if (np > 0) {
     const double es = sizeof(T);
-    const size_t hist_smem = size_t(g.nb) * 4;
+    const size_t hsmem = size_t(g.nb) * kSub * 4, ssmem = size_t(g.nb) * 4;
     static bool attr_done = false;
     if (!attr_done) {
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * 4)));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
       attr_done = true;
     }
-    auto launch_hist = [&](const T* p, int64_t n_c) {
-      int64_t nb64 = (n_c + 255) / 256;
-      const int64_t cap = int64_t(ctx->sm_count) * 8;
-      k_bin_hist<T><<<unsigned(nb64 < cap ? nb64 : cap), 256, hist_smem, st>>>(p, n_c, g, hist);
+    auto launch_hist = [&](const T* p, int64_t n_c, int64_t i0) {
+      const int64_t nt = (n_c + kBinTile - 1) / kBinTile, cap = int64_t(ctx->sm_count) * 4;
+      k_bin_hist<T><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % kSub));
     };
     auto launch_scatter = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
       pin.vel = v;
       pin.rho = r;
       pin.lcell3 = T(has_pay ? pay->lcell3 : 1.0);
-      const unsigned nbk = unsigned((n_c + 255) / 256);
-      if (has_pay) k_bin_scatter<T, true><<<nbk, 256, 0, st>>>(p, pin, n_c, i0, g, cursor, rec1);
-      else k_bin_scatter<T, false><<<nbk, 256, 0, st>>>(p, pin, n_c, i0, g, cursor, rec1);
+      const unsigned nbk = unsigned((n_c + kBinTile - 1) / kBinTile);
+      if (has_pay) k_bin_scatter<T, true><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, uint32_t((i0 / kBinTile) % kSub), rec1);
+      else k_bin_scatter<T, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, uint32_t((i0 / kBinTile) % kSub), rec1);
     };
     if (host_pos) {
-      // positions arrive from the host in chunks (copy stream); the bucket histogram of chunk c is taken while chunk c+1 moves
+      // positions arrive from the host in chunks (copy stream); the histogram of chunk c is taken while chunk c+1 moves
       VP_REQUIRE(!has_pay && o.row_stride == 0 && !o.use_x_keep, "vp_nn_grid: host position streaming is the plain compact form");
+      VP_REQUIRE(host_pos->chunk % kBinTile == 0 || host_pos->chunk >= np, "vp_nn_grid: host chunks must hold whole tiles");
       VP_TRY(vp_host_streams(ctx));
       const int64_t chunk = host_pos->chunk;
       T* posd = const_cast<T*>(pos);
@@ -1021,13 +1146,13 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         VP_CUDA(cudaMemcpyAsync(posd + 3 * i0, static_cast<const T*>(host_pos->pos_h) + 3 * i0, size_t(n_c) * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->copy_stream));
         VP_CUDA(cudaEventRecord(ctx->ev_h2d[c & 1], ctx->copy_stream));
         VP_CUDA(cudaStreamWaitEvent(st, ctx->ev_h2d[c & 1], 0));
-        launch_hist(posd + 3 * i0, n_c);
+        launch_hist(posd + 3 * i0, n_c, i0);
       }
     } else {
       vp_stage stage(ctx, "k1a_bin_hist", st, 1, double(np) * 3 * es);
-      launch_hist(pos, np);
+      launch_hist(pos, np, 0);
     }
-    k_bin_offsets<<<1, 1024, 0, st>>>(hist, cursor, g.nb, ctx->nn_stats_d);
+    k_bin_offsets<<<1, 1024, 0, st>>>(hist, cursor, g.nb * kSub, ctx->nn_stats_d);
     ctx->n_launch += 1;
     {
       // read pos (+vel, rho), write one record
@@ -1041,7 +1166,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       if (has_pay) k_cell_count<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab);
       else k_cell_count<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab);
     }
-    VP_TRY(vp_scan_exclusive_u32(ctx, tab, int64_t(ncells) + 1, sums, st));
+    VP_TRY(vp_scan_exclusive_u32(ctx, tab, int64_t(ncells) + 1, sums, st, "k1d_cell_scan"));
     {
       // record read, cursor bumped, record written in cell order
       vp_stage stage(ctx, "k1e_cell_place", st, 1, double(np) * (has_pay ? 64.0 : 32.0) + double(ncells) * 4.0);
@@ -1049,8 +1174,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       pg.sx = float(g.hx / 2097152.0); pg.sy = float(g.hy / 2097152.0); pg.sz = float(g.hz / 2097152.0);
       pg.hz = float(g.hz);
       pg.gz = uint32_t(gz);
-      if (has_pay) k_cell_place<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec);
-      else k_cell_place<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec);
+      if (has_pay) k_cell_place<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec, spay);
+      else k_cell_place<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec, nullptr);
     }
     VP_CHECK_LAUNCH();
   }
@@ -1062,8 +1187,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   so.nn = nn; so.nn_pos = nn_pos; so.list_b = list_b; so.list_c = node_list; so.stats = ctx->nn_stats_d;
   {
     // sorted records read once + cell starts read once + one index written per node
-    vp_stage stage(ctx, brick ? "k1f_search_brick" : "k1f_search_cells2", st, 1,
-                   double(np) * (has_pay ? 32.0 : 16.0) + double(ncells) * 4.0 + double(nnodes) * 4.0);
+    vp_stage stage(ctx, brick ? "k1f_search_brick" : "k1f_search_rows_plus", st, 1,
+                   double(np) * 16.0 + double(ncells) * 4.0 + double(nnodes) * 4.0);
     if (brick) {
       dim3 grid((nz + kBZ - 1) / kBZ, (ny + kBY - 1) / kBY, (nx + kBX - 1) / kBX);
       VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
@@ -1079,10 +1204,10 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       int by = 256 / bx;
       dim3 block(bx, by, 1), grid((nz + bx - 1) / bx, (ny + by - 1) / by, nx);
       VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
-      k_search_cells2<<<grid, block, 0, st>>>(srec, rs, start, g, L, eps, so);
+      k_search_rows<<<grid, block, 0, st>>>(srec, rs, start, g, L, eps, so);
     }
   }
-  {
+  if (brick) {   // (k_search_rows settles its unproven nodes itself, warp-cooperatively)
     vp_stage stage(ctx, "k1g_search_block4", st, 1);
     k_search_block4<<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
   }
@@ -1102,7 +1227,7 @@ int nn_payload_typed(vp_ctx* ctx, const void* pos, const void* vel, const void* 
   pay.vel = static_cast<const T*>(vel);
   pay.rho = static_cast<const T*>(rho);
   pay.lcell3 = lcell3;
-  pay.srec_out = reinterpret_cast<float4*>(spay);
+  pay.spay_out = reinterpret_cast<float4*>(spay);
   pay.nn_pos_out = nn_pos;
   return nn_grid_typed<T>(ctx, static_cast<const T*>(pos), np, qx, nx, qy, ny, qz, nz, nn_idx, &pay, opts, st);
 }
@@ -1530,7 +1655,7 @@ extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* ve
 
 extern "C" int vp_fields_sorted(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, float* const v_d[3],
                                 float* const p_d[3], float* e_d, float* m_d, void* stream) {
-  return vp_fields_from_records(ctx, nn_pos_d, n_nodes, spay_d, 2, 1, v_d, p_d, e_d, m_d, static_cast<cudaStream_t>(stream));
+  return vp_fields_from_records(ctx, nn_pos_d, n_nodes, spay_d, 1, 0, v_d, p_d, e_d, m_d, static_cast<cudaStream_t>(stream));
 }
 
 int vp_fields_from_records(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, int stride, int offset,

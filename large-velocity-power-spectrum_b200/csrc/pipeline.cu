@@ -65,7 +65,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   const int64_t chunk = np < (int64_t(1) << 24) ? np : (int64_t(1) << 24);
   size_t own = 0;
   if (on_host) own += vp_align256(size_t(np) * 3 * es) + vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 1024;
-  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * (on_host ? 16 : 32)) + vp_align256(size_t(nbins) * 16) + 8192;
+  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * 16) + vp_align256(size_t(nbins) * 16) + 8192;
   size_t inner = vp_nn_grid_scratch_bytes_tables(np, dtype, qx, N, qy, N, qz, N, nullptr);
   size_t inner2 = vp_pk_fields_scratch_bytes(plan);
   vp_arena_scope scope(ctx);
@@ -78,7 +78,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
     VP_REQUIRE(pos_res, "particles_to_pk: arena carve failed");
   }
   int32_t* nn_pos = static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4));
-  float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * (on_host ? 16 : 32)));   // host path: (v', m) in input order; device path: sorted 32-byte records
+  float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * 16));   // (v', m) records: input order (host path) or cell order (device path)
   float* planes[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < nplanes; ++i) {
     planes[i] = static_cast<float*>(vp_arena_alloc(ctx, n3 * 4));
@@ -110,7 +110,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   if (want_v) { v3[0] = planes[at++]; v3[1] = planes[at++]; v3[2] = planes[at++]; }
   if (want_p) { p3[0] = planes[at++]; if (!strict) { p3[1] = planes[at++]; p3[2] = planes[at++]; } }
   if (want_e) e1 = planes[at++];
-  VP_TRY(vp_fields_from_records(ctx, nn_pos, int64_t(n3), spay, on_host ? 1 : 2, on_host ? 0 : 1, v3, p3, e1, nullptr, st));
+  VP_TRY(vp_fields_from_records(ctx, nn_pos, int64_t(n3), spay, 1, 0, v3, p3, e1, nullptr, st));
 
   std::vector<double> hp(nbins);
   auto one = [&](float** f, int nc, double scale, int row) -> int {

@@ -81,10 +81,19 @@ __global__ void __launch_bounds__(kThreads) k_scan_sums(const uint32_t* __restri
   __shared__ uint32_t ws[kWarps];
   const int64_t base = int64_t(blockIdx.x) * kScanChunk;
   uint32_t s = 0;
+  if (base + kScanChunk <= m && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(a + base);
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    int64_t i = base + r * kThreads + threadIdx.x;
-    if (i < m) s += a[i];
+    for (int r = 0; r < 4; ++r) {
+      const uint4 v = a4[r * kThreads + threadIdx.x];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      int64_t i = base + r * kThreads + threadIdx.x;
+      if (i < m) s += a[i];
+    }
   }
   uint32_t tot;
   block_excl_scan_256(s, ws, &tot);
@@ -103,22 +112,37 @@ __global__ void __launch_bounds__(kThreads) k_scan_top(uint32_t* __restrict__ su
   }
 }
 
+// chunk = 4 sub-blocks of 1024 elements; inside a sub-block thread t owns elements 4t .. 4t+3 (one 16-byte access)
 __global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t* __restrict__ a, int64_t m,
                                                           const uint32_t* __restrict__ sums) {
   __shared__ uint32_t ws[kWarps];
-  const int64_t base = int64_t(blockIdx.x) * kScanChunk + int64_t(threadIdx.x) * 16;
-  uint32_t v[16], s = 0;
+  const int64_t cbase = int64_t(blockIdx.x) * kScanChunk;
+  uint32_t carry = sums[blockIdx.x];
+  const bool fast = cbase + kScanChunk <= m && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+#pragma unroll 1
+  for (int sb = 0; sb < 4; ++sb) {
+    const int64_t base = cbase + sb * (kThreads * 4) + int64_t(threadIdx.x) * 4;
+    uint32_t v[4];
+    if (fast) {
+      const uint4 q = *reinterpret_cast<const uint4*>(a + base);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    v[r] = (base + r < m) ? a[base + r] : 0u;
-    s += v[r];
-  }
-  uint32_t tot;
-  uint32_t ex = block_excl_scan_256(s, ws, &tot) + sums[blockIdx.x];
+      for (int r = 0; r < 4; ++r) v[r] = (base + r < m) ? a[base + r] : 0u;
+    }
+    const uint32_t s = (v[0] + v[1]) + (v[2] + v[3]);
+    uint32_t tot;
+    uint32_t ex = block_excl_scan_256(s, ws, &tot) + carry;
+    carry += tot;
+    uint32_t o[4];
+    o[0] = ex; o[1] = ex + v[0]; o[2] = o[1] + v[1]; o[3] = o[2] + v[2];
+    if (fast) {
+      *reinterpret_cast<uint4*>(a + base) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    if (base + r < m) a[base + r] = ex;
-    ex += v[r];
+      for (int r = 0; r < 4; ++r)
+        if (base + r < m) a[base + r] = o[r];
+    }
   }
 }
 
@@ -226,12 +250,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_scatter(const uint32_t* __restr
 
 }  // namespace
 
-int vp_scan_exclusive_u32(vp_ctx* ctx, uint32_t* a, int64_t m, uint32_t* sums, cudaStream_t st) {
+int vp_scan_exclusive_u32(vp_ctx* ctx, uint32_t* a, int64_t m, uint32_t* sums, cudaStream_t st, const char* stage_name) {
   if (m <= 0) return VP_OK;
   const int64_t nchunks64 = (m + kScanChunk - 1) / kScanChunk;
   VP_REQUIRE(nchunks64 < (int64_t(1) << 31), "vp_scan: too many elements");
   const int nchunks = int(nchunks64);
-  vp_stage stage(ctx, "k1d_cell_scan", st, 3, double(m) * 12.0);   // read twice, written once
+  vp_stage stage(ctx, stage_name, st, 3, double(m) * 12.0);   // read twice, written once
   k_scan_sums<<<nchunks, kThreads, 0, st>>>(a, m, sums);
   k_scan_top<<<1, kThreads, 0, st>>>(sums, nchunks);
   k_scan_apply<<<nchunks, kThreads, 0, st>>>(a, m, sums);

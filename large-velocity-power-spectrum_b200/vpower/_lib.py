@@ -56,6 +56,7 @@ SIGNATURES = {
     "vp_slab_scatter_p2p": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, C.POINTER(_L), _P]),
     "vp_gather_rows": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "vp_build_fields": (_I, [_P, _P, _L, _P, _P, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
+    "vp_snapshot_preamble": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _dp, _dp, _P]),
     "vp_deposit_ngp": (_I, [_P, _P, _I, _L, _P, _I, _I, _D, _P, _P]),
     "vp_pk_plan_create": (_I, [_P, _I, _dp, _dp, _I, C.POINTER(_P)]),
     "vp_pk_plan_destroy": (_I, [_P]),
@@ -287,8 +288,7 @@ class SlabExchangeP2P:
 
 
 def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):
-    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, srec[np,8] f32 = the cell-sorted 32-byte records:
-    floats 0..3 the search half, floats 4..7 the payload (v'x, v'y, v'z, m)).
+    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, spay[np,4] f32 in cell order).
     With opts.row_stride > 0 the three tensors are column views of one interleaved row tensor."""
     torch = _torch()
     assert pos_t.is_cuda and vel_t.dtype == pos_t.dtype
@@ -300,7 +300,7 @@ def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts
     shape = (len(qx_a), len(qy_a), len(qz_a))
     nn_idx = torch.empty(shape, dtype=torch.int32, device=pos_t.device) if want_idx else None
     nn_pos = torch.empty(shape, dtype=torch.int32, device=pos_t.device)
-    spay = torch.empty((pos_t.shape[0], 8), dtype=torch.float32, device=pos_t.device)
+    spay = torch.empty((pos_t.shape[0], 4), dtype=torch.float32, device=pos_t.device)
     _check(load_library().vp_nn_grid_payload(
         ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()), _P(rho_t.data_ptr()) if rho_t is not None else None,
         _dtype_code(pos_t), pos_t.shape[0], qx_p, shape[0], qy_p, shape[1], qz_p, shape[2], float(lcell3),
@@ -357,6 +357,17 @@ def gather_rows(idx_t, src_t):
     _check(load_library().vp_gather_rows(ctx(), _P(idx_t.data_ptr()), n, _P(src_t.data_ptr()), row, _P(out.data_ptr()),
                                          stream_ptr()))
     return out
+
+
+def snapshot_preamble(pos_t, vel_t, mass_t, shift=True, bulk=True):
+    """In place on CUDA tensors: pos -= min(pos) per axis, vel -= mass-weighted mean velocity.  -> (min[3], bulk[3])."""
+    mn, bk = (C.c_double * 3)(), (C.c_double * 3)()
+    ref = pos_t if pos_t is not None else vel_t
+    _check(load_library().vp_snapshot_preamble(
+        ctx(), _P(pos_t.data_ptr()) if pos_t is not None else None, _P(vel_t.data_ptr()) if vel_t is not None else None,
+        _P(mass_t.data_ptr()) if mass_t is not None else None, _dtype_code(ref), ref.shape[0], 1 if shift else 0, 1 if bulk else 0,
+        mn, bk, stream_ptr()))
+    return np.array(list(mn)), np.array(list(bk))
 
 
 # --------------------------------------------------------------------------- K3

@@ -81,6 +81,20 @@ class CudaBackend:
         f = _lib.fields_sorted(nn_pos, spay, want_v=False, want_e=True)
         return [f["e"]], 1.0
 
+    def fields_all(self, gridded, quantities, strict):
+        """Every plane the quantities need from ONE pass over (nn_pos, sorted records) -> {quantity: (planes, multiplicity)}."""
+        nn_pos, spay = gridded
+        want_p = (True, not strict, not strict) if "momentum" in quantities else (False, False, False)
+        f = _lib.fields_sorted(nn_pos, spay, want_v="velocity" in quantities, want_p=want_p, want_e="energy" in quantities)
+        out = {}
+        if "velocity" in quantities:
+            out["velocity"] = ([f["vx"], f["vy"], f["vz"]], 1.0)
+        if "momentum" in quantities:
+            out["momentum"] = ([f["px"]], 3.0) if strict else ([f["px"], f["py"], f["pz"]], 1.0)
+        if "energy" in quantities:
+            out["energy"] = ([f["e"]], 1.0)
+        return out
+
     def fft_local(self, slabs):
         return self.plan.dist_local(slabs)
 
@@ -179,8 +193,9 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
 
     out = {}
     ns_total = None
+    planes = backend.fields_all(gridded, quantities, momentum_strict) if hasattr(backend, "fields_all") else None
     for q in quantities:
-        slabs, mult = backend.fields(gridded, q, momentum_strict)
+        slabs, mult = planes.pop(q) if planes is not None else backend.fields(gridded, q, momentum_strict)
         if getattr(backend, "p2p", False):
             # fused exchange: the y pass stores into every rank's receive buffer; a stream-ordered tiny all-reduce is
             # the barrier between "all ranks have written" and "this rank reads"

@@ -20,11 +20,18 @@ __all__ = ["load_snapshot", "GasParticles", "BoxField", "ann_interpolate", "make
 
 
 # ------------------------------------------------------------------------------------------ snapshot
-def load_snapshot(file, Lbox=1.0, remove_bulk_velocity=True, shift_to_origin=True):
+def _is_dev(a):
+    return type(a).__module__.startswith("torch") and getattr(a, "is_cuda", False)
+
+
+def load_snapshot(file, Lbox=1.0, remove_bulk_velocity=True, shift_to_origin=True, device=False):
     """PartType0 {Coordinates, Masses, Density, Velocities} -> GasParticles.  interp.py:84-131.
 
     HDF5 needs h5py (not in this image); a `.npz` with the same four keys
     ('PartType0/Coordinates', ...) or bare ('Coordinates', ...) is accepted as well.
+    device=True (not in the reference): the four arrays are uploaded once and stay CUDA tensors; the shift and the
+    bulk-velocity removal then run as device reductions (vp_snapshot_preamble) and `ann_interp_to_field` grids them in
+    place -- nothing O(Np) happens on the host after the file has been read.
     """
     if str(file).endswith(".npz"):
         z = np.load(file)
@@ -35,6 +42,9 @@ def load_snapshot(file, Lbox=1.0, remove_bulk_velocity=True, shift_to_origin=Tru
         with h5py.File(file, "r") as f:
             g = f["PartType0"]
             c, m, d, v = g["Coordinates"][:], g["Masses"][:], g["Density"][:], g["Velocities"][:]
+    if device:
+        dt = np.float64 if np.asarray(c).dtype == np.float64 else np.float32
+        c, m, d, v = (_lib.to_device(np.asarray(a, dtype=dt)) for a in (c, m, d, v))
     gp = GasParticles(c, m, d, v, Lbox=Lbox)
     if remove_bulk_velocity is True:
         gp.remove_bulk_velocity()
@@ -62,12 +72,18 @@ class GasParticles:
         return GasParticles(self.pos[index], self.mass[index], self.density[index], self.v[index], self.Lbox)
 
     def shift_to_origin(self) -> None:
-        """interp.py:169-175."""
+        """interp.py:169-175.  CUDA tensors: one device reduction + one update (vp_snapshot_preamble)."""
+        if _is_dev(self.pos):
+            _lib.snapshot_preamble(self.pos, None, None, shift=True, bulk=False)
+            return
         for c in range(3):
             self.pos[:, c] -= np.min(self.pos[:, c])
 
     def remove_bulk_velocity(self) -> None:
-        """Subtract the mass-weighted mean velocity.  interp.py:178-182."""
+        """Subtract the mass-weighted mean velocity.  interp.py:178-182.  CUDA tensors: on the device."""
+        if _is_dev(self.v):
+            _lib.snapshot_preamble(None, self.v, self.mass, shift=False, bulk=True)
+            return
         M = np.sum(self.mass)
         for c in range(3):
             self.v[:, c] -= np.sum(self.mass * self.v[:, c]) / M
@@ -101,10 +117,13 @@ class GasParticles:
             raise Exception("vpower_b200: only the exact search (eps=0) is implemented")
         Lcell = self.Lbox / Nsize
         ax = _lattice_axis(self.Lbox, Nsize)
-        dt = np.float64 if np.asarray(self.pos).dtype == np.float64 else np.float32
-        pos_t = _lib.to_device(np.asarray(self.pos, dtype=dt))
-        vel_t = _lib.to_device(np.asarray(self.v, dtype=dt))
-        rho_t = _lib.to_device(np.asarray(self.density, dtype=dt))
+        if _is_dev(self.pos):
+            pos_t, vel_t, rho_t = self.pos.contiguous(), self.v.contiguous(), self.density.contiguous()
+        else:
+            dt = np.float64 if np.asarray(self.pos).dtype == np.float64 else np.float32
+            pos_t = _lib.to_device(np.asarray(self.pos, dtype=dt))
+            vel_t = _lib.to_device(np.asarray(self.v, dtype=dt))
+            rho_t = _lib.to_device(np.asarray(self.density, dtype=dt))
         nn, nn_pos, spay = _lib.nn_grid_payload(pos_t, vel_t, rho_t, ax, ax, ax, Lcell ** 3)
         del pos_t
         return BoxField._from_device(nn, vel_t, rho_t, Lcell, nn_pos, spay)

@@ -223,7 +223,7 @@ def test_boxfield_host_helpers_match_reference_expressions():
 
 def test_cell_list_plan_invariants_without_a_device():
     """vp_nn_grid_plan is host arithmetic: the linear cell index must fit 32 bits, the buckets of 2^bucket_shift consecutive
-    cells must cover the grid with at most 16384 of them (the shared-memory histogram of the first pass), and the
+    cells must cover the grid with at most 2048 of them (the shared-memory counters of the bucket pass), and the
     1-particle-per-node lattices must come out corner aligned -- for every BASELINE configuration (cfg5 cannot be run on one
     device) and for awkward shapes."""
     from vpower import _lib
@@ -234,7 +234,7 @@ def test_cell_list_plan_invariants_without_a_device():
         assert gx >= 1 and gy >= 1 and gz >= 1
         ncells = gx * gy * gz
         assert ncells < 2 ** 32 - 1
-        assert 1 <= p["n_buckets"] <= 16384 and 0 <= p["bucket_shift"] <= 31
+        assert 1 <= p["n_buckets"] <= 2048 and 0 <= p["bucket_shift"] <= 31
         assert p["n_buckets"] == -(-ncells // (1 << p["bucket_shift"]))           # the buckets cover every cell
         return p
 
@@ -242,10 +242,10 @@ def test_cell_list_plan_invariants_without_a_device():
         ax = np.linspace(0.5 / N, 1.0 + 0.5 / N, N)                            # library lattice
         p = check(Np, ax, ax, ax)
         assert (p["cells_x"], p["cells_y"], p["cells_z"]) == (N + 1,) * 3 and p["corner_aligned"] == 1
-        # about 2^17 particles per bucket: the counting sort inside a bucket's window of records runs out of L2
-        assert Np <= (1 << 18) or 1 << 16 <= Np / p["n_buckets"] <= 1 << 18
+        # about 2^20 particles per bucket: the counting sort inside a bucket's window of records runs out of L2
+        assert Np <= (1 << 21) or 1 << 19 <= Np / p["n_buckets"] <= 1 << 21
     p = check(1 << 30, *(np.linspace(0.5 / 1024, 1.0 + 0.5 / 1024, 1024),) * 3)
-    assert p["bucket_shift"] == 17 and p["n_buckets"] == 8217 and p["scratch_MiB"] < 150 * 1024
+    assert p["bucket_shift"] == 20 and p["n_buckets"] == 1028 and p["scratch_MiB"] < 150 * 1024
     # cfg5 (2048^3): one device cannot hold it; a slab of it (8 ranks) must plan fine, the whole lattice gets coarser cells
     ax5 = np.linspace(0.5 / 2048, 1.0 + 0.5 / 2048, 2048)
     o = _lib.NNOpts()
