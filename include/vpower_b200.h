@@ -96,6 +96,9 @@ int vp_nn_grid(vp_ctx* ctx, const void* pos_d, int pos_dtype, int64_t np, const 
 /* Number of lattice nodes the last vp_nn_grid on this ctx needed the wide (ring >= 2) search for,
  * and the number it could not prove at all (only possible with use_x_keep).  Syncs `stream`. */
 int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_t* n_kept, void* stream);
+/* The same plus two diagnostics: out5 = { n_wide, n_unresolved, n_kept, nodes the wider prefilter stage took, particles
+ * outside the cell grid (clamped into end cells; nodes next to end cells then go to the exact stage) }.  Syncs. */
+int vp_nn_grid_stats_ex(vp_ctx* ctx, int64_t* out5, void* stream);
 /* The cell list vp_nn_grid would build for these arguments -- host arithmetic only, no device, no ctx (useful for sizing
  * and for checking the key layout at sizes that do not fit a test machine).  info_out[10] = { cells_x, cells_y, cells_z,
  * yb, lb, nyc, bins, row_bits, scratch_MiB, corner_aligned }: the sort key is (row << lb) | local with
@@ -104,15 +107,25 @@ int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresolved, int64_
 int vp_nn_grid_plan(int64_t np, const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz,
                     const vp_nn_opts* opts, int64_t* info_out);
 
-/* K1 with a payload (whole-path form).  Besides (optionally) nn_idx_d it returns
- *   spay_d   [np] float4 = (vx', vy', vz', m) in CELL-SORTED particle order, v' = (rho*v)/rho, m = rho*lcell3
- *            evaluated in the input dtype (interp.py:199-213,272-273), rho_d == NULL -> rho = 1;
+/* K1 with a payload.  Besides (optionally) nn_idx_d it returns
+ *   spay_d   [np] x 8 float: the CELL-SORTED 32-byte records -- floats 0..3 the search half (cell-relative offsets, particle
+ *            index), floats 4..7 = (vx', vy', vz', m), v' = (rho*v)/rho, m = rho*lcell3 evaluated in the input dtype
+ *            (interp.py:199-213,272-273), rho_d == NULL -> rho = 1;
  *   nn_pos_d [nx,ny,nz] int32 = position in that sorted order of every node's nearest particle,
  * so that vp_fields_sorted reads the payload almost sequentially instead of gathering by particle index. */
 int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
                        const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz, double lcell3,
                        int32_t* nn_idx_d /* may be NULL */, int32_t* nn_pos_d, float* spay_d, const vp_nn_opts* opts,
                        void* stream);
+/* K1 + K3 in one call (the whole-path form): the search stages write the requested field planes themselves -- the stage
+ * that settles a node reads the payload half of the winner's record (the 32-byte sector the search has just read) and
+ * stores vx, vy, vz / px, py, pz / e / m at that node (same planes and arithmetic as vp_build_fields, interp.py:272-273,
+ * 501-557).  v_d / p_d may be NULL or hold NULL entries, e_d / m_d may be NULL (at least one plane must be requested);
+ * nn_idx_d may be NULL.  The sorted records live in the ctx arena for the duration of the call. */
+int vp_nn_grid_fields(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                      const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz, double lcell3,
+                      float* const v_d[3], float* const p_d[3], float* e_d, float* m_d, int32_t* nn_idx_d,
+                      const vp_nn_opts* opts, void* stream);
 /* K3 on the sorted payload: same planes as vp_build_fields (interp.py:501-557). */
 int vp_fields_sorted(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, float* const v_d[3],
                      float* const p_d[3], float* e_d, float* m_d, void* stream);

@@ -78,19 +78,25 @@ __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const f
 }
 
 // ------------------------------------------------------------------ y pass: lines strided by NZ, C columns per CTA
-// Destination of the y pass, two layouts of the half spectrum:
-//   row-major  (tile_major = 0):  base[d] + (xoff + x_local)*N*kzc + ky*kzc + (kz - d*kzc)
-//   tile-major (tile_major = 1):  base[d] + (((xoff + x_local)*(kzc/C) + zt_local)*N + ky)*C + c -- the C columns of a tile stay
-//       together, so everything one CTA stores for one x is ONE contiguous block of N*C*8 bytes (a warp store = 256
-//       contiguous bytes instead of four 64-byte pieces): the form used when the store crosses NVLink.
-//   single GPU, in place      : base[0] = the field itself, xoff = 0, kzc = N/2, row-major (a CTA writes where it read)
-//   NCCL exchange             : base[d] = send buffer block d ([dest][x_local][ky][kzc]), xoff = 0, row-major
-//   peer-to-peer (fused)      : base[d] = rank d's receive buffer mapped through CUDA IPC, xoff = rank*N/nranks, tile-major --
-//                               the tile is stored over NVLink where the x pass of rank d will read it
+// Destination of the y pass, two layouts of the half spectrum [x][ky][kz]:
+//   row-major (blocked = 0):  base[d] + (xoff + x_local)*N*kzc + ky*kzc + (kz - d*kzc)
+//   blocked   (blocked = 1):  base[d] + ((((ky/16)*nxtot + xoff + x_local)*(kzc/C) + zt_local)*16 + ky%16)*C + c
+//       -- 16 consecutive ky of one (x, kz tile) form ONE contiguous block of 16*C*8 bytes (1 KB at C = 8), and for a fixed
+//       (ky, kz tile) consecutive x are only (kzc/C)*16*C*8 bytes apart (64 KB at N = 1024 on one GPU instead of the 4 MB
+//       of the row-major layout).  Why: a line FFT along x reads 64-byte pieces one x-stride apart, and
+//       profiles/r2_ubench_strided.jsonl shows what that costs on B200 -- 7.5 TB/s at 4 KB, 6.1 at 64 KB, 3.0 at 4 MB.
+//       The y pass stores whole 1 KB blocks (a warp store = 256 contiguous bytes), which is also what NVLink wants.
+//   single GPU        : base[0] = a second buffer (the y pass cannot be in place with this layout), blocked
+//   NCCL exchange     : base[d] = send buffer block d ([dest][x_local][ky][kzc]), xoff = 0, row-major
+//   peer-to-peer      : base[d] = rank d's receive buffer mapped through CUDA IPC, xoff = rank*N/nranks, blocked --
+//                       the blocks are stored over NVLink where the x pass of rank d will read them
+//   diagnostics       : base[0] = the field itself, row-major, in place (a CTA writes where it read)
+constexpr int kYB = 16;   // ky per block of the blocked layout
 struct YDest {
   float2* base[16];
   int xoff;
-  int tile_major;
+  int blocked;
+  int nxtot;    // x planes of the destination array (N)
 };
 
 template <int R2, int R3, int C>
@@ -108,24 +114,27 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * NZ];
   F::run(v, t, sm + c, tw);
   const int kz0 = zt * C, d = kz0 / kzc;
-  float2* ob;
-  int sky;
-  if (dst.tile_major) {
-    ob = dst.base[d] + ((size_t(dst.xoff) + x) * (kzc / C) + (kz0 - d * kzc) / C) * (size_t(L) * C) + c;
-    sky = C;
-  } else {
-    ob = dst.base[d] + (size_t(dst.xoff) + x) * L * kzc + (kz0 - d * kzc) + c;
-    sky = kzc;
-  }
+  if (dst.blocked) {
+    const int tiles_r = kzc / C;
+    float2* ob = dst.base[d] + ((size_t(dst.xoff) + x) * tiles_r + (kz0 - d * kzc) / C) * (kYB * C) + c;
+    const size_t blk = size_t(dst.nxtot) * tiles_r * (kYB * C);      // one ky block of all x
 #pragma unroll
-  for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * sky] = v[j];
+    for (int j = 0; j < 16; ++j) {
+      const int ky = F::kout(j, t);
+      ob[size_t(ky / kYB) * blk + (ky % kYB) * C] = v[j];
+    }
+  } else {
+    float2* ob = dst.base[d] + (size_t(dst.xoff) + x) * L * kzc + (kz0 - d * kzc) + c;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * kzc] = v[j];
+  }
 }
 
 // ------------------------------------------------------------------ x pass with |F|^2, then shell binning
 struct FieldSet {
   float2* f[3];
   int n;
-  int tile_major;   // layout of the half spectrum the x pass reads (see YDest)
+  int blocked;      // layout of the half spectrum the x pass reads (see YDest)
 };
 
 // x pass of 1..3 components of one (ky, kz-tile): the sum over components of |F|^2 is collected in a shared-memory tile
@@ -147,9 +156,11 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
   const int tiles_z = NZ / C;
   const int ky = blockIdx.x / tiles_z, zt = blockIdx.x % tiles_z;
-  const size_t xstride = size_t(L) * NZ;
+  // element (x, ky, zt, c): row-major  x*L*NZ + ky*NZ + zt*C + c;  blocked  ((((ky/16)*L + x)*tiles_z + zt)*16 + ky%16)*C + c
+  const size_t xstride = fs.blocked ? size_t(tiles_z) * (kYB * C) : size_t(L) * NZ;
+  const size_t tile_off = fs.blocked ? (size_t(ky / kYB) * L * tiles_z + zt) * (kYB * C) + (ky % kYB) * C : size_t(ky) * NZ + size_t(zt) * C;
   for (int comp = 0; comp < fs.n; ++comp) {
-    const float2* base = fs.f[comp] + (fs.tile_major ? (size_t(zt) * L + ky) * C : size_t(ky) * NZ + size_t(zt) * C) + c;
+    const float2* base = fs.f[comp] + tile_off + c;
     float2 v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
@@ -491,7 +502,8 @@ YDest ydest_blocks(float2* out, int nranks, int nx, int N, int kzc) {
   YDest d;
   for (int r = 0; r < 16; ++r) d.base[r] = r < nranks ? out + size_t(r) * nx * N * kzc : nullptr;
   d.xoff = 0;
-  d.tile_major = 0;
+  d.blocked = 0;
+  d.nxtot = nx;
   return d;
 }
 // x pass + |F|^2 (k_fft_x_pow) and shell binning (k_bin_tiles).  psum is accumulated into (the caller zeroes it); cnt is
@@ -632,7 +644,9 @@ extern "C" int vp_pk_plan_destroy(vp_pk_plan* p) {
 }
 
 size_t vp_pk_fields_scratch_bytes(const vp_pk_plan* pl) {
-  if (pl->pow2) return vp_align256(size_t(pl->N) * (pl->N / 2) * (((pl->N / 2 + 1) + 31) / 32 * 32) * sizeof(float)) + 8192;   // folded power tiles
+  if (pl->pow2)   // folded power tiles + the second cube of the out-of-place y pass
+    return vp_align256(size_t(pl->N) * (pl->N / 2) * (((pl->N / 2 + 1) + 31) / 32 * 32) * sizeof(float)) +
+           vp_align256(size_t(pl->N) * pl->N * (pl->N / 2) * sizeof(float2)) + 16384;
   const size_t n3 = size_t(pl->N) * pl->N * pl->N;
   return vp_align256(n3 * sizeof(float2)) + vp_align256(n3 * sizeof(double)) + vp_align256(sizeof(double2) * pl->N) + 16384;
 }
@@ -687,15 +701,28 @@ extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, do
   const int N = pl->N;
   VP_CUDA(cudaMemsetAsync(psum_d, 0, sizeof(double) * pl->nbins, st));
   VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
+  // The y pass writes the blocked layout out of place: component 0 into a scratch cube, component c into the (dead) cube of
+  // component c - 1 -- one extra cube whatever the number of components.
+  vp_arena_scope scope(pl->ctx);
+  const size_t cube = vp_align256(size_t(N) * N * (N / 2) * sizeof(float2));
+  VP_TRY(vp_arena_reserve(pl->ctx, vp_pk_fields_scratch_bytes(pl)));
+  float2* extra = static_cast<float2*>(vp_arena_alloc(pl->ctx, cube));
+  VP_REQUIRE(extra, "vp_pk_fields: arena carve failed");
   FieldSet fs;
   fs.n = ncomp;
-  fs.tile_major = 0;
+  fs.blocked = 1;
   for (int c = 0; c < 3; ++c) fs.f[c] = nullptr;
   for (int c = 0; c < ncomp; ++c) {
     VP_REQUIRE(field_d[c], "vp_pk_fields: null field %d", c);
     VP_TRY(run_z(field_d[c], N, N, pl, st));
-    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), ydest_blocks(reinterpret_cast<float2*>(field_d[c]), 1, N, N, N / 2), N, N, N / 2, pl, st));
-    fs.f[c] = reinterpret_cast<float2*>(field_d[c]);
+    YDest dst;
+    for (int r = 0; r < 16; ++r) dst.base[r] = nullptr;
+    dst.base[0] = c == 0 ? extra : reinterpret_cast<float2*>(field_d[c - 1]);
+    dst.xoff = 0;
+    dst.blocked = 1;
+    dst.nxtot = N;
+    VP_TRY(run_y(reinterpret_cast<float2*>(field_d[c]), dst, N, N, N / 2, pl, st));
+    fs.f[c] = dst.base[0];
   }
   VP_TRY(run_x_bin(fs, N, N / 2, 0, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
   vp_stage stage(pl->ctx, "k5_plane_bin", st, 1, 8.0 * double(N) * N * ncomp);
@@ -741,11 +768,11 @@ extern "C" int vp_pk_dist_local(vp_pk_plan* pl, float* const* field_d, int ncomp
   return VP_OK;
 }
 
-static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int tile_major, double* psum_d, uint64_t* nsample_d, void* stream);
+static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int blocked, double* psum_d, uint64_t* nsample_d, void* stream);
 extern "C" int vp_pk_dist_final(vp_pk_plan* pl, float* const* recv_d, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
   return dist_final_impl(pl, recv_d, ncomp, 0, psum_d, nsample_d, stream);
 }
-static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int tile_major, double* psum_d, uint64_t* nsample_d, void* stream) {
+static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int blocked, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && recv_d && psum_d && nsample_d && ncomp >= 1 && ncomp <= 3, "vp_pk_dist_final: bad argument");
   vp_call_guard guard(pl->ctx, static_cast<cudaStream_t>(stream));
   VP_REQUIRE(pl->pow2, "vp_pk_dist_final: N=%d has no slab path", pl->N);
@@ -756,7 +783,7 @@ static int dist_final_impl(vp_pk_plan* pl, float* const* recv_d, int ncomp, int 
   VP_CUDA(cudaMemsetAsync(nsample_d, 0, sizeof(uint64_t) * pl->nbins, st));
   FieldSet fs;
   fs.n = ncomp;
-  fs.tile_major = tile_major;
+  fs.blocked = blocked;
   for (int c = 0; c < 3; ++c) fs.f[c] = c < ncomp ? reinterpret_cast<float2*>(recv_d[c]) : nullptr;
   VP_TRY(run_x_bin(fs, N, pl->kzc, pl->rank * pl->kzc, pl, psum_d, reinterpret_cast<unsigned long long*>(nsample_d), st));
   if (pl->rank == 0) {   // the packed kz=0 column (planes kz=0 and kz=N/2) lives on rank 0
@@ -833,7 +860,8 @@ extern "C" int vp_pk_dist_local_p2p(vp_pk_plan* pl, float* const* field_d, int n
     YDest dst;
     for (int d = 0; d < 16; ++d) dst.base[d] = d < pl->nranks ? pl->peer[c][d] : nullptr;
     dst.xoff = pl->rank * nx;
-    dst.tile_major = 1;
+    dst.blocked = 1;
+    dst.nxtot = N;
     VP_TRY(run_y(reinterpret_cast<const float2*>(field_d[c]), dst, N, nx, pl->kzc, pl, st));
   }
   return VP_OK;
@@ -842,7 +870,7 @@ extern "C" int vp_pk_dist_local_p2p(vp_pk_plan* pl, float* const* field_d, int n
 extern "C" int vp_pk_dist_final_p2p(vp_pk_plan* pl, int ncomp, double* psum_d, uint64_t* nsample_d, void* stream) {
   VP_REQUIRE(pl && ncomp >= 1 && ncomp <= pl->p2p_ncomp, "vp_pk_dist_final_p2p: bad argument");
   float* r[3] = {reinterpret_cast<float*>(pl->recv[0]), reinterpret_cast<float*>(pl->recv[1]), reinterpret_cast<float*>(pl->recv[2])};
-  return dist_final_impl(pl, r, ncomp, 1, psum_d, nsample_d, stream);   // the peer stores arrive tile-major (see YDest)
+  return dist_final_impl(pl, r, ncomp, 1, psum_d, nsample_d, stream);   // the peer stores arrive in the blocked layout (see YDest)
 }
 
 extern "C" int vp_fft_r2c_inplace(vp_pk_plan* pl, float* field_d, void* stream) {

@@ -20,7 +20,11 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -35,6 +39,7 @@ struct Grid {
   int ps, vs, rs;              // element strides between consecutive particles in pos / vel / rho (3,3,1 when compact)
   int bshift;                  // bucket of a cell = linear cell index >> bshift,  linear = (cx*gy + cy)*gz + cz
   uint32_t nb;                 // number of buckets
+  float hxf, hyf, hzf;         // cell size in f32 (operands straight from the constant bank in the search loops)
 };
 
 // ---- record formats
@@ -46,22 +51,24 @@ constexpr uint32_t kFixMax = (1u << kFixBits) - 1u;
 constexpr uint32_t kFarBit = 0x80000000u;   // idx bit 31: the particle lies outside the cell grid (clamped into an end cell)
 struct __align__(16) RecA { uint32_t u0, u1, cell, idx; };
 struct __align__(32) Rec32 { RecA a; float4 b; };
-// Sorted records (search format), one per particle in cell order, two arrays: spos float4 = (ux, uy, uz32, idx bits) and, with a
-// payload, spay float4 = (v'x, v'y, v'z, m): ux, uy = offset from the low corner of the particle's cell; uz32 = offset from the low corner of
+// Sorted record (search format), one per particle in cell order: float4 a = (ux, uy, uz32, idx bits) [+ float4 b = (v'x, v'y,
+// v'z, m) with a payload, the two halves in one 32-byte record]: ux, uy = offset from the low corner of the particle's cell; uz32 = offset from the low corner of
 // the aligned 32-cell z block the cell lies in (cz & ~31) -- a brick of the search kernel spans exactly one such block
 // plus one cell, so staging re-bases z with one add.  Every consumer knows the cell (it walks the cell table).
 typedef float4 rec_t;
 
+// (explicit round-to-nearest operations: with FMA contraction the compiler may form f - c from the UNROUNDED product, which
+// comes out at -1e-17 for a particle whose f rounds up to an integer -- and every kernel must assign the same cell)
 __device__ __forceinline__ int cell_fix(double x, double o, double ih, int g, uint32_t& fix, bool& far) {
-  const double f = (x - o) * ih;
+  const double f = __dmul_rn(__dsub_rn(x, o), ih);
   int c;
   if (!(f > 0.0)) c = 0;
   else if (f >= double(g)) c = g - 1;
   else c = int(f);
-  double u = f - double(c);                      // in [0,1) unless the particle was clamped into an end cell (or is NaN)
+  double u = __dsub_rn(f, double(c));            // in [0,1) unless the particle was clamped into an end cell (or is NaN)
   if (!(u >= 0.0)) { far = far || (u < 0.0) || (u != u); u = 0.0; }
   if (u >= 1.0) { far = true; u = 1.0; }
-  uint32_t q = uint32_t(u * 2097152.0);
+  uint32_t q = uint32_t(__dmul_rn(u, 2097152.0));
   fix = q > kFixMax ? kFixMax : q;
   return c;
 }
@@ -92,6 +99,7 @@ __device__ __forceinline__ bool load_pos(const T* __restrict__ pos, const Grid& 
 // Part 1 (k_bin_hist): particles per (bucket, sub-stream) -- persistent CTAs, shared-memory counters, one flush per CTA.
 constexpr int kBinTile = 4096;
 constexpr int kSub = 8;
+constexpr int kClu = 8;      // tiles per thread-block cluster of the scatter kernel: they claim their runs together
 template <typename T>
 __global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ hist_g,
                                                    uint32_t tile0) {
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int
   __syncthreads();
   const int64_t ntiles = (np + kBinTile - 1) / kBinTile;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t sub = uint32_t((tile0 + tile) % kSub);
+    const uint32_t sub = uint32_t(((tile0 + tile) / kClu) % kSub);   // all tiles of a cluster append to the same sub-stream
     const int64_t base = tile * kBinTile;
 #pragma unroll 4
     for (int r = 0; r < kBinTile / 256; ++r) {
@@ -178,14 +186,83 @@ struct PayloadIn {
 // its sub-stream cursor, and the records go straight from registers to their slots: all records of a run are written
 // within the same few microseconds, and temporally adjacent tiles append adjacent runs, so L2 assembles whole lines.
 template <typename T, bool PAY>
-__global__ void __launch_bounds__(1024) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
-                                                       uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
-  // pos / pin.vel / pin.rho point at particle i0 (a chunk); the stored index is global (i0 + local)
+__global__ void __launch_bounds__(1024, 2) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
+                                                          uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
+  // pos / pin.vel / pin.rho point at particle i0 (a chunk); the stored index is global (i0 + local).
+  // 32 registers per thread = two CTAs per SM, so that one tile's loads overlap the other's stores: only the search half
+  // of the record is carried across the two barriers, the payload is loaded right before the store.  (Persistent CTAs with
+  // all position loads hoisted in front were slower: 31.0 vs 25.4 ms at 2^30 particles.)
   extern __shared__ uint32_t sh_cnt[];          // [nb] particles of this tile per bucket, then the first slot of its run
   for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) sh_cnt[b] = 0u;
   __syncthreads();
   constexpr int kItems = kBinTile / 1024;
-  const uint32_t sub = (tile0 + blockIdx.x) % kSub;
+  const uint32_t sub = ((tile0 + blockIdx.x) / kClu) % kSub;
+  const int64_t base = int64_t(blockIdx.x) * kBinTile;
+  uint32_t ra[kItems][3], slot[kItems];          // fixed-point offsets (2 words), linear cell; bucket-local rank, later the slot
+  bool farv[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int64_t i = base + r * 1024 + threadIdx.x;
+    slot[r] = 0xffffffffu;
+    farv[r] = false;
+    double x, y, z;
+    if (i >= np || !load_pos(pos, g, i, x, y, z)) continue;
+    uint32_t fx, fy, fz;
+    bool far = false;
+    const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+              cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+    const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+    slot[r] = atomicAdd(&sh_cnt[lin >> g.bshift], 1u);
+    const unsigned long long w = (unsigned long long)fx | ((unsigned long long)fy << kFixBits) | ((unsigned long long)fz << (2 * kFixBits));
+    ra[r][0] = uint32_t(w); ra[r][1] = uint32_t(w >> 32); ra[r][2] = lin;
+    farv[r] = far;
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) {
+    const uint32_t c = sh_cnt[b];
+    if (c) sh_cnt[b] = atomicAdd(cursor + b * kSub + sub, c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    if (slot[r] == 0xffffffffu) continue;
+    const int64_t i = base + r * 1024 + threadIdx.x;
+    const uint32_t dst = sh_cnt[ra[r][2] >> g.bshift] + slot[r];
+    const uint32_t idx = uint32_t(i0 + i) | (farv[r] ? kFarBit : 0u);
+    if (PAY) {
+      T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
+      T m = pin.lcell3;
+      if (pin.rho) {
+        const T rr = pin.rho[size_t(g.rs) * i];
+        vx = (vx * rr) / rr;
+        vy = (vy * rr) / rr;
+        vz = (vz * rr) / rr;
+        m = rr * pin.lcell3;
+      }
+      st256(static_cast<Rec32*>(rec1) + dst, ra[r][0], ra[r][1], ra[r][2], idx, __float_as_uint(float(vx)), __float_as_uint(float(vy)),
+            __float_as_uint(float(vz)), __float_as_uint(float(m)));
+    } else {
+      static_cast<uint4*>(rec1)[dst] = make_uint4(ra[r][0], ra[r][1], ra[r][2], idx);
+    }
+  }
+}
+
+// The same with thread-block clusters (sm_90+/sm_100): the kClu CTAs of a cluster rank their tiles independently, add up
+// their per-bucket counts through distributed shared memory, claim ONE run per bucket for the whole cluster (kClu times
+// longer: ~1 KB instead of ~128 B at 1024 buckets) and write into it side by side -- DRAM sees the long runs it needs
+// (profiles/r2_ubench_scatter_gather.jsonl: runs of 32 records move at the copy rate, runs of 4 at ~55 %).
+template <typename T, bool PAY>
+__global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(1024)
+k_bin_scatter_clu(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g, uint32_t* __restrict__ cursor,
+                  uint32_t tile0, void* __restrict__ rec1) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ uint32_t sh_cnt[];          // [nb] counts of this tile, later the first slot of this tile's part of the run
+  uint32_t* sh_base = sh_cnt + g.nb;            // [nb] (cluster rank 0 only) first slot of the cluster's run
+  const unsigned crank = cluster.block_rank();
+  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) sh_cnt[b] = 0u;
+  __syncthreads();
+  constexpr int kItems = kBinTile / 1024;
+  const uint32_t sub = ((tile0 + blockIdx.x) / kClu) % kSub;
   const int64_t base = int64_t(blockIdx.x) * kBinTile;
   uint32_t ra[kItems][4], rb[kItems][4], bkt[kItems], rank[kItems];
 #pragma unroll
@@ -217,10 +294,33 @@ __global__ void __launch_bounds__(1024) k_bin_scatter(const T* __restrict__ pos,
       rb[r][3] = __float_as_uint(float(m));
     }
   }
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) {
-    const uint32_t c = sh_cnt[b];
-    if (c) sh_cnt[b] = atomicAdd(cursor + b * kSub + sub, c);
+  cluster.sync();                               // every tile of the cluster has its counts
+  // per bucket (at most two per thread, nb <= 2048): slots taken by the lower-ranked tiles, and the cluster's total
+  uint32_t off[2] = {0u, 0u}, tot[2] = {0u, 0u};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint32_t b = threadIdx.x + q * 1024;
+    if (b < g.nb) {
+      for (unsigned r = 0; r < unsigned(kClu); ++r) {
+        const uint32_t c = *cluster.map_shared_rank(sh_cnt + b, r);
+        if (r < crank) off[q] += c;
+        tot[q] += c;
+      }
+    }
+  }
+  cluster.sync();                               // all remote reads of the counts are done: they may be overwritten now
+  if (crank == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t b = threadIdx.x + q * 1024;
+      if (b < g.nb) sh_base[b] = tot[q] ? atomicAdd(cursor + b * kSub + sub, tot[q]) : 0u;
+    }
+  }
+  cluster.sync();                               // the claims of rank 0 are visible
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint32_t b = threadIdx.x + q * 1024;
+    if (b < g.nb) sh_cnt[b] = *cluster.map_shared_rank(sh_base + b, 0) + off[q];
   }
   __syncthreads();
 #pragma unroll
@@ -230,6 +330,7 @@ __global__ void __launch_bounds__(1024) k_bin_scatter(const T* __restrict__ pos,
     if (PAY) st256(static_cast<Rec32*>(rec1) + dst, ra[r][0], ra[r][1], ra[r][2], ra[r][3], rb[r][0], rb[r][1], rb[r][2], rb[r][3]);
     else static_cast<uint4*>(rec1)[dst] = make_uint4(ra[r][0], ra[r][1], ra[r][2], ra[r][3]);
   }
+  cluster.sync();                               // rank 0's shared memory stays alive until every tile has read its claims
 }
 
 // per-cell counts: T[cell] += 1 (the records of one bucket are contiguous, so the counters in flight are L2 resident)
@@ -252,8 +353,7 @@ struct PlaceGeom {
 };
 template <bool PAY>
 __global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec1, vp_nn_stats_dev* __restrict__ stats,
-                                                     uint32_t* __restrict__ tab, PlaceGeom pg, float4* __restrict__ spos,
-                                                     float4* __restrict__ spay) {
+                                                     uint32_t* __restrict__ tab, PlaceGeom pg, void* __restrict__ srec) {
   const uint32_t n = uint32_t(stats->n_kept);
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= n) return;
@@ -272,10 +372,12 @@ __global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec
   const float ux = (float(fx) + 0.5f) * pg.sx, uy = (float(fy) + 0.5f) * pg.sy;
   const float uz = fmaf(float(cz & 31u), pg.hz, (float(fz) + 0.5f) * pg.sz);
   if (r[3] & kFarBit) atomicAdd(&stats->n_far, 1ull);
-  // search half and payload half go to separate arrays: the search streams 16-byte records (a 32-byte stride halves what
-  // L1 holds and made it 2x slower), the field kernel reads whole 16-byte payload records
-  spos[dst] = make_float4(ux, uy, uz, __uint_as_float(r[3]));
-  if (PAY) spay[dst] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+  // ONE 32-byte store per record: a whole sector.  (Writing the search half and the payload half to two arrays -- two
+  // scattered 16-byte partial-sector stores -- took 43.5 ms instead of 18.0 ms at 2^30 particles.)
+  if (PAY)
+    st256(static_cast<Rec32*>(srec) + dst, __float_as_uint(ux), __float_as_uint(uy), __float_as_uint(uz), r[3], r[4], r[5], r[6], r[7]);
+  else
+    static_cast<float4*>(srec)[dst] = make_float4(ux, uy, uz, __uint_as_float(r[3]));
 }
 
 __global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
@@ -364,17 +466,41 @@ __device__ __forceinline__ int judge(const Cand& c, float eps, float margin) {
   return (c.b2 - c.b1 > tol) ? 0 : 1;
 }
 
+// Field planes written straight from the search (K3 fused into K1): the stage that settles a node reads the payload half
+// of the winner's record -- the same 32-byte sector the search has just read -- and writes the node's value of every
+// requested plane (interp.py:272-273, 501-557).  Null pointers = plane not wanted; all null = no fusion.
+struct FieldOut {
+  float *vx, *vy, *vz, *px, *py, *pz, *e, *m;
+  int on;
+};
+__device__ __forceinline__ void write_fields(const FieldOut& f, const rec_t* __restrict__ part, int rs, size_t node, int pos) {
+  const float4 w = __ldg(part + size_t(pos) * rs + 1);
+  if (f.vx) f.vx[node] = w.x;
+  if (f.vy) f.vy[node] = w.y;
+  if (f.vz) f.vz[node] = w.z;
+  if (f.px) f.px[node] = w.x * w.w;
+  if (f.py) f.py[node] = w.y * w.w;
+  if (f.pz) f.pz[node] = w.z * w.w;
+  if (f.e) f.e[node] = w.w * (w.x * w.x + w.y * w.y + w.z * w.z);   // interp.py:546 (no 1/2)
+  if (f.m) f.m[node] = w.w;
+}
+
 struct SearchOut {
   int32_t* nn;        // particle index per node (may be null)
   int32_t* nn_pos;    // sorted position per node (may be null)
   uint32_t* list_b;   // nodes for the wider stage
   uint32_t* list_c;   // nodes for the exact stage
   vp_nn_stats_dev* stats;
+  FieldOut f;
 };
+__device__ __forceinline__ void settle(const SearchOut& o, const rec_t* __restrict__ part, int rs, size_t node, int pos) {
+  if (o.nn) o.nn[node] = int(__float_as_uint(__ldg(&part[size_t(pos) * rs].w)) & ~kFarBit);
+  if (o.nn_pos) o.nn_pos[node] = pos;
+  if (o.f.on) write_fields(o.f, part, rs, node, pos);
+}
 __device__ __forceinline__ void emit(const SearchOut& o, const rec_t* __restrict__ part, int rs, size_t node, int verdict, int pos) {
   if (verdict == 0) {
-    if (o.nn) o.nn[node] = int(__float_as_uint(__ldg(&part[size_t(pos) * rs].w)) & ~kFarBit);
-    if (o.nn_pos) o.nn_pos[node] = pos;
+    settle(o, part, rs, node, pos);
   } else if (verdict == 1) {
     o.list_c[atomicAdd(&o.stats->n_wide, 1ull)] = uint32_t(node);
   } else {
@@ -397,116 +523,59 @@ __device__ __forceinline__ void scan_zcells(const rec_t* __restrict__ part, int 
   if (zs < zb) scan_range(part, rs, s1, __ldg(start + row + zb + 1), qx, qy, rz + float(wz - ((zs + 1) & ~31)) * hz, c);
 }
 
-// Stage B, warp-cooperative: the node stage A could not prove is re-decided by its whole warp on the 32-cell union of the
-// three 4x2x2 bars through the window (proves sqrt(2) h with corner-aligned nodes) -- ONE CELL PER LANE, the per-lane
-// (winner, runner-up) pairs merged with shuffles, the same verdict.  Every lane of the warp must call this with the same
-// (i, j, k).  What is still unproven or ambiguous goes to the exact kernel.
-__device__ __forceinline__ void warp_plus32(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, const Grid& g,
-                                            const Lattice& L, float eps, const SearchOut& out, int lane, int i, int j, int k, bool far) {
-  const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-  const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
-  const int wx1 = min(wx + 1, g.gx - 1), wy1 = min(wy + 1, g.gy - 1), wz1 = min(wz + 1, g.gz - 1);
-  const int x0 = max(wx - 1, 0), x1 = min(wx + 2, g.gx - 1);
-  const int y0 = max(wy - 1, 0), y1 = min(wy + 2, g.gy - 1);
-  const int z0 = max(wz - 1, 0), z1 = min(wz + 2, g.gz - 1);
-  if (far && (touches_end(x0, x1, g.gx) || touches_end(y0, y1, g.gy) || touches_end(z0, z1, g.gz))) {
-    if (lane == 0) out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
-    return;
-  }
-  // lanes 0..15: the four central rows x 4 cells along z;  lanes 16..31: the eight rows one step outside in x OR y x 2 cells
-  int X, Y, Z;
-  if (lane < 16) {
-    X = wx + (lane >> 3); Y = wy + ((lane >> 2) & 1); Z = wz - 1 + (lane & 3);
-  } else {
-    const int m = lane - 16, r8 = m >> 1;      // r8: (-1,0) (-1,1) (2,0) (2,1) (0,-1) (1,-1) (0,2) (1,2)
-    const int dx = r8 < 4 ? ((r8 & 2) ? 2 : -1) : (r8 & 1);
-    const int dy = r8 < 4 ? (r8 & 1) : ((r8 & 2) ? 2 : -1);
-    X = wx + dx; Y = wy + dy; Z = wz + (m & 1);
-  }
-  Cand c;
-  c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
-  if (X >= 0 && X < g.gx && Y >= 0 && Y < g.gy && Z >= 0 && Z < g.gz) {
-    const size_t cell = (size_t(X) * g.gy + Y) * g.gz + Z;
-    scan_range(part, rs, __ldg(start + cell), __ldg(start + cell + 1), __ldg(L.rx + i) - float(X - wx) * float(g.hx),
-               __ldg(L.ry + j) - float(Y - wy) * float(g.hy), __ldg(L.rz + k) + float(wz - (Z & ~31)) * float(g.hz), c);
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const float ob1 = __shfl_xor_sync(0xffffffffu, c.b1, o), ob2 = __shfl_xor_sync(0xffffffffu, c.b2, o);
-    const int obi = __shfl_xor_sync(0xffffffffu, c.bi, o);
-    const bool lt = ob1 < c.b1;
-    c.b2 = fminf(fminf(c.b2, ob2), lt ? c.b1 : ob1);
-    c.bi = lt ? obi : c.bi;
-    c.b1 = lt ? ob1 : c.b1;
-  }
-  // nearest unexamined point: beyond a 4-cell bar end along one axis, or outside the 2-cell window along two axes
-  const double qxd = L.qx[i], qyd = L.qy[j], qzd = L.qz[k];
-  const double m4 = fmin(axis_margin(qxd, g.ox, g.hx, x0, x1, g.gx, g.closed_xlo, g.closed_xhi),
-                         fmin(axis_margin(qyd, g.oy, g.hy, y0, y1, g.gy, false, false),
-                              axis_margin(qzd, g.oz, g.hz, z0, z1, g.gz, false, false)));
-  const double a2 = axis_margin(qxd, g.ox, g.hx, wx, wx1, g.gx, g.closed_xlo, g.closed_xhi);
-  const double b2 = axis_margin(qyd, g.oy, g.hy, wy, wy1, g.gy, false, false);
-  const double c2 = axis_margin(qzd, g.oz, g.hz, wz, wz1, g.gz, false, false);
-  const double lo1 = fmin(a2, fmin(b2, c2));
-  const double lo2 = (lo1 == a2) ? fmin(b2, c2) : ((lo1 == b2) ? fmin(a2, c2) : fmin(a2, b2));   // two smallest of (a2, b2, c2)
-  const double diag = (lo2 == INFINITY) ? INFINITY : sqrt(lo1 * lo1 + lo2 * lo2);
-  const double md = fmin(m4, diag);
-  float m = INFINITY;
-  if (md != INFINITY) m = md > 0.0 ? __double2float_rd(md * (1.0 - 1.0 / 1048576.0)) : 0.f;
-  if (lane == 0) {
-    if (judge(c, eps, m) == 0) {
-      if (out.nn) out.nn[node] = int(__float_as_uint(__ldg(&part[size_t(c.bi) * rs].w)) & ~kFarBit);
-      if (out.nn_pos) out.nn_pos[node] = c.bi;
-    } else {
-      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
-    }
-  }
-}
-
-// Stage A + B (any lattice / any cell size): one thread per node (consecutive lanes = consecutive z nodes), the 2x2x2 window
-// as 4 cell rows x 2 contiguous cells; the nodes of a warp that this cannot prove are then taken one after the other by
-// the whole warp (warp_plus32).
-__global__ void __launch_bounds__(256) k_search_rows(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
-                                                      Lattice L, float eps, SearchOut out) {
-  // block = (z nodes, y rows), blockDim.x a multiple of 32: a warp = 32 consecutive z nodes of one (i, j); grid = (z chunks, y chunks, x)
+// Stage A (any lattice / any cell size): one thread per node (consecutive lanes = consecutive z nodes), the 2x2x2 window as
+// 4 cell rows x 2 contiguous cells.  The z offsets of the records are relative to the 32-cell block of their own cell: when
+// cell wz + 1 opens a new block (one lane in 32) a row is two runs with two query offsets -- those lanes take the second
+// cell in a separate, rare tail.  Register budget: 32 (8 CTAs of 256 threads per SM) -- the loop is latency bound, and a
+// version carrying the wider stage inline needed 64 registers and ran 2.2x slower.
+template <int RS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_search_rows(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
+                                                         Lattice L, float eps, SearchOut out) {
+  // block = (z nodes, y rows); grid = (z chunks, y chunks, x)
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int i = blockIdx.z;
-  const int lane = threadIdx.x & 31;
-  if (j >= L.ny) return;                       // uniform per warp
-  const bool valid = k < L.nz;
-  const bool far = out.stats->n_far != 0;
-  int verdict = -1;
-  if (valid) {
-    const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-    const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
-    if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
-      out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
-    } else {
-      const float rx = __ldg(L.rx + i), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
-      const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
-      const int z1 = min(wz + 1, g.gz - 1);
-      Cand c;
-      c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+  if (k >= L.nz || j >= L.ny) return;
+  const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
+  const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
+  if (out.stats->n_far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
+    out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    return;
+  }
+  const int z1 = min(wz + 1, g.gz - 1);
+  const bool cross = (wz & 31) == 31 && z1 > wz;
+  uint32_t rs0[4], re0[4];
+  {
+    const int zl = cross ? wz : z1;               // last cell of the first run
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int X = wx + a, Y = wy + b;
-          if (X >= g.gx || Y >= g.gy) continue;
-          scan_zcells(part, rs, start, (size_t(X) * g.gy + Y) * g.gz, wz, z1, wz, rx - float(a) * hx, ry - float(b) * hy, rz, hz, c);
-        }
-      const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
-      verdict = judge(c, eps, m);
-      if (verdict != 2) emit(out, part, rs, node, verdict, c.bi);
+    for (int r = 0; r < 4; ++r) {
+      const int X = wx + (r >> 1), Y = wy + (r & 1);
+      const bool in = X < g.gx && Y < g.gy;
+      const size_t row = in ? (size_t(X) * g.gy + Y) * g.gz : 0;
+      rs0[r] = in ? __ldg(start + row + wz) : 0u;
+      re0[r] = in ? __ldg(start + row + zl + 1) : 0u;
     }
   }
-  unsigned need = __ballot_sync(0xffffffffu, verdict == 2);
-  while (need) {
-    const int src = __ffs(need) - 1;
-    need &= need - 1;
-    warp_plus32(part, rs, start, g, L, eps, out, lane, i, j, k - lane + src, far);
+  const float rx = __ldg(L.rx + i), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
+  Cand c;
+  c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+  {
+    const float qz0 = rz + float(wz & 31) * g.hzf;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) scan_range(part, RS, rs0[r], re0[r], rx - float(r >> 1) * g.hxf, ry - float(r & 1) * g.hyf, qz0, c);
   }
+  if (cross) {
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+      const int X = wx + (r >> 1), Y = wy + (r & 1);
+      if (X >= g.gx || Y >= g.gy) continue;
+      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
+      scan_range(part, RS, __ldg(start + row + wz + 1), __ldg(start + row + z1 + 1), rx - float(r >> 1) * g.hxf, ry - float(r & 1) * g.hyf,
+                 rz - g.hzf, c);
+    }
+  }
+  const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
+  emit(out, part, RS, node, judge(c, eps, m), c.bi);
 }
 
 // Stage A, brick form: the lattice windows are consecutive cells along every axis (node i <-> cells [w0+i, w0+i+1]) and
@@ -715,8 +784,7 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
     if (md != INFINITY) m = md > 0.0 ? __double2float_rd(md * (1.0 - 1.0 / 1048576.0)) : 0.f;
     const int verdict = judge(c, eps, m);
     if (verdict == 0) {
-      if (out.nn) out.nn[node] = int(__float_as_uint(__ldg(&part[size_t(c.bi) * rs].w)) & ~kFarBit);
-      if (out.nn_pos) out.nn_pos[node] = c.bi;
+      settle(out, part, rs, node, c.bi);
     } else {
       out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = node;
     }
@@ -728,9 +796,11 @@ __global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__
 // particle has been examined).
 template <typename T>
 __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start,
-                                                       const T* __restrict__ pos, Grid g, Lattice L, int32_t* __restrict__ nn,
-                                                       int32_t* __restrict__ nn_pos, const uint32_t* __restrict__ list,
-                                                       vp_nn_stats_dev* __restrict__ stats) {
+                                                       const T* __restrict__ pos, Grid g, Lattice L, SearchOut out) {
+  int32_t* __restrict__ nn = out.nn;
+  int32_t* __restrict__ nn_pos = out.nn_pos;
+  const uint32_t* __restrict__ list = out.list_c;
+  vp_nn_stats_dev* __restrict__ stats = out.stats;
   const unsigned long long nw = stats->n_wide;
   const int lane = threadIdx.x & 31;
   const unsigned long long warp0 = (unsigned long long)(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -812,6 +882,7 @@ __global__ void __launch_bounds__(256) k_search_exact(const rec_t* __restrict__ 
     if (lane == 0) {
       if (nn) nn[node] = (b.idx == 0x7fffffff) ? -1 : b.idx;
       if (nn_pos) nn_pos[node] = bpos;
+      if (out.f.on && bpos >= 0) write_fields(out.f, part, rs, size_t(node), bpos);
     }
   }
 }
@@ -962,6 +1033,7 @@ Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, c
   if (bshift < 0) bshift = 0;
   if (bshift > 31) bshift = 31;
   while (bshift < 31 && ((ncells + (uint64_t(1) << bshift) - 1) >> bshift) > kMaxBuckets) ++bshift;
+  g.hxf = float(g.hx); g.hyf = float(g.hy); g.hzf = float(g.hz);
   g.bshift = bshift;
   g.nb = uint32_t((ncells + (uint64_t(1) << bshift) - 1) >> bshift);
   if (g.nb < 1) g.nb = 1;
@@ -973,10 +1045,10 @@ size_t vp_scan_scratch_bytes_local(int64_t m) { return vp_align256(size_t((m + 4
 struct NNScratch {
   size_t rec1, spos, tab, hist, sums, tail, total;
 };
-NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint32_t nb, int64_t nnodes) {
+NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint32_t nb, int64_t nnodes, bool own_srec = true) {
   NNScratch s;
   s.rec1 = vp_align256(size_t(np) * (pay ? sizeof(Rec32) : sizeof(RecA)));
-  s.spos = vp_align256(size_t(np) * sizeof(rec_t) + 256);
+  s.spos = own_srec ? vp_align256(size_t(np) * (pay ? 2 : 1) * sizeof(rec_t) + 256) : 256;   // (with a payload the caller may supply this array)
   s.tab = vp_align256((ncells + 8) * 4);
   s.hist = 2 * vp_align256((size_t(nb) * kSub + 1) * 4);          // (bucket, sub-stream) histogram and cursors
   s.sums = vp_scan_scratch_bytes_local(int64_t(ncells) + 1);
@@ -986,15 +1058,16 @@ NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint32_t nb, int64_t
   return s;
 }
 
-// Optional payload travelling with the particles (whole-path use): sorted (v', m) records and the sorted position of every
-// node's nearest particle, so that the field kernel reads the payload almost sequentially.
+// Optional payload travelling with the particles (whole-path use): sorted 32-byte records (search half + (v', m) half) and
+// the sorted position of every node's nearest particle, so that the field kernel reads the payload almost sequentially.
 template <typename T>
 struct NNPayload {
   const T* vel = nullptr;
   const T* rho = nullptr;
   double lcell3 = 1.0;
-  float4* spay_out = nullptr;    // [np] float4
-  int32_t* nn_pos_out = nullptr;  // [nnodes]
+  float4* srec_out = nullptr;    // [np] x 2 float4; null = scratch (only with fused field planes)
+  int32_t* nn_pos_out = nullptr;  // [nnodes]; may be null with fused field planes
+  FieldOut fo = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
 };
 
 template <typename T>
@@ -1005,7 +1078,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   VP_REQUIRE(nnodes < (int64_t(1) << 32), "vp_nn_grid: lattice too large for 32-bit node ids");
   VP_REQUIRE(np < (int64_t(1) << 31), "vp_nn_grid: np must be < 2^31 per device");
   const bool has_pay = pay != nullptr;
-  if (has_pay) VP_REQUIRE(pay->vel && pay->spay_out && pay->nn_pos_out, "vp_nn_grid: incomplete payload description");
+  if (has_pay) VP_REQUIRE(pay->vel && ((pay->srec_out && pay->nn_pos_out) || pay->fo.on), "vp_nn_grid: incomplete payload description");
   vp_nn_opts o;
   memset(&o, 0, sizeof o);
   if (opts) o = *opts;
@@ -1087,20 +1160,20 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   L.nx = nx; L.ny = ny; L.nz = nz;
 
   // ---- scratch
-  const NNScratch sc = nn_scratch(np, has_pay, ncells, g.nb, nnodes);
+  const NNScratch sc = nn_scratch(np, has_pay, ncells, g.nb, nnodes, !(has_pay && pay->srec_out));
   vp_arena_scope scope(ctx);
   VP_TRY(vp_arena_reserve(ctx, sc.total));
   void* rec1 = vp_arena_alloc(ctx, sc.tail);
-  rec_t* srec = static_cast<rec_t*>(vp_arena_alloc(ctx, sc.spos));
-  float4* spay = has_pay ? pay->spay_out : nullptr;
+  rec_t* srec_own = static_cast<rec_t*>(vp_arena_alloc(ctx, sc.spos));
+  rec_t* srec = (has_pay && pay->srec_out) ? reinterpret_cast<rec_t*>(pay->srec_out) : srec_own;
   uint32_t* xtab = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.tab));
   uint32_t* hist = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.hist));
   uint32_t* sums = static_cast<uint32_t*>(vp_arena_alloc(ctx, sc.sums));
-  VP_REQUIRE(rec1 && srec && xtab && hist && sums, "vp_nn_grid: arena carve failed");
+  VP_REQUIRE(rec1 && srec_own && xtab && hist && sums, "vp_nn_grid: arena carve failed");
   uint32_t* cursor = hist + vp_align256((size_t(g.nb) * kSub + 1) * 4) / 4;
   uint32_t* node_list = static_cast<uint32_t*>(rec1);                                           // -> exact kernel
   uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> wider stage
-  const int rs = 1;                   // float4 stride of the sorted search records
+  const int rs = has_pay ? 2 : 1;     // float4 stride of the sorted records
 
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
   VP_CUDA(cudaMemsetAsync(xtab, 0, (ncells + 8) * 4, st));
@@ -1111,6 +1184,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   if (np > 0) {
     const double es = sizeof(T);
     const size_t hsmem = size_t(g.nb) * kSub * 4, ssmem = size_t(g.nb) * 4;
+    // thread-block clusters claiming one run per bucket together: measured 55 ms against 26 ms without (four cluster-wide
+    // barriers per tile with one 1024-thread CTA per SM), kept behind a switch
+    const bool use_clusters = getenv("VP_SCATTER_CLUSTERS") != nullptr;
     static bool attr_done = false;
     if (!attr_done) {
       VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
@@ -1119,7 +1195,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     }
     auto launch_hist = [&](const T* p, int64_t n_c, int64_t i0) {
       const int64_t nt = (n_c + kBinTile - 1) / kBinTile, cap = int64_t(ctx->sm_count) * 4;
-      k_bin_hist<T><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % kSub));
+      k_bin_hist<T><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
     };
     auto launch_scatter = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
@@ -1127,13 +1203,20 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       pin.rho = r;
       pin.lcell3 = T(has_pay ? pay->lcell3 : 1.0);
       const unsigned nbk = unsigned((n_c + kBinTile - 1) / kBinTile);
-      if (has_pay) k_bin_scatter<T, true><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, uint32_t((i0 / kBinTile) % kSub), rec1);
-      else k_bin_scatter<T, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, uint32_t((i0 / kBinTile) % kSub), rec1);
+      const uint32_t t0 = uint32_t((i0 / kBinTile) % (kSub * kClu));
+      if (use_clusters) {
+        const unsigned nbc = (nbk + kClu - 1) / kClu * kClu;      // whole clusters; the surplus CTAs only take part in the syncs
+        if (has_pay) k_bin_scatter_clu<T, true><<<nbc, 1024, 2 * ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+        else k_bin_scatter_clu<T, false><<<nbc, 1024, 2 * ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+      } else {
+        if (has_pay) k_bin_scatter<T, true><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+        else k_bin_scatter<T, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+      }
     };
     if (host_pos) {
       // positions arrive from the host in chunks (copy stream); the histogram of chunk c is taken while chunk c+1 moves
       VP_REQUIRE(!has_pay && o.row_stride == 0 && !o.use_x_keep, "vp_nn_grid: host position streaming is the plain compact form");
-      VP_REQUIRE(host_pos->chunk % kBinTile == 0 || host_pos->chunk >= np, "vp_nn_grid: host chunks must hold whole tiles");
+      VP_REQUIRE(host_pos->chunk % (kBinTile * kClu) == 0 || host_pos->chunk >= np, "vp_nn_grid: host chunks must hold whole cluster tiles");
       VP_TRY(vp_host_streams(ctx));
       const int64_t chunk = host_pos->chunk;
       T* posd = const_cast<T*>(pos);
@@ -1174,8 +1257,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       pg.sx = float(g.hx / 2097152.0); pg.sy = float(g.hy / 2097152.0); pg.sz = float(g.hz / 2097152.0);
       pg.hz = float(g.hz);
       pg.gz = uint32_t(gz);
-      if (has_pay) k_cell_place<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec, spay);
-      else k_cell_place<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec, nullptr);
+      if (has_pay) k_cell_place<true><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec);
+      else k_cell_place<false><<<nbk, 256, 0, st>>>(rec1, ctx->nn_stats_d, tab, pg, srec);
     }
     VP_CHECK_LAUNCH();
   }
@@ -1185,10 +1268,11 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   const float eps = 2e-5f * hmax;
   SearchOut so;
   so.nn = nn; so.nn_pos = nn_pos; so.list_b = list_b; so.list_c = node_list; so.stats = ctx->nn_stats_d;
+  so.f = has_pay ? pay->fo : FieldOut{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   {
     // sorted records read once + cell starts read once + one index written per node
-    vp_stage stage(ctx, brick ? "k1f_search_brick" : "k1f_search_rows_plus", st, 1,
-                   double(np) * 16.0 + double(ncells) * 4.0 + double(nnodes) * 4.0);
+    vp_stage stage(ctx, brick ? "k1f_search_brick" : "k1f_search_rows", st, 1,
+                   double(np) * (has_pay ? 32.0 : 16.0) + double(ncells) * 4.0 + double(nnodes) * 4.0);
     if (brick) {
       dim3 grid((nz + kBZ - 1) / kBZ, (ny + kBY - 1) / kBY, (nx + kBX - 1) / kBX);
       VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
@@ -1200,20 +1284,31 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       k_search_brick<<<grid, 256, kBrickSmem, st>>>(srec, rs, start, g, L, eps, so);
     } else {
       // block = (z nodes, y rows), one x plane per blockIdx.z: no integer division in the kernel
-      int bx = nz >= 256 ? 256 : ((nz + 31) / 32) * 32;
-      int by = 256 / bx;
+      // A warp = 32 consecutive z nodes; the 8 warps of a CTA take 8 consecutive y rows, so that the cell rows two
+      // neighbouring node rows share are fetched into the SM's L1 once (9 cell rows instead of 16 per CTA).
+      int bx = 32, by = 8;
+      if (const char* ev = getenv("VP_SEARCH_BLOCK")) { bx = atoi(ev); if (bx < 32 || bx > 256 || (bx & (bx - 1))) bx = 32; by = 256 / bx; }
+      if (nz > 32 && ny < by) { bx = 256; by = 1; }
       dim3 block(bx, by, 1), grid((nz + bx - 1) / bx, (ny + by - 1) / by, nx);
       VP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "vp_nn_grid: lattice too large for the search launch");
-      k_search_rows<<<grid, block, 0, st>>>(srec, rs, start, g, L, eps, so);
+      // 40 registers without spills (6 CTAs per SM) or 32 with 28 bytes of spills (8 CTAs per SM)
+      static const bool occ8 = getenv("VP_SEARCH_OCC6") == nullptr;   // measured: 39.6 ms (8 CTAs/SM) vs 44.0 ms (6)
+      if (rs == 2) {
+        if (occ8) k_search_rows<2, 8><<<grid, block, 0, st>>>(srec, start, g, L, eps, so);
+        else k_search_rows<2, 6><<<grid, block, 0, st>>>(srec, start, g, L, eps, so);
+      } else {
+        if (occ8) k_search_rows<1, 8><<<grid, block, 0, st>>>(srec, start, g, L, eps, so);
+        else k_search_rows<1, 6><<<grid, block, 0, st>>>(srec, start, g, L, eps, so);
+      }
     }
   }
-  if (brick) {   // (k_search_rows settles its unproven nodes itself, warp-cooperatively)
+  {
     vp_stage stage(ctx, "k1g_search_block4", st, 1);
     k_search_block4<<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
   }
   {
     vp_stage stage(ctx, "k1h_search_exact", st, 1);
-    k_search_exact<T><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, pos, g, L, nn, nn_pos, node_list, ctx->nn_stats_d);
+    k_search_exact<T><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, pos, g, L, so);
   }
   VP_CHECK_LAUNCH();
   return VP_OK;
@@ -1227,7 +1322,7 @@ int nn_payload_typed(vp_ctx* ctx, const void* pos, const void* vel, const void* 
   pay.vel = static_cast<const T*>(vel);
   pay.rho = static_cast<const T*>(rho);
   pay.lcell3 = lcell3;
-  pay.spay_out = reinterpret_cast<float4*>(spay);
+  pay.srec_out = reinterpret_cast<float4*>(spay);
   pay.nn_pos_out = nn_pos;
   return nn_grid_typed<T>(ctx, static_cast<const T*>(pos), np, qx, nx, qy, ny, qz, nz, nn_idx, &pay, opts, st);
 }
@@ -1653,9 +1748,39 @@ extern "C" int vp_nn_grid_payload(vp_ctx* ctx, const void* pos_d, const void* ve
   return VP_ERR_ARG;
 }
 
+// K1 + K3 in one call: the search stages write the requested field planes themselves (no nn_pos / record round trip).
+extern "C" int vp_nn_grid_fields(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
+                                 const double* qx_h, int nx, const double* qy_h, int ny, const double* qz_h, int nz, double lcell3,
+                                 float* const v_d[3], float* const p_d[3], float* e_d, float* m_d, int32_t* nn_idx_d,
+                                 const vp_nn_opts* opts, void* stream) {
+  VP_REQUIRE(ctx && pos_d && vel_d && qx_h && qy_h && qz_h, "vp_nn_grid_fields: null argument");
+  VP_REQUIRE(np >= 0 && nx > 0 && ny > 0 && nz > 0, "vp_nn_grid_fields: bad sizes");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
+  VP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FieldOut fo;
+  fo.vx = v_d ? v_d[0] : nullptr; fo.vy = v_d ? v_d[1] : nullptr; fo.vz = v_d ? v_d[2] : nullptr;
+  fo.px = p_d ? p_d[0] : nullptr; fo.py = p_d ? p_d[1] : nullptr; fo.pz = p_d ? p_d[2] : nullptr;
+  fo.e = e_d; fo.m = m_d;
+  fo.on = (fo.vx || fo.vy || fo.vz || fo.px || fo.py || fo.pz || fo.e || fo.m) ? 1 : 0;
+  VP_REQUIRE(fo.on, "vp_nn_grid_fields: no plane requested");
+  if (dtype == VP_F32) {
+    NNPayload<float> pay;
+    pay.vel = static_cast<const float*>(vel_d); pay.rho = static_cast<const float*>(rho_d); pay.lcell3 = lcell3; pay.fo = fo;
+    return nn_grid_typed<float>(ctx, static_cast<const float*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, &pay, opts, st);
+  }
+  if (dtype == VP_F64) {
+    NNPayload<double> pay;
+    pay.vel = static_cast<const double*>(vel_d); pay.rho = static_cast<const double*>(rho_d); pay.lcell3 = lcell3; pay.fo = fo;
+    return nn_grid_typed<double>(ctx, static_cast<const double*>(pos_d), np, qx_h, nx, qy_h, ny, qz_h, nz, nn_idx_d, &pay, opts, st);
+  }
+  vp_set_error("vp_nn_grid_fields: unknown dtype %d", dtype);
+  return VP_ERR_ARG;
+}
+
 extern "C" int vp_fields_sorted(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, float* const v_d[3],
                                 float* const p_d[3], float* e_d, float* m_d, void* stream) {
-  return vp_fields_from_records(ctx, nn_pos_d, n_nodes, spay_d, 1, 0, v_d, p_d, e_d, m_d, static_cast<cudaStream_t>(stream));
+  return vp_fields_from_records(ctx, nn_pos_d, n_nodes, spay_d, 2, 1, v_d, p_d, e_d, m_d, static_cast<cudaStream_t>(stream));
 }
 
 int vp_fields_from_records(vp_ctx* ctx, const int32_t* nn_pos_d, int64_t n_nodes, const float* spay_d, int stride, int offset,
@@ -1719,6 +1844,17 @@ extern "C" int vp_nn_grid_stats(vp_ctx* ctx, int64_t* n_wide, int64_t* n_unresol
   if (n_wide) *n_wide = int64_t(h.n_wide);
   if (n_unresolved) *n_unresolved = int64_t(h.n_unresolved);
   if (n_kept) *n_kept = int64_t(h.n_kept);
+  return VP_OK;
+}
+
+extern "C" int vp_nn_grid_stats_ex(vp_ctx* ctx, int64_t* out5, void* stream) {
+  VP_REQUIRE(ctx && out5, "vp_nn_grid_stats_ex: null argument");
+  vp_call_guard guard(ctx, static_cast<cudaStream_t>(stream));
+  vp_nn_stats_dev h;
+  VP_CUDA(cudaMemcpyAsync(&h, ctx->nn_stats_d, sizeof h, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  VP_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  out5[0] = int64_t(h.n_wide); out5[1] = int64_t(h.n_unresolved); out5[2] = int64_t(h.n_kept); out5[3] = int64_t(h.n_b);
+  out5[4] = int64_t(h.n_far);
   return VP_OK;
 }
 

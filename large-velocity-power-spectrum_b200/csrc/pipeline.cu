@@ -65,7 +65,7 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   const int64_t chunk = np < (int64_t(1) << 24) ? np : (int64_t(1) << 24);
   size_t own = 0;
   if (on_host) own += vp_align256(size_t(np) * 3 * es) + vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 1024;
-  own += vp_align256(n3 * 4) * (1 + nplanes) + vp_align256(size_t(np) * 16) + vp_align256(size_t(nbins) * 16) + 8192;
+  own += vp_align256(n3 * 4) * ((on_host ? 1 : 0) + nplanes) + (on_host ? vp_align256(size_t(np) * 16) : 0) + vp_align256(size_t(nbins) * 16) + 8192;
   size_t inner = vp_nn_grid_scratch_bytes_tables(np, dtype, qx, N, qy, N, qz, N, nullptr);
   size_t inner2 = vp_pk_fields_scratch_bytes(plan);
   vp_arena_scope scope(ctx);
@@ -77,8 +77,8 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
     pos_res = vp_arena_alloc(ctx, size_t(np) * 3 * es);
     VP_REQUIRE(pos_res, "particles_to_pk: arena carve failed");
   }
-  int32_t* nn_pos = static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4));
-  float* spay = static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * 16));   // (v', m) records: input order (host path) or cell order (device path)
+  int32_t* nn_pos = on_host ? static_cast<int32_t*>(vp_arena_alloc(ctx, n3 * 4)) : nullptr;
+  float* spay = on_host ? static_cast<float*>(vp_arena_alloc(ctx, size_t(np) * 16)) : nullptr;   // host path: (v', m) records in input order
   float* planes[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < nplanes; ++i) {
     planes[i] = static_cast<float*>(vp_arena_alloc(ctx, n3 * 4));
@@ -86,13 +86,18 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
   }
   double* psum_d = static_cast<double*>(vp_arena_alloc(ctx, size_t(nbins) * 8));
   uint64_t* ns_d = static_cast<uint64_t*>(vp_arena_alloc(ctx, size_t(nbins) * 8));
-  VP_REQUIRE(nn_pos && spay && psum_d && ns_d, "particles_to_pk: arena carve failed");
+  VP_REQUIRE((!on_host || (nn_pos && spay)) && psum_d && ns_d, "particles_to_pk: arena carve failed");
 
+  int at = 0;
+  float *v3[3] = {nullptr, nullptr, nullptr}, *p3[3] = {nullptr, nullptr, nullptr}, *e1 = nullptr;
+  if (want_v) { v3[0] = planes[at++]; v3[1] = planes[at++]; v3[2] = planes[at++]; }
+  if (want_p) { p3[0] = planes[at++]; if (!strict) { p3[1] = planes[at++]; p3[2] = planes[at++]; } }
+  if (want_e) e1 = planes[at++];
   if (on_host) {
-    // Host arrays: the positions cross PCIe first and the whole gridding (keys as the chunks land, sort, search) runs
-    // while velocity and density follow; those are packed chunk by chunk into (v', m) records in INPUT order on a side
-    // stream, and the planes are gathered through the ORIGINAL particle index (nn_pos / spay then hold that index and
-    // those records).  Only the plane gather and the transforms remain after the last byte has arrived.
+    // Host arrays: the positions cross PCIe first and the whole gridding (bucket pass as the chunks land, counting sort,
+    // search) runs while velocity and density follow; those are packed chunk by chunk into (v', m) records in INPUT order
+    // on a side stream, and the planes are gathered through the ORIGINAL particle index (nn_pos / spay then hold that index
+    // and those records).  Only the plane gather and the transforms remain after the last byte has arrived.
     vp_host_chunks hc;
     hc.pos_h = pos; hc.vel_h = vel; hc.rho_h = rho; hc.chunk = chunk;
     void* staging = vp_arena_alloc(ctx, vp_host_chunk_staging_bytes(chunk, dtype, rho != nullptr) + 512);
@@ -101,16 +106,11 @@ static int run_path(vp_ctx* ctx, const void* pos, const void* vel, const void* r
     VP_TRY(vp_host_fork(ctx, st));
     VP_TRY(vp_nn_grid_host_pos(ctx, &hc, pos_res, dtype, np, qx, N, qy, N, qz, N, nn_pos, st));
     VP_TRY(vp_pack_payload_host(ctx, &hc, dtype, np, lcell3, staging, spay, st));
+    VP_TRY(vp_fields_from_records(ctx, nn_pos, int64_t(n3), spay, 1, 0, v3, p3, e1, nullptr, st));
   } else {
-    VP_TRY(vp_nn_grid_payload(ctx, pos_d, vel_d, rho_d, dtype, np, qx, N, qy, N, qz, N, lcell3, nullptr, nn_pos, spay, nullptr, st));
+    // device arrays: the search stages write the planes themselves (K3 fused into K1)
+    VP_TRY(vp_nn_grid_fields(ctx, pos_d, vel_d, rho_d, dtype, np, qx, N, qy, N, qz, N, lcell3, v3, p3, e1, nullptr, nullptr, nullptr, st));
   }
-
-  int at = 0;
-  float *v3[3] = {nullptr, nullptr, nullptr}, *p3[3] = {nullptr, nullptr, nullptr}, *e1 = nullptr;
-  if (want_v) { v3[0] = planes[at++]; v3[1] = planes[at++]; v3[2] = planes[at++]; }
-  if (want_p) { p3[0] = planes[at++]; if (!strict) { p3[1] = planes[at++]; p3[2] = planes[at++]; } }
-  if (want_e) e1 = planes[at++];
-  VP_TRY(vp_fields_from_records(ctx, nn_pos, int64_t(n3), spay, 1, 0, v3, p3, e1, nullptr, st));
 
   std::vector<double> hp(nbins);
   auto one = [&](float** f, int nc, double scale, int row) -> int {

@@ -44,8 +44,11 @@ SIGNATURES = {
     "vp_launch_count": (C.c_ulonglong, [_P]),
     "vp_nn_grid": (_I, [_P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _P, C.POINTER(NNOpts), _P]),
     "vp_nn_grid_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _P]),
+    "vp_nn_grid_stats_ex": (_I, [_P, C.POINTER(_L), _P]),
     "vp_nn_grid_plan": (_I, [_L, _dp, _I, _dp, _I, _dp, _I, C.POINTER(NNOpts), C.POINTER(_L)]),
     "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
+    "vp_nn_grid_fields": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P,
+                               C.POINTER(NNOpts), _P]),
     "vp_fields_sorted": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
     "vp_slab_bucket": (_I, [_P, _P, _P, _P, _I, _L, _dp, _dp, _I, _P, _L, C.POINTER(_L), _P]),
     "vp_slab_p2p_close": (_I, [_P]),
@@ -288,7 +291,8 @@ class SlabExchangeP2P:
 
 
 def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts: NNOpts | None = None):
-    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, spay[np,4] f32 in cell order).
+    """K1 with the payload sorted alongside: -> (nn_idx or None, nn_pos, srec[np,8] f32 = the cell-sorted 32-byte records:
+    floats 0..3 the search half, floats 4..7 the payload (v'x, v'y, v'z, m)).
     With opts.row_stride > 0 the three tensors are column views of one interleaved row tensor."""
     torch = _torch()
     assert pos_t.is_cuda and vel_t.dtype == pos_t.dtype
@@ -300,13 +304,45 @@ def nn_grid_payload(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_idx=True, opts
     shape = (len(qx_a), len(qy_a), len(qz_a))
     nn_idx = torch.empty(shape, dtype=torch.int32, device=pos_t.device) if want_idx else None
     nn_pos = torch.empty(shape, dtype=torch.int32, device=pos_t.device)
-    spay = torch.empty((pos_t.shape[0], 4), dtype=torch.float32, device=pos_t.device)
+    spay = torch.empty((pos_t.shape[0], 8), dtype=torch.float32, device=pos_t.device)
     _check(load_library().vp_nn_grid_payload(
         ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()), _P(rho_t.data_ptr()) if rho_t is not None else None,
         _dtype_code(pos_t), pos_t.shape[0], qx_p, shape[0], qy_p, shape[1], qz_p, shape[2], float(lcell3),
         _P(nn_idx.data_ptr()) if want_idx else None, _P(nn_pos.data_ptr()), _P(spay.data_ptr()),
         C.byref(opts) if opts is not None else None, stream_ptr()))
     return nn_idx, nn_pos, spay
+
+
+def nn_grid_fields(pos_t, vel_t, rho_t, qx, qy, qz, lcell3, want_v=True, want_p=(False, False, False), want_e=False,
+                   want_m=False, want_idx=False, opts: NNOpts | None = None):
+    """K1 + K3 fused: -> (dict of float32 CUDA cubes vx,vy,vz,px,py,pz,e,m as requested, nn_idx or None)."""
+    torch = _torch()
+    assert pos_t.is_cuda and vel_t.dtype == pos_t.dtype
+    if opts is None or opts.row_stride == 0:
+        assert pos_t.is_contiguous() and vel_t.is_contiguous()
+    qx_a, qx_p = _as_dp(qx)
+    qy_a, qy_p = _as_dp(qy)
+    qz_a, qz_p = _as_dp(qz)
+    shape = (len(qx_a), len(qy_a), len(qz_a))
+    out = {}
+
+    def cube(name, on):
+        if on:
+            out[name] = torch.empty(shape, dtype=torch.float32, device=pos_t.device)
+            return out[name].data_ptr()
+        return None
+
+    v = (_P * 3)(*[cube(nm, want_v) for nm in ("vx", "vy", "vz")])
+    p = (_P * 3)(*[cube(nm, on) for nm, on in zip(("px", "py", "pz"), want_p)])
+    e = cube("e", want_e)
+    m = cube("m", want_m)
+    nn_idx = torch.empty(shape, dtype=torch.int32, device=pos_t.device) if want_idx else None
+    _check(load_library().vp_nn_grid_fields(
+        ctx(), _P(pos_t.data_ptr()), _P(vel_t.data_ptr()), _P(rho_t.data_ptr()) if rho_t is not None else None,
+        _dtype_code(pos_t), pos_t.shape[0], qx_p, shape[0], qy_p, shape[1], qz_p, shape[2], float(lcell3), v, p,
+        _P(e) if e else None, _P(m) if m else None, _P(nn_idx.data_ptr()) if want_idx else None,
+        C.byref(opts) if opts is not None else None, stream_ptr()))
+    return out, nn_idx
 
 
 def fields_sorted(nn_pos_t, spay_t, want_v=True, want_p=(False, False, False), want_e=False, want_m=False):
@@ -343,9 +379,9 @@ def nn_grid_plan(np_particles, qx, qy, qz, opts: NNOpts | None = None):
 
 
 def nn_grid_stats():
-    a, b, c = _L(), _L(), _L()
-    _check(load_library().vp_nn_grid_stats(ctx(), C.byref(a), C.byref(b), C.byref(c), stream_ptr()))
-    return {"n_wide": a.value, "n_unresolved": b.value, "n_kept": c.value}
+    o = (_L * 5)()
+    _check(load_library().vp_nn_grid_stats_ex(ctx(), o, stream_ptr()))
+    return {"n_wide": int(o[0]), "n_unresolved": int(o[1]), "n_kept": int(o[2]), "n_stage_b": int(o[3]), "n_far": int(o[4])}
 
 
 def gather_rows(idx_t, src_t):

@@ -64,6 +64,28 @@ class CudaBackend:
         st = _lib.nn_grid_stats()
         return (nn_pos, spay), st["n_unresolved"]
 
+    def grid_slab_fields(self, pos, vel, rho, ax_loc, ax, lcell3, keep, quantities, strict):
+        """Gridding of the slab with the field planes written by the search itself (vp_nn_grid_fields).
+        -> ({quantity: (planes, multiplicity)}, number of unproven nodes)."""
+        lo, hi, open_lo, open_hi = keep
+        o = _lib.NNOpts()
+        o.use_x_keep = 1
+        o.x_keep_lo, o.x_keep_hi = float(lo), float(hi)
+        o.x_lo_is_domain_edge, o.x_hi_is_domain_edge = int(open_lo), int(open_hi)
+        if pos.stride(0) != 3:          # column views of the interleaved rows that came out of the particle exchange
+            o.row_stride = int(pos.stride(0))
+        want_p = (True, not strict, not strict) if "momentum" in quantities else (False, False, False)
+        f, _ = _lib.nn_grid_fields(pos, vel, rho, ax_loc, ax, ax, lcell3, want_v="velocity" in quantities, want_p=want_p,
+                                   want_e="energy" in quantities, opts=o)
+        out = {}
+        if "velocity" in quantities:
+            out["velocity"] = ([f["vx"], f["vy"], f["vz"]], 1.0)
+        if "momentum" in quantities:
+            out["momentum"] = ([f["px"]], 3.0) if strict else ([f["px"], f["py"], f["pz"]], 1.0)
+        if "energy" in quantities:
+            out["energy"] = ([f["e"]], 1.0)
+        return out, _lib.nn_grid_stats()["n_unresolved"]
+
     def bucket(self, pos, vel, rho, lo, hi):
         return _lib.slab_bucket(pos, vel, rho, lo, hi)
 
@@ -177,8 +199,14 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
         if sharded and nranks > 1:
             pos, vel, rho = exchange_particles(*shard, ax, nranks, rank, halo, group, backend)
         mark("exchange_particles")
-        gridded, unresolved = backend.grid_slab(pos, vel, rho, ax[x0:x1], ax, lcell3,
-                                                keep_range(ax, x0, x1, nranks, rank, halo))
+        if hasattr(backend, "grid_slab_fields"):       # the search writes the planes itself
+            gridded = None
+            planes, unresolved = backend.grid_slab_fields(pos, vel, rho, ax[x0:x1], ax, lcell3,
+                                                          keep_range(ax, x0, x1, nranks, rank, halo), quantities, momentum_strict)
+        else:
+            planes = None
+            gridded, unresolved = backend.grid_slab(pos, vel, rho, ax[x0:x1], ax, lcell3,
+                                                    keep_range(ax, x0, x1, nranks, rank, halo))
         mark("grid_slab")
         flag = torch.tensor([int(unresolved > 0)], dtype=torch.int64, device=_device_of(pos))
         if nranks > 1:
@@ -193,7 +221,8 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
 
     out = {}
     ns_total = None
-    planes = backend.fields_all(gridded, quantities, momentum_strict) if hasattr(backend, "fields_all") else None
+    if planes is None and hasattr(backend, "fields_all"):
+        planes = backend.fields_all(gridded, quantities, momentum_strict)
     for q in quantities:
         slabs, mult = planes.pop(q) if planes is not None else backend.fields(gridded, q, momentum_strict)
         if getattr(backend, "p2p", False):

@@ -90,7 +90,8 @@ def test_nn_vs_oracle(lib, orc, dtype, Np, N, clustered):
     ref, ties = orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax, return_ties=True)
     nn = lib.nn_grid(lib.to_device(pos), ax, ax, ax).cpu().numpy()
     assert np.array_equal(nn, ref)                       # ties included: both sides pick the lowest index
-    assert lib.nn_grid_stats()["n_unresolved"] == 0
+    st = lib.nn_grid_stats()
+    assert st["n_unresolved"] == 0 and st["n_far"] == 0  # every particle lies inside the cell grid of a lattice covering the box
 
 
 def test_nn_script_lattice_and_ties(lib, orc):
@@ -751,3 +752,45 @@ def test_nn_full_size_spot_check(lib, orc):
         bad += int(best != got)
     assert bad == 0
     assert R < 20 * h
+
+
+@pytest.mark.parametrize("Np,N,clustered", [(1 << 18, 64, False), (40 ** 3, 40, True), (5000, 48, False)])
+def test_fused_gridding_fields_equals_two_step(lib, orc, Np, N, clustered):
+    """vp_nn_grid_fields (the search stages write the planes) == vp_nn_grid_payload + vp_fields_sorted == the oracle's
+    gather, bit for bit, and the indices it returns are the oracle's."""
+    pos, vel, dens, _ = orc.synth_particles(5, Np, 1.0, clustered=clustered, lattice_n=40 if clustered else None)
+    ax = orc.lattice_axis_lib(1.0, N)
+    lc3 = (1.0 / N) ** 3
+    dp, dv, dr = lib.to_device(pos), lib.to_device(vel), lib.to_device(dens)
+    f1, nn = lib.nn_grid_fields(dp, dv, dr, ax, ax, ax, lc3, want_v=True, want_p=(True, True, True), want_e=True, want_m=True,
+                                want_idx=True)
+    _, nn_pos, srec = lib.nn_grid_payload(dp, dv, dr, ax, ax, ax, lc3)
+    f2 = lib.fields_sorted(nn_pos, srec, want_v=True, want_p=(True, True, True), want_e=True, want_m=True)
+    ref = orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax)
+    assert np.array_equal(nn.cpu().numpy(), ref)
+    for k in f2:
+        assert np.array_equal(f1[k].cpu().numpy(), f2[k].cpu().numpy()), k
+    v32 = (vel * dens[:, None]) / dens[:, None]
+    assert np.array_equal(f1["vx"].cpu().numpy(), v32[ref, 0]) and np.array_equal(f1["m"].cpu().numpy(), (dens * np.float32(lc3))[ref])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_snapshot_preamble_on_device(lib, vp, orc, dtype):
+    """shift_to_origin / remove_bulk_velocity as device reductions (vp_snapshot_preamble) vs the reference's numpy
+    expressions (interp.py:169-182): the shift is exact, the bulk velocity agrees to the rounding of the summation order."""
+    import torch
+    pos, vel, dens, _ = orc.synth_particles(9, 100003, 1.0)
+    mass = (1.0 + orc.hash_uniform(9, 100003, 11)).astype(dtype)
+    pos, vel = (pos + 0.37).astype(dtype), (vel + 0.25).astype(dtype)
+    gp_ref = vp.interp.GasParticles(pos.copy(), mass.copy(), dens.astype(dtype), vel.copy(), 1.0)
+    gp_ref.remove_bulk_velocity()
+    gp_ref.shift_to_origin()
+    gp = vp.interp.GasParticles(lib.to_device(pos), lib.to_device(mass), lib.to_device(dens.astype(dtype)), lib.to_device(vel), 1.0)
+    gp.remove_bulk_velocity()
+    gp.shift_to_origin()
+    assert np.array_equal(gp.pos.cpu().numpy(), gp_ref.pos)                       # minimum and subtraction are exact
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    assert np.max(np.abs(gp.v.cpu().numpy() - gp_ref.v)) < tol * np.max(np.abs(vel))
+    bf = gp.ann_interp_to_field(16)                                               # device-resident particles are gridded in place
+    ax = orc.lattice_axis_lib(1.0, 16)
+    assert np.array_equal(bf._dev["nn"].cpu().numpy(), orc.nn_exact_lattice(gp_ref.pos.astype(np.float64), ax, ax, ax))
