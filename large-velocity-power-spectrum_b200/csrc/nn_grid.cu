@@ -530,33 +530,31 @@ __device__ __forceinline__ void scan_zcells(const rec_t* __restrict__ part, int 
 // version carrying the wider stage inline needed 64 registers and ran 2.2x slower.
 template <int RS, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_search_rows(const rec_t* __restrict__ part, const uint32_t* __restrict__ start, Grid g,
-                                                         Lattice L, float eps, SearchOut out) {
-  // block = (z nodes, y rows); grid = (z chunks, y chunks, x)
+                                                            Lattice L, float eps, SearchOut out) {
+  // block = (z nodes, y rows); grid = (z chunks, y chunks, x).  32-bit cell and node arithmetic (both counts are < 2^32).
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int i = blockIdx.z;
   if (k >= L.nz || j >= L.ny) return;
-  const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-  const int wx = __ldg(L.wx + i), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
+  const uint32_t node = (uint32_t(blockIdx.z) * uint32_t(L.ny) + uint32_t(j)) * uint32_t(L.nz) + uint32_t(k);
+  const int wx = __ldg(L.wx + blockIdx.z), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
   if (out.stats->n_far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
-    out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+    out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = node;
     return;
   }
-  const int z1 = min(wz + 1, g.gz - 1);
-  const bool cross = (wz & 31) == 31 && z1 > wz;
+  const bool cross = (wz & 31) == 31 && wz + 1 < g.gz;
   uint32_t rs0[4], re0[4];
   {
-    const int zl = cross ? wz : z1;               // last cell of the first run
+    const uint32_t zl = uint32_t(cross ? wz : min(wz + 1, g.gz - 1)) + 1u;   // one past the last cell of the first run
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int X = wx + (r >> 1), Y = wy + (r & 1);
       const bool in = X < g.gx && Y < g.gy;
-      const size_t row = in ? (size_t(X) * g.gy + Y) * g.gz : 0;
-      rs0[r] = in ? __ldg(start + row + wz) : 0u;
-      re0[r] = in ? __ldg(start + row + zl + 1) : 0u;
+      const uint32_t row = in ? (uint32_t(X) * uint32_t(g.gy) + uint32_t(Y)) * uint32_t(g.gz) : 0u;
+      rs0[r] = in ? __ldg(start + row + uint32_t(wz)) : 0u;
+      re0[r] = in ? __ldg(start + row + zl) : 0u;
     }
   }
-  const float rx = __ldg(L.rx + i), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
+  const float rx = __ldg(L.rx + blockIdx.z), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
   Cand c;
   c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
   {
@@ -564,17 +562,16 @@ __global__ void __launch_bounds__(256, MINB) k_search_rows(const rec_t* __restri
 #pragma unroll
     for (int r = 0; r < 4; ++r) scan_range(part, RS, rs0[r], re0[r], rx - float(r >> 1) * g.hxf, ry - float(r & 1) * g.hyf, qz0, c);
   }
-  if (cross) {
+  if (cross) {   // (one lane in 32) cell wz + 1 opens a new 32-cell block: its records have another z reference
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
       const int X = wx + (r >> 1), Y = wy + (r & 1);
       if (X >= g.gx || Y >= g.gy) continue;
-      const size_t row = (size_t(X) * g.gy + Y) * g.gz;
-      scan_range(part, RS, __ldg(start + row + wz + 1), __ldg(start + row + z1 + 1), rx - float(r >> 1) * g.hxf, ry - float(r & 1) * g.hyf,
-                 rz - g.hzf, c);
+      const uint32_t row = (uint32_t(X) * uint32_t(g.gy) + uint32_t(Y)) * uint32_t(g.gz) + uint32_t(wz);
+      scan_range(part, RS, __ldg(start + row + 1), __ldg(start + row + 2), rx - float(r >> 1) * g.hxf, ry - float(r & 1) * g.hyf, rz - g.hzf, c);
     }
   }
-  const float m = fminf(__ldg(L.mx + i), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
+  const float m = fminf(__ldg(L.mx + blockIdx.z), fminf(__ldg(L.my + j), __ldg(L.mz + k)));
   emit(out, part, RS, node, judge(c, eps, m), c.bi);
 }
 
@@ -1355,81 +1352,89 @@ __global__ void __launch_bounds__(256) k_bucket_count(const T* __restrict__ pos,
 struct SlabDest {
   void* base[16];   // all equal for the local form; peer-mapped receive buffers for the fused exchange
 };
-// 512 particles per block.  Every block claims one contiguous row range per destination (one global atomic each),
-// stages its rows in shared memory grouped by destination and writes each group out as one coalesced run -- 128-byte
-// store instructions whether the destination is local HBM or a peer's buffer over NVLink.
-constexpr int kBktItems = 2;
-// staged rows per block (a particle inside a halo goes to two ranks); overflow -> direct stores
-template <typename T> struct BktCap { static constexpr int v = sizeof(T) == 4 ? 1024 : 768; };
-template <typename T>
-__global__ void __launch_bounds__(256) k_bucket_scatter(const T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ rho,
+// Tiles of 512 x ITEMS particles per CTA (2048 for f32).  Pass 1: which destinations take each particle (one ballot per
+// destination and item; only the per-warp counts are kept).  Then ONE contiguous row range is claimed per destination
+// (one global atomic each) and the same ballots are formed again to place every row in shared memory, grouped by
+// destination; each group leaves as one coalesced run -- 128-byte store instructions whether the destination is local
+// HBM or a peer's buffer over NVLink.  Rows that do not fit the staging area (very wide halos) are stored directly.
+template <typename T> struct SlabTile { static constexpr int items = sizeof(T) == 4 ? 4 : 2; };
+template <typename T, int W>
+__global__ void __launch_bounds__(512) k_bucket_scatter(const T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ rho,
                                                          int64_t np, SlabRanges R, unsigned long long* __restrict__ cursors,
-                                                         SlabDest D, int w) {
-  __shared__ unsigned sc[16];             // rows of this block per destination
-  __shared__ unsigned pre[17];            // exclusive prefix of sc
+                                                         SlabDest D, int cap_rows) {
+  constexpr int ITEMS = SlabTile<T>::items;
+  constexpr int w = W;
+  extern __shared__ __align__(16) unsigned char slab_smem[];
+  T* stage = reinterpret_cast<T*>(slab_smem);            // [cap_rows][w]
+  __shared__ unsigned wcnt[ITEMS][16][16];                 // [item][warp][destination]: count, then first staged row
+  __shared__ unsigned pre[17];                             // exclusive prefix of the rows per destination
   __shared__ unsigned long long sbase[16];
-  constexpr int kBktCap = BktCap<T>::v;
-  __shared__ T stage[kBktCap * 7];
-  if (threadIdx.x < 16) sc[threadIdx.x] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t i0 = int64_t(blockIdx.x) * (256 * kBktItems);
-  unsigned myoff[kBktItems][16];
-  bool okv[kBktItems];
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int64_t i0 = int64_t(blockIdx.x) * (512 * ITEMS);
+  double x[ITEMS];
+  bool okv[ITEMS];
 #pragma unroll
-  for (int r = 0; r < kBktItems; ++r) {
-    const int64_t i = i0 + r * 256 + threadIdx.x;
+  for (int r = 0; r < ITEMS; ++r) {
+    const int64_t i = i0 + r * 512 + tid;
     okv[r] = i < np;
-    const double x = okv[r] ? double(pos[3 * i]) : 0.0;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      myoff[r][d] = 0xffffffffu;
-      if (d < R.n) {
-        const bool in = okv[r] && x >= R.lo[d] && x <= R.hi[d];
-        const unsigned m = __ballot_sync(0xffffffffu, in);
-        unsigned wb = 0;
-        if (lane == 0 && m) wb = atomicAdd(&sc[d], __popc(m));
-        wb = __shfl_sync(0xffffffffu, wb, 0);
-        if (in) myoff[r][d] = wb + __popc(m & ((1u << lane) - 1u));
-      }
+    x[r] = okv[r] ? double(pos[3 * i]) : 0.0;
+    for (int d = 0; d < R.n; ++d) {
+      const unsigned m = __ballot_sync(0xffffffffu, okv[r] && x[r] >= R.lo[d] && x[r] <= R.hi[d]);
+      if (lane == 0) wcnt[r][wp][d] = __popc(m);
     }
   }
   __syncthreads();
-  if (threadIdx.x < R.n) sbase[threadIdx.x] = sc[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, (unsigned long long)sc[threadIdx.x]) : 0ull;
-  if (threadIdx.x == 0) {
+  if (tid < R.n) {
+    unsigned run = 0;
+    for (int r = 0; r < ITEMS; ++r)
+      for (int q = 0; q < 16; ++q) {
+        const unsigned c = wcnt[r][q][tid];
+        wcnt[r][q][tid] = run;
+        run += c;
+      }
+    pre[tid + 1] = run;                                  // (count; turned into the prefix below)
+    sbase[tid] = run ? atomicAdd(cursors + tid, (unsigned long long)run) : 0ull;
+  }
+  __syncthreads();
+  if (tid == 0) {
     unsigned a = 0;
-    for (int d = 0; d < R.n; ++d) { pre[d] = a; a += sc[d]; }
-    for (int d = R.n; d <= 16; ++d) pre[d] = a;
+    pre[0] = 0;
+    for (int d = 0; d < R.n; ++d) { a += pre[d + 1]; pre[d + 1] = a; }
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kBktItems; ++r) {
-    if (!okv[r]) continue;
-    const int64_t i = i0 + r * 256 + threadIdx.x;
+  for (int r = 0; r < ITEMS; ++r) {
+    const int64_t i = i0 + r * 512 + tid;
     T row[7];
-    row[0] = pos[3 * i]; row[1] = pos[3 * i + 1]; row[2] = pos[3 * i + 2];
-    row[3] = vel[3 * i]; row[4] = vel[3 * i + 1]; row[5] = vel[3 * i + 2];
-    row[6] = rho ? rho[i] : T(0);
+    if (okv[r]) {
+      row[0] = pos[3 * i]; row[1] = pos[3 * i + 1]; row[2] = pos[3 * i + 2];
+      row[3] = vel[3 * i]; row[4] = vel[3 * i + 1]; row[5] = vel[3 * i + 2];
+      row[6] = rho ? rho[i] : T(0);
+    }
+    for (int d = 0; d < R.n; ++d) {
+      const bool in = okv[r] && x[r] >= R.lo[d] && x[r] <= R.hi[d];
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const unsigned rank = wcnt[r][wp][d] + __popc(m & ((1u << lane) - 1u));
+        const unsigned p = pre[d] + rank;
+        if (p < unsigned(cap_rows)) {
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      if (d < R.n && myoff[r][d] != 0xffffffffu) {
-        const unsigned p = pre[d] + myoff[r][d];
-        if (p < unsigned(kBktCap)) {
-          for (int c = 0; c < w; ++c) stage[p * w + c] = row[c];
-        } else {   // staging area full (very wide halos): store directly
-          T* o = static_cast<T*>(D.base[d]) + (sbase[d] + myoff[r][d]) * size_t(w);
-          for (int c = 0; c < w; ++c) o[c] = row[c];
+          for (int c = 0; c < W; ++c) stage[p * W + c] = row[c];
+        } else {   // staging area full: store directly
+          T* o = static_cast<T*>(D.base[d]) + (sbase[d] + rank) * size_t(w);
+#pragma unroll
+          for (int c = 0; c < W; ++c) o[c] = row[c];
         }
       }
     }
   }
   __syncthreads();
-  const unsigned tot = min(pre[16], unsigned(kBktCap));
-  int d = 0;
-  for (unsigned f = threadIdx.x; f < tot * unsigned(w); f += 256) {
-    const unsigned rr = f / unsigned(w), c = f - rr * unsigned(w);
-    while (rr >= pre[d + 1]) ++d;                  // f only grows: the destination index is monotone per thread
-    static_cast<T*>(D.base[d])[(sbase[d] + (rr - pre[d])) * size_t(w) + c] = stage[f];
+  for (int d = 0; d < R.n; ++d) {
+    const unsigned r0 = min(pre[d], unsigned(cap_rows)), r1 = min(pre[d + 1], unsigned(cap_rows));
+    const T* src = stage + size_t(r0) * w;
+    T* dst = static_cast<T*>(D.base[d]) + (sbase[d] + (r0 - pre[d])) * size_t(w);
+    const unsigned nel = (r1 - r0) * unsigned(w);
+    for (unsigned e = tid; e < nel; e += 512) dst[e] = src[e];
   }
 }
 
@@ -1466,7 +1471,17 @@ int slab_bucket_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int
     vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * w * sizeof(T) + double(total) * w * sizeof(T));
     SlabDest D;
     for (int d = 0; d < 16; ++d) D.base[d] = rows;
-    k_bucket_scatter<T><<<unsigned((np + 256 * kBktItems - 1) / (256 * kBktItems)), 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
+    constexpr int kTile = 512 * SlabTile<T>::items;
+    const int cap_rows = kTile + kTile / 4;                 // a particle inside a halo goes to two ranks
+    const size_t smem = size_t(cap_rows) * 7 * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      attr = true;
+    }
+    if (w == 7) k_bucket_scatter<T, 7><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
+    else k_bucket_scatter<T, 6><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
   }
   VP_CHECK_LAUNCH();
   VP_CUDA(cudaStreamSynchronize(st));   // cnt/cur live in the scope released on return
@@ -1506,7 +1521,17 @@ int slab_scatter_p2p_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho
     vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * 2.0 * w * sizeof(T));
     SlabDest D;
     for (int d = 0; d < 16; ++d) D.base[d] = d < R.n ? ctx->slab_peer[d] : nullptr;
-    k_bucket_scatter<T><<<unsigned((np + 256 * kBktItems - 1) / (256 * kBktItems)), 256, 0, st>>>(pos, vel, rho, np, R, cur, D, w);
+    constexpr int kTile = 512 * SlabTile<T>::items;
+    const int cap_rows = kTile + kTile / 4;                 // a particle inside a halo goes to two ranks
+    const size_t smem = size_t(cap_rows) * 7 * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      attr = true;
+    }
+    if (w == 7) k_bucket_scatter<T, 7><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
+    else k_bucket_scatter<T, 6><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
     VP_CHECK_LAUNCH();
   }
   VP_CUDA(cudaStreamSynchronize(st));   // cur lives in the scope released on return

@@ -243,7 +243,7 @@ class SlabExchangeP2P:
         import torch.distributed as dist
         if need_bytes <= self.cap_bytes:
             return
-        cap = int(need_bytes * 1.15) + (1 << 20)
+        cap = int(need_bytes * (1.15 if need_bytes < (8 << 30) else 1.03)) + (1 << 20)
         # an exported buffer may only be freed once no peer maps it any more: unmap everywhere, barrier, then re-allocate
         _check(load_library().vp_slab_p2p_close(ctx()))
         dist.barrier(group=self.group)

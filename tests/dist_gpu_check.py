@@ -50,6 +50,7 @@ def main():
                 np.allclose(o[q], out[q], rtol=1e-12) for o in (out_p, out_p2) for q in qs)
             print(f"N={N} world={world}: fused peer-store transpose and particle exchange == NCCL paths: {same_p}", flush=True)
             ok &= same_p
+        be.close()                                                    # collective: unmap peers, barrier, free
         del be
         if rank == 0:
             same_s = np.array_equal(ns_s, ns) and all(np.allclose(out_s[q], out[q], rtol=1e-12) for q in qs)
