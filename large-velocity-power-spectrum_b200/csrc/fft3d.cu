@@ -42,28 +42,28 @@ struct vp_pk_plan {
 namespace {
 
 // ------------------------------------------------------------------ z pass: N reals -> N/2 packed complex
-template <int R2, int R3>
+template <int R1, int R2, int R3>
 __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const float2* __restrict__ tw_half,
                                                const float2* __restrict__ tw_full) {
-  using F = LineFFT<R2, R3, 1>;
+  using F = LineFFT<R1, R2, R3, 1>;
   constexpr int L = F::L, T = F::T, LINES = 256 / T, XS = xsize<L, 1>();
   extern __shared__ float2 sm[];
   const int tid = threadIdx.x, ll = tid / T, t = tid % T;
   float2* g = reinterpret_cast<float2*>(data) + (size_t(blockIdx.x) * LINES + ll) * L;
   float2* s = sm + ll * XS;
-  float2 v[16];
+  float2 v[F::P];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = g[j * T + t];
+  for (int j = 0; j < F::P; ++j) v[j] = g[j * T + t];
   F::run(v, t, s, tw_half);
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) s[F::kout(j, t)] = v[j];
+  for (int j = 0; j < F::P; ++j) s[F::kout(j, t)] = v[j];
   __syncthreads();
   for (int k = t; k <= L / 2; k += T) {
     if (k == 0) {
       float2 z0 = s[0];
       g[0] = make_float2(z0.x + z0.y, z0.x - z0.y);  // (X[0], X[N/2]) packed
-    } else if (k == L / 2) {
+    } else if (L % 2 == 0 && k == L / 2) {
       g[k] = cconj(s[k]);
     } else {
       float2 zk = s[k], zc = cconj(s[L - k]);
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) k_fft_z(float* __restrict__ data, const f
 //   peer-to-peer      : base[d] = rank d's receive buffer mapped through CUDA IPC, xoff = rank*N/nranks, blocked --
 //                       the blocks are stored over NVLink where the x pass of rank d will read them
 //   diagnostics       : base[0] = the field itself, row-major, in place (a CTA writes where it read)
-constexpr int kYB = 16;   // ky per block of the blocked layout
+template <int L>
+__host__ __device__ constexpr int yb_of() { return L % 16 == 0 ? 16 : 10; }   // ky per block of the blocked layout (divides L)
 struct YDest {
   float2* base[16];
   int xoff;
@@ -99,19 +100,19 @@ struct YDest {
   int nxtot;    // x planes of the destination array (N)
 };
 
-template <int R2, int R3, int C>
+template <int R1, int R2, int R3, int C>
 __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_y(const float2* __restrict__ data, YDest dst, int NZ, int kzc,
                                                                                    const float2* __restrict__ tw) {
-  using F = LineFFT<R2, R3, C>;
-  constexpr int L = F::L, T = F::T;
+  using F = LineFFT<R1, R2, R3, C>;
+  constexpr int L = F::L, T = F::T, kYB = yb_of<L>();
   extern __shared__ float2 sm[];
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
   const int tiles = NZ / C;
   const int x = blockIdx.x / tiles, zt = blockIdx.x % tiles;
   const float2* base = data + size_t(x) * L * NZ + zt * C + c;
-  float2 v[16];
+  float2 v[F::P];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * NZ];
+  for (int j = 0; j < F::P; ++j) v[j] = base[size_t(j * T + t) * NZ];
   F::run(v, t, sm + c, tw);
   const int kz0 = zt * C, d = kz0 / kzc;
   if (dst.blocked) {
@@ -119,14 +120,14 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
     float2* ob = dst.base[d] + ((size_t(dst.xoff) + x) * tiles_r + (kz0 - d * kzc) / C) * (kYB * C) + c;
     const size_t blk = size_t(dst.nxtot) * tiles_r * (kYB * C);      // one ky block of all x
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < F::P; ++j) {
       const int ky = F::kout(j, t);
       ob[size_t(ky / kYB) * blk + (ky % kYB) * C] = v[j];
     }
   } else {
     float2* ob = dst.base[d] + (size_t(dst.xoff) + x) * L * kzc + (kz0 - d * kzc) + c;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ob[size_t(F::kout(j, t)) * kzc] = v[j];
+    for (int j = 0; j < F::P; ++j) ob[size_t(F::kout(j, t)) * kzc] = v[j];
   }
 }
 
@@ -145,12 +146,12 @@ struct FieldSet {
 template <int L>
 __host__ __device__ constexpr int nrp_of() { return ((L / 2 + 1) + 31) / 32 * 32; }
 
-template <int R2, int R3, int C>
+template <int R1, int R2, int R3, int C>
 __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_x_pow(FieldSet fs, int NZ, const float2* __restrict__ tw,
                                                                                        float2* __restrict__ plane0, int kz_offset,
                                                                                        float* __restrict__ P) {
-  using F = LineFFT<R2, R3, C>;
-  constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1, NRP = nrp_of<L>();
+  using F = LineFFT<R1, R2, R3, C>;
+  constexpr int L = F::L, T = F::T, NT = T * C, XS = xsize<L, C>(), PP = L + 4, NR = L / 2 + 1, NRP = nrp_of<L>(), kYB = yb_of<L>();
   extern __shared__ float2 sm[];                                   // exchange area
   float* pt = reinterpret_cast<float*>(sm + XS);                   // [C][PP] sum over components of |F|^2
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
@@ -161,23 +162,23 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   const size_t tile_off = fs.blocked ? (size_t(ky / kYB) * L * tiles_z + zt) * (kYB * C) + (ky % kYB) * C : size_t(ky) * NZ + size_t(zt) * C;
   for (int comp = 0; comp < fs.n; ++comp) {
     const float2* base = fs.f[comp] + tile_off + c;
-    float2 v[16];
+    float2 v[F::P];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+    for (int j = 0; j < F::P; ++j) v[j] = base[size_t(j * T + t) * xstride];
     if (comp) __syncthreads();  // previous component's last exchange reads are done
     F::run(v, t, sm + c, tw);
     if (kz_offset + zt * C + c == 0) {
       float2* pl = plane0 + (size_t(comp) * L + ky) * L;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pl[F::kout(j, t)] = v[j];
+      for (int j = 0; j < F::P; ++j) pl[F::kout(j, t)] = v[j];
     }
     float* col = pt + c * PP;
     if (comp == 0) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) col[F::kout(j, t)] = v[j].x * v[j].x + v[j].y * v[j].y;
+      for (int j = 0; j < F::P; ++j) col[F::kout(j, t)] = v[j].x * v[j].x + v[j].y * v[j].y;
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) col[F::kout(j, t)] += v[j].x * v[j].x + v[j].y * v[j].y;   // same thread, same slots
+      for (int j = 0; j < F::P; ++j) col[F::kout(j, t)] += v[j].x * v[j].x + v[j].y * v[j].y;   // same thread, same slots
     }
   }
   __syncthreads();
@@ -385,38 +386,38 @@ __global__ void k_expand_power(const float2* __restrict__ packed, int N, double*
 }
 
 // ------------------------------------------------------------------ launch helpers
-template <int R2, int R3>
+template <int R1, int R2, int R3>
 int launch_z(float* data, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
-  using F = LineFFT<R2, R3, 1>;
+  using F = LineFFT<R1, R2, R3, 1>;
   constexpr int LINES = 256 / F::T;
   VP_REQUIRE((size_t(nx) * N) % LINES == 0, "fft z pass: %d x %d lines is not a multiple of %d", nx, N, LINES);
   size_t smem = size_t(LINES) * xsize<F::L, 1>() * sizeof(float2);
   static bool attr = false;
-  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_z<R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_z<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
   size_t nlines = size_t(nx) * N;
   vp_stage stage(pl->ctx, "k4a_fft_z", st, 1, 8.0 * double(nx) * N * N);   // 4 B/real read + 4 B/real written in place
-  k_fft_z<R2, R3><<<unsigned(nlines / LINES), 256, smem, st>>>(data, pl->tw_half, pl->tw_full);
+  k_fft_z<R1, R2, R3><<<unsigned(nlines / LINES), LINES * F::T, smem, st>>>(data, pl->tw_half, pl->tw_full);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
 
-template <int R2, int R3, int C>
+template <int R1, int R2, int R3, int C>
 int launch_y(const float2* data, const YDest& dst, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
-  using F = LineFFT<R2, R3, C>;
+  using F = LineFFT<R1, R2, R3, C>;
   size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2);
   static bool attr = false;
-  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_y<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_y<R1, R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
   const int NZ = N / 2;
   VP_REQUIRE(kzc % C == 0, "fft y pass: %d columns per rank is not a multiple of the tile width %d", kzc, C);
   vp_stage stage(pl->ctx, "k4b_fft_y", st, 1, 8.0 * double(nx) * N * N);   // 8 B/mode read + written, nx*N*N/2 modes
-  k_fft_y<R2, R3, C><<<unsigned(nx * (NZ / C)), F::T * C, smem, st>>>(data, dst, NZ, kzc, pl->tw_full);
+  k_fft_y<R1, R2, R3, C><<<unsigned(nx * (NZ / C)), F::T * C, smem, st>>>(data, dst, NZ, kzc, pl->tw_full);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
 
-template <int R2, int R3, int C>
+template <int R1, int R2, int R3, int C>
 int launch_x_pow(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
-  using F = LineFFT<R2, R3, C>;
+  using F = LineFFT<R1, R2, R3, C>;
   constexpr int NT = F::T * C, NRP = nrp_of<F::L>();
   vp_ctx* ctx = pl->ctx;
   VP_REQUIRE(NZ % C == 0, "fft x pass: %d columns is not a multiple of the tile width %d", NZ, C);
@@ -428,11 +429,11 @@ int launch_x_pow(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, doub
   VP_REQUIRE(P, "fft x pass: arena carve failed");
   const size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2) + size_t(C) * (F::L + 4) * sizeof(float);
   static bool attr = false;
-  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x_pow<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x_pow<R1, R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
   {
     // 8 B/mode read per component, the folded power tile written (4 B per pair of modes)
     vp_stage stage(ctx, "k4c_fft_x_pow", st, 1, 8.0 * double(N) * N * NZ * fs.n + 4.0 * double(N) * NZ * (N / 2 + 1));
-    k_fft_x_pow<R2, R3, C><<<ntiles, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->plane0, kz_offset, P);
+    k_fft_x_pow<R1, R2, R3, C><<<ntiles, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->plane0, kz_offset, P);
     VP_CHECK_LAUNCH();
   }
   // binning: per-warp f64 accumulators in shared memory
@@ -475,24 +476,30 @@ int launch_x_pow(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, doub
 
 int run_z(float* d, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_z<2, 1>(d, N, nx, pl, st);
-    case 128: return launch_z<4, 1>(d, N, nx, pl, st);
-    case 256: return launch_z<8, 1>(d, N, nx, pl, st);
-    case 512: return launch_z<16, 1>(d, N, nx, pl, st);
-    case 1024: return launch_z<16, 2>(d, N, nx, pl, st);
-    case 2048: return launch_z<16, 4>(d, N, nx, pl, st);
+    case 64: return launch_z<16, 2, 1>(d, N, nx, pl, st);
+    case 128: return launch_z<16, 4, 1>(d, N, nx, pl, st);
+    case 256: return launch_z<16, 8, 1>(d, N, nx, pl, st);
+    case 512: return launch_z<16, 16, 1>(d, N, nx, pl, st);
+    case 1024: return launch_z<16, 16, 2>(d, N, nx, pl, st);
+    case 2048: return launch_z<16, 16, 4>(d, N, nx, pl, st);
+    case 250: return launch_z<5, 5, 5>(d, N, nx, pl, st);      // half length 125
+    case 500: return launch_z<10, 5, 5>(d, N, nx, pl, st);     // 250
+    case 1000: return launch_z<10, 10, 5>(d, N, nx, pl, st);   // 500
   }
   vp_set_error("fft z pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
 }
 int run_y(const float2* d, const YDest& dst, int N, int nx, int kzc, const vp_pk_plan* pl, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_y<4, 1, 32>(d, dst, N, nx, kzc, pl, st);
-    case 128: return launch_y<8, 1, 32>(d, dst, N, nx, kzc, pl, st);
-    case 256: return launch_y<16, 1, 16>(d, dst, N, nx, kzc, pl, st);
-    case 512: return launch_y<16, 2, 8>(d, dst, N, nx, kzc, pl, st);
-    case 1024: return launch_y<16, 4, 8>(d, dst, N, nx, kzc, pl, st);
-    case 2048: return launch_y<16, 8, 8>(d, dst, N, nx, kzc, pl, st);
+    case 64: return launch_y<16, 4, 1, 32>(d, dst, N, nx, kzc, pl, st);
+    case 128: return launch_y<16, 8, 1, 32>(d, dst, N, nx, kzc, pl, st);
+    case 256: return launch_y<16, 16, 1, 16>(d, dst, N, nx, kzc, pl, st);
+    case 512: return launch_y<16, 16, 2, 8>(d, dst, N, nx, kzc, pl, st);
+    case 1024: return launch_y<16, 16, 4, 8>(d, dst, N, nx, kzc, pl, st);
+    case 2048: return launch_y<16, 16, 8, 8>(d, dst, N, nx, kzc, pl, st);
+    case 250: return launch_y<10, 5, 5, 5>(d, dst, N, nx, kzc, pl, st);
+    case 500: return launch_y<10, 10, 5, 10>(d, dst, N, nx, kzc, pl, st);
+    case 1000: return launch_y<10, 10, 10, 10>(d, dst, N, nx, kzc, pl, st);
   }
   vp_set_error("fft y pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
@@ -510,12 +517,15 @@ YDest ydest_blocks(float2* out, int nranks, int nx, int N, int kzc) {
 // overwritten with the mode counts of this rank's tiles.
 int run_x_bin(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, double* psum, unsigned long long* cnt, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_x_pow<4, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 128: return launch_x_pow<8, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 256: return launch_x_pow<16, 1, 16>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 512: return launch_x_pow<16, 2, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 1024: return launch_x_pow<16, 4, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
-    case 2048: return launch_x_pow<16, 8, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 64: return launch_x_pow<16, 4, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 128: return launch_x_pow<16, 8, 1, 32>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 256: return launch_x_pow<16, 16, 1, 16>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 512: return launch_x_pow<16, 16, 2, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 1024: return launch_x_pow<16, 16, 4, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 2048: return launch_x_pow<16, 16, 8, 8>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 250: return launch_x_pow<10, 5, 5, 5>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 500: return launch_x_pow<10, 10, 5, 10>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
+    case 1000: return launch_x_pow<10, 10, 10, 10>(fs, N, NZ, kz_offset, pl, psum, cnt, st);
   }
   vp_set_error("fft x pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
@@ -523,9 +533,9 @@ int run_x_bin(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, double*
 
 // the x pass without binning (diagnostic transform): reuse the y kernel on a transposed view is not possible
 // in place, so the diagnostic transform runs the x lines with the generic strided kernel below.
-template <int R2, int R3, int C>
+template <int R1, int R2, int R3, int C>
 __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft_x(float2* __restrict__ data, int NZ, const float2* __restrict__ tw) {
-  using F = LineFFT<R2, R3, C>;
+  using F = LineFFT<R1, R2, R3, C>;
   constexpr int L = F::L, T = F::T;
   extern __shared__ float2 sm[];
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
@@ -533,33 +543,36 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   const int y = blockIdx.x / tiles, zt = blockIdx.x % tiles;
   const size_t xstride = size_t(L) * NZ;
   float2* base = data + size_t(y) * NZ + zt * C + c;
-  float2 v[16];
+  float2 v[F::P];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = base[size_t(j * T + t) * xstride];
+  for (int j = 0; j < F::P; ++j) v[j] = base[size_t(j * T + t) * xstride];
   F::run(v, t, sm + c, tw);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) base[size_t(F::kout(j, t)) * xstride] = v[j];
+  for (int j = 0; j < F::P; ++j) base[size_t(F::kout(j, t)) * xstride] = v[j];
 }
-template <int R2, int R3, int C>
+template <int R1, int R2, int R3, int C>
 int launch_x(float2* data, int N, const vp_pk_plan* pl, cudaStream_t st) {
-  using F = LineFFT<R2, R3, C>;
+  using F = LineFFT<R1, R2, R3, C>;
   size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2);
   static bool attr = false;
-  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x<R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x<R1, R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
   const int NZ = N / 2;
   vp_stage stage(pl->ctx, "k4c_fft_x", st, 1, 8.0 * double(N) * N * N);
-  k_fft_x<R2, R3, C><<<unsigned(N * (NZ / C)), F::T * C, smem, st>>>(data, NZ, pl->tw_full);
+  k_fft_x<R1, R2, R3, C><<<unsigned(N * (NZ / C)), F::T * C, smem, st>>>(data, NZ, pl->tw_full);
   VP_CHECK_LAUNCH();
   return VP_OK;
 }
 int run_x(float2* d, int N, const vp_pk_plan* pl, cudaStream_t st) {
   switch (N) {
-    case 64: return launch_x<4, 1, 32>(d, N, pl, st);
-    case 128: return launch_x<8, 1, 32>(d, N, pl, st);
-    case 256: return launch_x<16, 1, 16>(d, N, pl, st);
-    case 512: return launch_x<16, 2, 8>(d, N, pl, st);
-    case 1024: return launch_x<16, 4, 8>(d, N, pl, st);
-    case 2048: return launch_x<16, 8, 8>(d, N, pl, st);
+    case 64: return launch_x<16, 4, 1, 32>(d, N, pl, st);
+    case 128: return launch_x<16, 8, 1, 32>(d, N, pl, st);
+    case 256: return launch_x<16, 16, 1, 16>(d, N, pl, st);
+    case 512: return launch_x<16, 16, 2, 8>(d, N, pl, st);
+    case 1024: return launch_x<16, 16, 4, 8>(d, N, pl, st);
+    case 2048: return launch_x<16, 16, 8, 8>(d, N, pl, st);
+    case 250: return launch_x<10, 5, 5, 5>(d, N, pl, st);
+    case 500: return launch_x<10, 10, 5, 10>(d, N, pl, st);
+    case 1000: return launch_x<10, 10, 10, 10>(d, N, pl, st);
   }
   vp_set_error("fft x pass: unsupported N=%d", N);
   return VP_ERR_UNSUPPORTED;
@@ -590,7 +603,9 @@ extern "C" int vp_pk_plan_create(vp_ctx* ctx, int N, const double* k_h, const do
   p->ctx = ctx;
   p->N = N;
   p->nbins = nbins;
-  bool is_pow2 = (N & (N - 1)) == 0 && N >= 64 && N <= 2048;
+  // lines with a register/shared-memory transform: powers of two 64..2048, and the 2^a 5^b sizes the reference is run at
+  // (scripts/parallel_optimized.py:30 NTOT = 1000; scripts/buffer_test.sh -N 500; 250 as their half)
+  bool is_pow2 = ((N & (N - 1)) == 0 && N >= 64 && N <= 2048) || N == 250 || N == 500 || N == 1000;
   // the fused binning folds kx <-> -kx: needs a symmetric k table (true for fftfreq; false with a fold shift)
   bool symmetric = true;
   for (int r = 1; r < N / 2; ++r)

@@ -1,13 +1,15 @@
 // Register-resident line FFT used by all three passes of the 3-D transform.
 //
-// A line of L = 16*R2*R3 complex points is transformed by T = L/16 threads, 16 points per thread:
-//   stage 1: radix-16 butterflies on points  j*T + t           (j = 0..15)       -> twiddle W_L^(t*k1)
-//   stage 2: radix-R2 butterflies, 16/R2 per thread                               -> twiddle W_L^(16*d3*k2)
-//   stage 3: radix-R3 butterflies, 16/R3 per thread (absent when R3 == 1)
+// A line of L = R1*R2*R3 complex points is transformed by T = L/R1 threads, R1 points per thread (R1 = 16 for the
+// power-of-two lines, 10 or 5 for the 2^a 5^b lines behind N = 250, 500, 1000; R2 and R3 divide R1):
+//   stage 1: radix-R1 butterflies on points  j*T + t           (j = 0..R1-1)     -> twiddle W_L^(t*k1)
+//   stage 2: radix-R2 butterflies, R1/R2 per thread                               -> twiddle W_L^(R1*d3*k2)
+//   stage 3: radix-R3 butterflies, R1/R3 per thread (absent when R3 == 1)
 // Stages exchange data through shared memory; the array index at every exchange is the mixed-radix
 // number (d1,d2,d3) = d1*T + d2*R3 + d3 whose digits are replaced n -> k stage by stage, so the final
-// register slot j of thread t holds output index  kout(j,t)  (see below).  The index maps are checked
-// against numpy in tests/test_fft_index_model.py.
+// register slot j of thread t holds output index  kout(j,t)  (see below).  The index maps, twiddles and kout are
+// restated in numpy and checked against numpy.fft for every instantiated radix combination in
+// tests/test_fft_index_model.py.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -96,6 +98,38 @@ __device__ __forceinline__ void dft<16>(float2* u) {
   }
 }
 
+template <>
+__device__ __forceinline__ void dft<5>(float2* u) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f, s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+  const float2 t1 = cadd(u[1], u[4]), t2 = cadd(u[2], u[3]), t3 = csub(u[1], u[4]), t4 = csub(u[2], u[3]);
+  const float2 a0 = u[0];
+  const float2 m1 = make_float2(a0.x + c1 * t1.x + c2 * t2.x, a0.y + c1 * t1.y + c2 * t2.y);
+  const float2 m2 = make_float2(a0.x + c2 * t1.x + c1 * t2.x, a0.y + c2 * t1.y + c1 * t2.y);
+  const float2 n1 = cmul_mi(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));   // -i (s1 t3 + s2 t4)
+  const float2 n2 = cmul_mi(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));   // -i (s2 t3 - s1 t4)
+  u[0] = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
+  u[1] = cadd(m1, n1);
+  u[4] = csub(m1, n1);
+  u[2] = cadd(m2, n2);
+  u[3] = csub(m2, n2);
+}
+template <>
+__device__ __forceinline__ void dft<10>(float2* u) {
+  // n = 2*n2 + n1: two 5-point transforms (even, odd inputs), X[k2] = E[k2] + W10^k2 O[k2], X[k2+5] = E[k2] - W10^k2 O[k2]
+  float2 e[5] = {u[0], u[2], u[4], u[6], u[8]}, o[5] = {u[1], u[3], u[5], u[7], u[9]};
+  dft<5>(e);
+  dft<5>(o);
+  o[1] = cmul(o[1], make_float2(0.80901699437494742410f, -0.58778525229247312917f));
+  o[2] = cmul(o[2], make_float2(0.30901699437494742410f, -0.95105651629515357212f));
+  o[3] = cmul(o[3], make_float2(-0.30901699437494742410f, -0.95105651629515357212f));
+  o[4] = cmul(o[4], make_float2(-0.80901699437494742410f, -0.58778525229247312917f));
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    u[k] = cadd(e[k], o[k]);
+    u[k + 5] = csub(e[k], o[k]);
+  }
+}
+
 // Shared-memory placement of exchange index `idx` (in float2 units, before the column/line offset).
 // A skew of one element per 16 keeps the strided stage-2/3 reads off a single bank group.
 template <int ISTRIDE>
@@ -107,27 +141,29 @@ __host__ __device__ constexpr int xsize() {  // float2 elements needed for one l
   return ISTRIDE == 1 ? L + (L >> 4) : L * ISTRIDE + 2 * (L >> 4);
 }
 
-template <int R2, int R3, int ISTRIDE>
+template <int R1, int R2, int R3, int ISTRIDE>
 struct LineFFT {
-  static constexpr int L = 16 * R2 * R3;
+  static constexpr int P = R1;            // points per thread
+  static constexpr int L = R1 * R2 * R3;
   static constexpr int T = R2 * R3;
-  static constexpr int M2 = 16 / R2;
-  static constexpr int M3 = R3 > 1 ? 16 / R3 : 16;
+  static constexpr int M2 = R1 / R2;
+  static constexpr int M3 = R3 > 1 ? R1 / R3 : R1;
+  static_assert(R1 % R2 == 0 && R1 % R3 == 0, "the later radices must divide the number of points per thread");
 
   // output index held in register slot j of thread t after run()
   __device__ __forceinline__ static int kout(int j, int t) {
-    if (R3 == 1) return (t * M2 + j / R2) + 16 * (j % R2);
-    return t + T * (j / R3) + 16 * R2 * (j % R3);
+    if (R3 == 1) return (t * M2 + j / R2) + R1 * (j % R2);
+    return t + T * (j / R3) + R1 * R2 * (j % R3);
   }
 
   // v[j] = x[j*T + t] on entry.  sm points at this line's (or this column's) exchange area.
   // tw = table of W_L^m, m in [0,L).  Every thread of the CTA must call this (it contains barriers).
-  __device__ __forceinline__ static void run(float2 (&v)[16], int t, float2* sm, const float2* __restrict__ tw) {
-    dft<16>(v);
+  __device__ __forceinline__ static void run(float2 (&v)[R1], int t, float2* sm, const float2* __restrict__ tw) {
+    dft<R1>(v);
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], __ldg(tw + t * k1));
+    for (int k1 = 1; k1 < R1; ++k1) v[k1] = cmul(v[k1], __ldg(tw + t * k1));
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) sm[xphys<ISTRIDE>(k1 * T + t)] = v[k1];
+    for (int k1 = 0; k1 < R1; ++k1) sm[xphys<ISTRIDE>(k1 * T + t)] = v[k1];
     __syncthreads();
 #pragma unroll
     for (int b = 0; b < M2; ++b) {
@@ -138,7 +174,7 @@ struct LineFFT {
       dft<R2>(u);
       if (R3 > 1) {
 #pragma unroll
-        for (int k2 = 1; k2 < R2; ++k2) u[k2] = cmul(u[k2], __ldg(tw + 16 * d3 * k2));
+        for (int k2 = 1; k2 < R2; ++k2) u[k2] = cmul(u[k2], __ldg(tw + R1 * d3 * k2));
       }
 #pragma unroll
       for (int a = 0; a < R2; ++a) v[a + R2 * b] = u[a];
@@ -154,7 +190,7 @@ struct LineFFT {
     __syncthreads();
 #pragma unroll
     for (int b = 0; b < M3; ++b) {
-      const int g = t + T * b, k1 = g % 16, k2 = g / 16;
+      const int g = t + T * b, k1 = g % R1, k2 = g / R1;
       float2 u[R3 > 1 ? R3 : 1];
 #pragma unroll
       for (int a = 0; a < R3; ++a) u[a] = sm[xphys<ISTRIDE>(k1 * T + k2 * R3 + a)];

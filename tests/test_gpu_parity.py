@@ -197,7 +197,7 @@ def test_fft_half_spectrum(lib, N):
 
 
 # ------------------------------------------------------------------------------------------ K4+K5 fused
-@pytest.mark.parametrize("N,L", [(64, 1.0), (128, 2.5), (256, 1.0), (48, 0.7), (16, 1.0)])
+@pytest.mark.parametrize("N,L", [(64, 1.0), (128, 2.5), (256, 1.0), (48, 0.7), (16, 1.0), (250, 0.7), (500, 1.0)])
 def test_pk_fields_vs_oracle(lib, orc, N, L):
     import torch
     rng = np.random.default_rng(100 + N)
@@ -794,3 +794,38 @@ def test_snapshot_preamble_on_device(lib, vp, orc, dtype):
     bf = gp.ann_interp_to_field(16)                                               # device-resident particles are gridded in place
     ax = orc.lattice_axis_lib(1.0, 16)
     assert np.array_equal(bf._dev["nn"].cpu().numpy(), orc.nn_exact_lattice(gp_ref.pos.astype(np.float64), ax, ax, ax))
+
+
+def test_fft_binning_N1000_reference_default(lib, orc):
+    """N = 1000, the reference MPI script's default NTOT (scripts/parallel_optimized.py:30), runs the mixed-radix line
+    transform (10 x 10 x 10 points; the z pass 10 x 10 x 5 on the half length), not a fallback: Parseval over all modes,
+    shells partitioning the N^3 modes (library edges: 500 shells; script edges: 499), exact linearity,
+    and a plane wave landing in its shell."""
+    import torch
+    N, L = 1000, 1.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30e9:
+        pytest.skip("needs ~20 GB of device memory")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.randn((N, N, N), generator=g, device="cuda", dtype=torch.float32)
+    f[:, :, ::2] += 0.5
+    want = float((f.double() ** 2).sum().item()) * N ** 3
+    k = orc.k_axis(L, N)
+    one = lib.PkPlan(N, k, np.array([0.0, 1e30]))
+    psum, ns = one.fields([f.clone()])
+    assert int(ns[0]) == N ** 3 and abs(psum[0] - want) / want < 1e-5
+    centres, edges = orc.edges_lib(2 * np.pi / L, np.pi * N / L, 2 * np.pi / L)
+    assert len(centres) == 500
+    plan = lib.PkPlan(N, k, edges)
+    p1, n1 = plan.fields([f.clone()])
+    p2, n2 = plan.fields([2.0 * f])
+    assert np.array_equal(n1, n2) and np.allclose(p2, 4.0 * p1, rtol=1e-13, atol=0)
+    import bench
+    assert np.array_equal(n1, bench.integer_shell_counts(N))
+    cs, es = orc.edges_script(2 * np.pi / L, np.pi * N / L, 2 * np.pi / L)
+    assert len(cs) == 499
+    x = (torch.arange(N, device="cuda", dtype=torch.float64) / N)
+    wave = torch.cos(2 * np.pi * (3 * x[:, None, None] + 5 * x[None, :, None] + 7 * x[None, None, :])).float()
+    pw, nw = plan.fields([wave])
+    j0 = int(np.floor(np.sqrt(9 + 25 + 49) + 0.5)) - 1
+    assert abs(pw[j0] / (float(N) ** 6 / 2) - 1) < 1e-5 and np.delete(pw, j0).sum() < 1e-6 * float(N) ** 6 / 2
