@@ -498,6 +498,19 @@ def main():
                "sample": f"{sN}^3 lattice / {sNp} particles, {'+'.join(quantities)}, oracle port (cKDTree workers=-1, scipy.fft workers=-1); "
                          f"nn {r['s_nn']:.2f}s spectra {r['s_spectra']:.2f}s"}
 
+    nvlink = None
+    if world > 1 and phase_t.get("nvlink_bytes"):
+        # bytes this rank stored into peer buffers (exact, from the exchange tables) over the device time of the kernels that
+        # store them; reference: 770 GB/s per direction measured for a peer copy on this pool (B200_PROFILING.md), 900 nominal.
+        # Hardware NVLink counters are not exposed in this container (profiles/r2_nvlink_counters_unavailable.txt).
+        nb = phase_t["nvlink_bytes"]
+        ex_ms = table.get("k0_slab_bucket_scatter", {}).get("ms_per_step")
+        y_ms = table.get("k4b_fft_y", {}).get("ms_per_step")
+        nvlink = {"rank0_bytes_per_step": nb, "peak_GBps": 770.0,
+                  "particle_exchange": {"ms": ex_ms, "GBps": round(nb["particle_exchange"] / ex_ms / 1e6, 1) if ex_ms else None,
+                                        "frac": round(nb["particle_exchange"] / ex_ms / 1e6 / 770.0, 3) if ex_ms else None},
+                  "transpose_in_y_pass": {"ms": y_ms, "GBps": round(nb["transpose"] / y_ms / 1e6, 1) if y_ms else None,
+                                          "frac": round(nb["transpose"] / y_ms / 1e6 / 770.0, 3) if y_ms else None}}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Gpart/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -508,7 +521,7 @@ def main():
                            "momentum": "reference-strict (vx*m x3)", "input": "sharded by particle index range across ranks"},
                 "result": digest, "nn_stats": nn_stats, "seconds_per_pk": ms * 1e-3, "nn_gridding_gpart_s": None,
                 "gpu_launches": int(launches), "peak_device_bytes_per_gpu": int(peak_mem),
-                "roofline": roof, "stages": table, "dist_phases_ms_last_step": phase_t.get("phases_ms"), "cpu_baseline": cpu, "e2e": e2e,
+                "nvlink": nvlink, "roofline": roof, "stages": table, "dist_phases_ms_last_step": phase_t.get("phases_ms"), "cpu_baseline": cpu, "e2e": e2e,
                 "clocks": clk.summary()}
         nn_ms = sum(table[n]["ms_per_step"] for n in table if n.startswith("k1"))
         if nn_ms > 0:

