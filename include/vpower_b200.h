@@ -261,6 +261,16 @@ int vp_power_bin_full(vp_pk_plan* plan, const double* P_d, double* psum_d, uint6
 /* Full power cube: P_d[N,N,N] (f64) = sum_c |FFT(field_c)|^2 over the whole c2c spectrum -- the array
  * _vector_power/_scalar_power return (interp.py:1372-1421) before the 1/2 a^2 factor.  Fields are overwritten. */
 int vp_power_cube(vp_pk_plan* plan, float* const* field_d, int ncomp, double* P_d, void* stream);
+/* Folding as an outer stage (the reference's way past the memory of one transform, and its sub-spectrum interchange format).
+ *   vp_fold_field : BoxField.fold (interp.py:598-609) = _apply_phase/_get_phase (:1195-1225) + fold_field (:1228-1252):
+ *                   folded_d[n,n,n,ncomp] complex128 (n = N/m) = sum over the m^3 sub-blocks of field_c * exp(-i 2 pi beta.x / N),
+ *                   divided by m^1.5.  field_d[c]: [N,N,N] f32, untouched.
+ *   vp_fold_power : the transform inside FoldedBox.fold_spctrm (interp.py:755-791, _FFTW_vector_power/_FFTW_scalar_power):
+ *                   P_d[n,n,n] (f64) = sum_c |FFT_n(folded_c)|^2 of the complex field, before the 1/2 a^2 factor.  The |k| pairing
+ *                   with the beta shift and the histogram are vp_k_magnitude + vp_hist_weighted. */
+int vp_fold_field(vp_ctx* ctx, const float* const* field_d, int ncomp, int N, int m, const int* beta /* [3] */, double* folded_d,
+                  void* stream);
+int vp_fold_power(vp_ctx* ctx, const double* folded_d, int ncomp, int n, double* P_d, void* stream);
 /* |k| of _pair_power (interp.py:1448-1460): out_d[(i*n+j)*n+l] = sqrt((kx[i]*kx[i] + ky[j]*ky[j]) + kz[l]*kz[l]), f64. */
 int vp_k_magnitude(vp_ctx* ctx, const double* kx_h, const double* ky_h, const double* kz_h, int n, double* out_d,
                    void* stream);

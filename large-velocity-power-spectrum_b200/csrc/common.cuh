@@ -53,6 +53,8 @@ struct vp_nn_stats_dev {
   unsigned long long n_kept;        // particles that survived the x filter
   unsigned long long n_b;           // nodes sent to the wider prefilter stage
   unsigned long long n_far;         // particles outside the cell grid (clamped into end cells)
+  unsigned long long n_crowded;     // bricks the particle-centric search handed to the node-centric kernel
+  unsigned long long crowded_cursor;  // work cursor of that kernel
 };
 
 // optional per-stage timing with CUDA events on the launching stream (vp_profile_enable / vp_profile_report)

@@ -333,15 +333,26 @@ k_bin_scatter_clu(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64
   cluster.sync();                               // rank 0's shared memory stays alive until every tile has read its claims
 }
 
-// per-cell counts: T[cell] += 1 (the records of one bucket are contiguous, so the counters in flight are L2 resident)
+// per-cell counts: T[cell] += 1 (the records of one bucket are contiguous, so the counters in flight are L2 resident).
+// kIlp records per thread, block-strided, so that a thread has several independent loads / atomics in flight (one record per
+// thread left the kernels latency bound: ncu 93 % long-scoreboard stalls at 80 % occupancy).
+constexpr int kIlp = 4;
 template <bool PAY>
 __global__ void __launch_bounds__(256) k_cell_count(const void* __restrict__ rec1, const vp_nn_stats_dev* __restrict__ stats,
                                                      uint32_t* __restrict__ tab) {
   const uint32_t n = uint32_t(stats->n_kept);
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t cell = PAY ? static_cast<const Rec32*>(rec1)[i].a.cell : static_cast<const RecA*>(rec1)[i].cell;
-  atomicAdd(tab + cell, 1u);
+  const uint32_t i0 = blockIdx.x * (256u * kIlp) + threadIdx.x;
+  if (i0 >= n) return;
+  uint32_t cell[kIlp];
+#pragma unroll
+  for (int u = 0; u < kIlp; ++u) {
+    const uint32_t i = i0 + u * 256u;
+    cell[u] = 0xffffffffu;
+    if (i < n) cell[u] = PAY ? static_cast<const Rec32*>(rec1)[i].a.cell : static_cast<const RecA*>(rec1)[i].cell;
+  }
+#pragma unroll
+  for (int u = 0; u < kIlp; ++u)
+    if (cell[u] != 0xffffffffu) atomicAdd(tab + cell[u], 1u);
 }
 
 // counting-sort placement: the record goes to (start of its cell) + (a slot handed out by the cell's cursor), rewritten in
@@ -355,29 +366,45 @@ template <bool PAY>
 __global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec1, vp_nn_stats_dev* __restrict__ stats,
                                                      uint32_t* __restrict__ tab, PlaceGeom pg, void* __restrict__ srec) {
   const uint32_t n = uint32_t(stats->n_kept);
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  if (i >= n) return;
-  uint32_t r[8];
-  if (PAY) {
-    ld256(static_cast<const Rec32*>(rec1) + i, r);
-  } else {
-    const uint4 v = static_cast<const uint4*>(rec1)[i];
-    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  const uint32_t i0 = blockIdx.x * (256u * kIlp) + threadIdx.x;
+  if (i0 >= n) return;
+  uint32_t r[kIlp][8], dst[kIlp];
+  bool on[kIlp];
+#pragma unroll
+  for (int u = 0; u < kIlp; ++u) {
+    const uint32_t i = i0 + u * 256u;
+    on[u] = i < n;
+    if (on[u]) {
+      if (PAY) {
+        ld256(static_cast<const Rec32*>(rec1) + i, r[u]);
+      } else {
+        const uint4 v = static_cast<const uint4*>(rec1)[i];
+        r[u][0] = v.x; r[u][1] = v.y; r[u][2] = v.z; r[u][3] = v.w;
+      }
+    }
   }
-  const uint32_t cell = r[2];
-  const uint32_t dst = atomicAdd(tab + cell, 1u);
-  const unsigned long long w = (unsigned long long)r[0] | ((unsigned long long)r[1] << 32);
-  const uint32_t fx = uint32_t(w) & kFixMax, fy = uint32_t(w >> kFixBits) & kFixMax, fz = uint32_t(w >> (2 * kFixBits)) & kFixMax;
-  const uint32_t cz = cell % pg.gz;
-  const float ux = (float(fx) + 0.5f) * pg.sx, uy = (float(fy) + 0.5f) * pg.sy;
-  const float uz = fmaf(float(cz & 31u), pg.hz, (float(fz) + 0.5f) * pg.sz);
-  if (r[3] & kFarBit) atomicAdd(&stats->n_far, 1ull);
-  // ONE 32-byte store per record: a whole sector.  (Writing the search half and the payload half to two arrays -- two
-  // scattered 16-byte partial-sector stores -- took 43.5 ms instead of 18.0 ms at 2^30 particles.)
-  if (PAY)
-    st256(static_cast<Rec32*>(srec) + dst, __float_as_uint(ux), __float_as_uint(uy), __float_as_uint(uz), r[3], r[4], r[5], r[6], r[7]);
-  else
-    static_cast<float4*>(srec)[dst] = make_float4(ux, uy, uz, __uint_as_float(r[3]));
+#pragma unroll
+  for (int u = 0; u < kIlp; ++u)
+    if (on[u]) dst[u] = atomicAdd(tab + r[u][2], 1u);
+  unsigned nfar = 0;
+#pragma unroll
+  for (int u = 0; u < kIlp; ++u) {
+    if (!on[u]) continue;
+    const unsigned long long w = (unsigned long long)r[u][0] | ((unsigned long long)r[u][1] << 32);
+    const uint32_t fx = uint32_t(w) & kFixMax, fy = uint32_t(w >> kFixBits) & kFixMax, fz = uint32_t(w >> (2 * kFixBits)) & kFixMax;
+    const uint32_t cz = r[u][2] % pg.gz;
+    const float ux = (float(fx) + 0.5f) * pg.sx, uy = (float(fy) + 0.5f) * pg.sy;
+    const float uz = fmaf(float(cz & 31u), pg.hz, (float(fz) + 0.5f) * pg.sz);
+    nfar += (r[u][3] & kFarBit) ? 1u : 0u;
+    // ONE 32-byte store per record: a whole sector.  (Writing the search half and the payload half to two arrays -- two
+    // scattered 16-byte partial-sector stores -- took 43.5 ms instead of 18.0 ms at 2^30 particles.)
+    if (PAY)
+      st256(static_cast<Rec32*>(srec) + dst[u], __float_as_uint(ux), __float_as_uint(uy), __float_as_uint(uz), r[u][3], r[u][4], r[u][5],
+            r[u][6], r[u][7]);
+    else
+      static_cast<float4*>(srec)[dst[u]] = make_float4(ux, uy, uz, __uint_as_float(r[u][3]));
+  }
+  if (nfar) atomicAdd(&stats->n_far, (unsigned long long)nfar);
 }
 
 __global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
@@ -490,6 +517,7 @@ struct SearchOut {
   int32_t* nn_pos;    // sorted position per node (may be null)
   uint32_t* list_b;   // nodes for the wider stage
   uint32_t* list_c;   // nodes for the exact stage
+  uint32_t* crowded;  // bricks for k_search_crowded
   vp_nn_stats_dev* stats;
   FieldOut f;
 };
@@ -575,43 +603,85 @@ __global__ void __launch_bounds__(256, MINB) k_search_rows(const rec_t* __restri
   emit(out, part, RS, node, judge(c, eps, m), c.bi);
 }
 
-// Stage A, brick form: the lattice windows are consecutive cells along every axis (node i <-> cells [w0+i, w0+i+1]) and
-// the z windows start on a multiple of 32.  One CTA = kBX x kBY x 32 nodes.  The particles of the covering
-// (kBX+1) x (kBY+1) rows x 33 cells are staged once in shared memory with their coordinates re-based to the low corner of
-// the brick's first cell; a thread then owns the node column (j, k) and walks i, keeping the cell ranges of the two rows it
-// shares with the next node in registers.
+// Stage A, brick form (particle-centric): the lattice windows are consecutive cells along every axis (node i <-> cells
+// [w0+i, w0+i+1]) and the z windows start on a multiple of 32.  One CTA = kBX x kBY x 32 nodes and the particles of the covering
+// (kBX+1) x (kBY+1) cell rows x 33 cells -- 81 contiguous runs of the sorted array.  The roles are turned round: instead of every
+// node walking its 8 cells (four Poisson-length loops per lane: a warp runs to its longest lane, ~3x the mean trip count, and
+// the kernel is issue bound), every PARTICLE visits the 8 nodes whose window contains its cell -- one lane per particle,
+// exactly 8 pairs each, no divergence, and the 8 squared distances cost 6 squares + 12 adds together.
+//
+// One sweep.  Per node one 32-bit word in shared memory:  key = (n << 13) | (slot << 1) | flag.  n is the squared distance in
+// units of 1/S, formed in INTEGERS: each of the six per-axis squares (dx^2 * S, clamped to 2^17) is rounded once (adding 2^23
+// leaves the integer in the low mantissa bits), and a corner's n is one three-input add -- |d^2 S - n| <= 1.6.  S puts the
+// clamp just above the largest proof margin: a candidate with n >= 2^17 can never be proven, nor can it threaten a proven
+// winner.  slot = the particle's number inside the brick.  A particle tests its key against the word and only then issues
+// atomicMin (a shared-memory atomic costs ~1-2 cycles per lane on B200, a load + compare almost nothing; of the ~8
+// candidates of a node only the running minima, H_8 = 2.7 on average, get through).  Ambiguity is settled in the
+// same sweep.  The value a candidate c meets -- the word it read when it loses, the word the atomic returned when it goes
+// through -- is the current holder h; with M = n_h / S, q = 1.6 / S (quantisation) and tol = the rigorous f32 error bound
+// of judge():
+//     d_c < M - 2 tol - 2q   c replaces h, and its key carries flag 0: it beats h and every rival of h by more than tol
+//     d_c > M + 2 tol + 2q   c is clearly worse than the holder (whose key can only decrease from here): nothing to do
+//     otherwise              the flag bit of the word is set (atomicOr) -- the node's holder has a rival within the tolerance
+// Invariant: every candidate that has arrived is no better than the holder (up to q), and if the flag is clear the holder
+// beats each of them by more than tol; so an unflagged final holder is the true nearest particle whatever the order of
+// arrival -- the guarantee of judge()'s runner-up test (its flags are a subset of these).  The cell along z comes from the
+// coordinate itself: a particle within a rounding error (4e-6 h) of a cell face may be booked one cell off, but it is then
+// within that distance of the window face of every node it is wrongly offered to (or withheld from), and such a node cannot
+// pass the proof (tol >= 1.6e-4 * margin * h).
+// Pass 3, one thread per node: proven iff n <= the node's integer threshold (the largest n with b + tol(b) < margin^2 for
+// b = (n + 0.6)/S, tabulated per axis on the host; min over the axes) -> settle (index + field planes) or hand on (lists B / C).
+// The node arrays are padded by one node on every side, so the 8 updates of a particle are 8 immediate offsets from one base
+// and need no bounds tests; the padding nodes are never read.  A brick with more than 4095 particles (1.5 per cell) goes to the
+// node-centric kernel k_search_crowded.
 constexpr int kBX = 8, kBY = 8, kBZ = 32;
 constexpr int kBRows = (kBX + 1) * (kBY + 1);
-constexpr int kBCells = kBZ + 2;            // cell boundaries per row: 33 cells + end
-constexpr int kBrickCap = 3584;             // staged particles per brick (mean 2673 at one particle per cell); more -> cell-by-cell form
-constexpr size_t kBrickSmem = size_t(kBrickCap) * 16 + size_t(kBRows) * kBCells * 4 + (3 * size_t(kBRows) + 4) * 4;
+constexpr int kBThreads = 256;
+constexpr int kNX = kBX + 2, kNY = kBY + 2, kNZ = kBZ + 2;   // padded node box
+constexpr int kNodes = kNX * kNY * kNZ;
+constexpr uint32_t kSlotBits = 12, kSlotMax = (1u << kSlotBits) - 1u;      // particles per sweep
+constexpr uint32_t kQ = 1u << 17;                                            // clamp of one quantised axis term; n >= kQ: beyond the clamp
+struct BrickQ {
+  float S, invS;       // quantisation scale of d^2 and its inverse
+  float q2;            // 2 * 1.6 / S
+  uint32_t nt;         // coarse filter: |n_c - n_h| <= nt  covers  2 tol + 2q  for every distance below the clamp
+  const int *tx, *ty, *tz;   // per-axis proof thresholds on n (device)
+};
+constexpr size_t kBrickOffRow = size_t(kNodes) * 4;
+constexpr size_t kBrickOffSeg = kBrickOffRow + size_t(kSlotMax + 1);
+constexpr size_t kBrickOffNq = kBrickOffSeg + (3 * size_t(kBRows) + 4) * 4;
+constexpr size_t kBrickSmem = kBrickOffNq + size_t(kNX + kNY + kNZ + 2) * 4 + size_t(kBX) * 4;
 
-__device__ __forceinline__ void scan_smem(const float4* sp, uint32_t s, uint32_t e, float qx, float qy, float qz, Cand& c) {
-#pragma unroll 1
-  for (uint32_t p = s; p < e; ++p) {
-    const float4 q = sp[p];
-    const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
-    cand_update(c, fmaf(dz, dz, fmaf(dy, dy, dx * dx)), int(p));
-  }
-}
+__host__ __device__ constexpr int brick_off(int q) { return (q >> 2) * (kNY * kNZ) + ((q >> 1) & 1) * kNZ + (q & 1); }
 
-__global__ void __launch_bounds__(256) k_search_brick(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
-                                                       Lattice L, float eps, SearchOut out) {
+__global__ void __launch_bounds__(kBThreads, 5) k_search_brick(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start,
+                                                                Grid g, Lattice L, float eps, BrickQ bq, SearchOut out) {
   extern __shared__ __align__(16) unsigned char brick_smem[];
-  float4* sp = reinterpret_cast<float4*>(brick_smem);                                       // [kBrickCap] staged particles
-  // smem index of the first staged particle of cell (row, z); last entry of a row = end
-  uint32_t (*cofs)[kBCells] = reinterpret_cast<uint32_t (*)[kBCells]>(brick_smem + size_t(kBrickCap) * 16);
-  uint32_t* seg_s = reinterpret_cast<uint32_t*>(cofs + kBRows);
-  uint32_t* seg_last = seg_s + kBRows;
-  uint32_t* seg_off = seg_last + kBRows;                                                    // [kBRows + 1]
-  __shared__ int fallback;
+  uint32_t* nkey = reinterpret_cast<uint32_t*>(brick_smem);                                 // [kNodes] (n << 13) | (slot << 1) | flag
+  unsigned char* slotrow = brick_smem + kBrickOffRow;                                       // [4096] cell row of a slot
+  uint32_t* seg_s = reinterpret_cast<uint32_t*>(brick_smem + kBrickOffSeg);                 // first sorted position of a row's run
+  uint32_t* seg_last = seg_s + kBRows;                                                      // first position of its 33rd cell
+  uint32_t* seg_off = seg_last + kBRows;                                                    // [kBRows + 1] slot of its first particle
+  float* nqx = reinterpret_cast<float*>(brick_smem + kBrickOffNq);                          // brick-relative node coordinates, padded
+  float* nqy = nqx + kNX;
+  float* nqz = nqy + kNY;
+  int* ntx = reinterpret_cast<int*>(nqz + kNZ + 2);                                         // [kBX] proof thresholds along x
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int k0 = blockIdx.x * kBZ, j0 = blockIdx.y * kBY, i0 = blockIdx.z * kBX;
   const int X0 = __ldg(L.wx + i0), Y0 = __ldg(L.wy + j0), Z0 = __ldg(L.wz + k0);   // first cell of the brick
-  const int Zend = min(Z0 + kBZ, g.gz - 1);                                         // last staged cell along z
-  const float hx = float(g.hx), hy = float(g.hy), hz = float(g.hz);
+  const int Zend = min(Z0 + kBZ, g.gz - 1);                                         // last cell of the runs along z
+  const float hx = g.hxf, hy = g.hyf, hz = g.hzf;
 
-  // ---- stage: row segments -> shared memory
+  if (tid < kNX + kNY + kNZ) {
+    float v = 0.f;
+    if (tid < kNX) { const int i = tid - 1; if (i >= 0 && i < kBX && i0 + i < L.nx) v = __ldg(L.rx + i0 + i) + float(i) * hx; }
+    else if (tid < kNX + kNY) { const int j = tid - kNX - 1; if (j >= 0 && j < kBY && j0 + j < L.ny) v = __ldg(L.ry + j0 + j) + float(j) * hy; }
+    else { const int k = tid - kNX - kNY - 1; if (k >= 0 && k < kBZ && k0 + k < L.nz) v = __ldg(L.rz + k0 + k) + float(k) * hz; }
+    nqx[tid] = v;
+  } else if (tid < kNX + kNY + kNZ + kBX) {
+    const int i = tid - (kNX + kNY + kNZ);
+    ntx[i] = i0 + i < L.nx ? __ldg(bq.tx + i0 + i) : -1;
+  }
   if (tid < kBRows) {
     const int X = X0 + tid / (kBY + 1), Y = Y0 + tid % (kBY + 1);
     uint32_t s = 0, e = 0, l = 0xffffffffu;
@@ -626,7 +696,7 @@ __global__ void __launch_bounds__(256) k_search_brick(const rec_t* __restrict__ 
     seg_off[tid] = e - s;
   }
   __syncthreads();
-  if (w == 0) {   // exclusive prefix of the kBRows segment lengths
+  if (w == 0) {   // exclusive prefix of the kBRows run lengths
     uint32_t carry = 0;
     for (int base = 0; base < kBRows; base += 32) {
       const int r = base + lane;
@@ -640,91 +710,136 @@ __global__ void __launch_bounds__(256) k_search_brick(const rec_t* __restrict__ 
       if (r < kBRows) seg_off[r] = carry + incl - v;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) {
-      seg_off[kBRows] = carry;
-      fallback = carry > uint32_t(kBrickCap);
-    }
+    if (lane == 0) seg_off[kBRows] = carry;
   }
   __syncthreads();
-  const bool fb = fallback != 0;
-  if (!fb) {
-    for (int t = tid; t < kBRows * kBCells; t += 256) {
-      const int r = t / kBCells, z = t - r * kBCells;
-      const int X = X0 + r / (kBY + 1), Y = Y0 + r % (kBY + 1);
-      uint32_t v = seg_off[r];
-      if (X < g.gx && Y < g.gy) {
-        const size_t row = (size_t(X) * g.gy + Y) * g.gz;
-        v += __ldg(start + row + min(Z0 + z, Zend + 1)) - seg_s[r];
-      }
-      cofs[r][z] = v;
-    }
-    for (int r = w; r < kBRows; r += 8) {
-      const uint32_t s = seg_s[r], len = seg_off[r + 1] - seg_off[r], off = seg_off[r], last = seg_last[r];
-      const float bx = float(r / (kBY + 1)) * hx, by = float(r % (kBY + 1)) * hy;
-      for (uint32_t p = lane; p < len; p += 32) {
-        const float4 q = __ldg(part + size_t(s + p) * rs);
-        sp[off + p] = make_float4(q.x + bx, q.y + by, (s + p >= last) ? q.z + float(kBZ) * hz : q.z, __int_as_float(int(s + p)));
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- search: thread (j = warp, k = lane), i = 0 .. kBX-1
-  const int j = j0 + w, k = k0 + lane;
-  if (j >= L.ny || k >= L.nz) return;
+  // (the sweep below can take a brick in slices of x planes; measured on clustered input the dense bricks are better off in the
+  // node-centric kernel, so a brick either fits one sweep or is handed over)
+  const int planes = seg_off[kBRows] <= kSlotMax ? kBX : 0;
   const bool far = out.stats->n_far != 0;
-  const float ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
-  const float my = __ldg(L.my + j), mz = __ldg(L.mz + k);
-  const int wy = Y0 + w, wz = Z0 + lane;
-  if (fb) {
-    // crowded brick: same arithmetic from global memory, cell by cell
-    for (int ii = 0; ii < kBX; ++ii) {
-      const int i = i0 + ii;
-      if (i >= L.nx) break;
-      const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-      const int wx = X0 + ii;
-      if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
-        out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
-        continue;
-      }
-      const float rx = __ldg(L.rx + i);
-      Cand c;
-      c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          const int X = wx + a, Y = wy + b;
-          if (X >= g.gx || Y >= g.gy) continue;
-          scan_zcells(part, rs, start, (size_t(X) * g.gy + Y) * g.gz, wz, min(wz + 1, g.gz - 1), wz, rx - float(a) * hx,
-                      ry - float(b) * hy, rz, hz, c);
-        }
-      emit(out, part, rs, node, judge(c, eps, fminf(__ldg(L.mx + i), fminf(my, mz))), c.bi);
-    }
+  const int j = j0 + w, k = k0 + lane;     // pass 3: this thread's node column
+  if (planes == 0) {
+    // crowded brick: handed to the node-centric kernel, k_search_crowded
+    if (tid == 0) out.crowded[atomicAdd(&out.stats->n_crowded, 1ull)] = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     return;
   }
-  const float qy = ry + float(w) * hy, qz = rz + float(lane) * hz;   // brick-relative node coordinates
-  const int r0 = w;                                                    // row index of (ii, w): ii*(kBY+1) + w
-  uint32_t s0 = cofs[r0][lane], e0 = cofs[r0][lane + 2], s1 = cofs[r0 + 1][lane], e1 = cofs[r0 + 1][lane + 2];
-  for (int ii = 0; ii < kBX; ++ii) {
-    const int i = i0 + ii;
-    if (i >= L.nx) break;
-    const int rn = (ii + 1) * (kBY + 1) + w;
-    const uint32_t s2 = cofs[rn][lane], e2 = cofs[rn][lane + 2], s3 = cofs[rn + 1][lane], e3 = cofs[rn + 1][lane + 2];
-    const size_t node = (size_t(i) * L.ny + j) * L.nz + k;
-    const int wx = X0 + ii;
+  const int nthr_yz = (j < L.ny && k < L.nz) ? min(__ldg(bq.ty + j), __ldg(bq.tz + k)) : -1;
+  const float ihz = float(g.ihz);
+  for (int xa = 0; xa < kBX; xa += planes) {
+    const int r0 = xa * (kBY + 1), nrows = (planes + 1) * (kBY + 1);
+    const uint32_t sb = seg_off[r0], count = seg_off[r0 + nrows] - sb;
+    for (int n = tid; n < kNodes; n += kBThreads) nkey[n] = 0xffffffffu;
+    for (int r = r0 + w; r < r0 + nrows; r += kBThreads / 32) {       // the cell row of every slot
+      const uint32_t a = seg_off[r] - sb, e = seg_off[r + 1] - sb;
+      for (uint32_t p = a + lane; p < e; p += 32) slotrow[p] = (unsigned char)r;
+    }
+    __syncthreads();
+    // ---- the sweep: one lane per particle
+    // (software pipelined: the record of the lane's next particle is requested before this one is worked on)
+    auto locate = [&](uint32_t t, int& r, uint32_t& gpos) {
+      r = slotrow[t];
+      gpos = seg_s[r] + (sb + t - seg_off[r]);
+    };
+    int r_n = 0;
+    uint32_t gpos_n = 0;
+    float4 q_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (uint32_t(tid) < count) { locate(tid, r_n, gpos_n); q_n = __ldg(part + size_t(gpos_n) * rs); }
+    for (uint32_t t = tid; t < count; t += kBThreads) {
+      const int r = r_n;
+      const uint32_t gpos = gpos_n;
+      const float4 q = q_n;
+      if (t + kBThreads < count) { locate(t + kBThreads, r_n, gpos_n); q_n = __ldg(part + size_t(gpos_n) * rs); }
+      const uint32_t cx = uint32_t(r) / (kBY + 1), cy = uint32_t(r) - cx * (kBY + 1);
+      const float pz = (gpos >= seg_last[r]) ? q.z + float(kBZ) * hz : q.z;
+      int cz = int(pz * ihz);
+      cz = cz < 0 ? 0 : (cz > kBZ ? kBZ : cz);
+      const float px = q.x + float(cx) * hx, py = q.y + float(cy) * hy;
+      // the six per-axis squares in units of 1/S as integers: bits(min(d*d*S, 2^17) + 2^23) = 0x4B000000 + round(...)
+      auto quant = [&](float dd) { return __float_as_uint(fminf(dd * dd * bq.S, float(kQ)) + 8388608.f); };
+      const uint32_t ux0 = quant(nqx[cx] - px), ux1 = quant(nqx[cx + 1] - px), uy0 = quant(nqy[cy] - py), uy1 = quant(nqy[cy + 1] - py);
+      // (the three biases add up to 0xE1000000: taken off the z terms, so that a corner's n is one three-input add)
+      const uint32_t uz0 = quant(nqz[cz] - pz) - 0xE1000000u, uz1 = quant(nqz[cz + 1] - pz) - 0xE1000000u;
+      const uint32_t t2 = t << 1;
+      uint32_t* m = nkey + (cx * kNY + cy) * kNZ + uint32_t(cz);
+#pragma unroll
+      for (int qd = 0; qd < 8; ++qd) {
+        const uint32_t n = ((qd & 4) ? ux1 : ux0) + ((qd & 2) ? uy1 : uy0) + ((qd & 1) ? uz1 : uz0);
+        const uint32_t key = (n << (kSlotBits + 1)) + t2;
+        uint32_t h = m[brick_off(qd)];
+        if (key < h) h = atomicMin(m + brick_off(qd), key);
+        const uint32_t nh = h >> (kSlotBits + 1);
+        if (n - nh + bq.nt <= 2u * bq.nt && n < kQ - bq.nt) {          // rare: neither clearly better nor clearly worse
+          const float dc = float(n) * bq.invS, M = float(nh) * bq.invS, dm = fmaxf(dc, M);
+          if (fabsf(dc - M) <= 2.f * (8.f * sqrtf(dm) * eps + 8.f * eps * eps + 1e-6f * dm) + bq.q2) atomicOr(m + brick_off(qd), 1u);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass 3: one thread per node (k = lane: plane stores are coalesced)
+    if (j < L.ny && k < L.nz) {
+      const int wy = Y0 + w, wz = Z0 + lane;
+      for (int ii = xa; ii < xa + planes; ++ii) {
+        const int gi = i0 + ii;
+        if (gi >= L.nx) break;
+        const size_t node = (size_t(gi) * L.ny + j) * L.nz + k;
+        const int wx = X0 + ii;
+        if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
+          out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
+          continue;
+        }
+        const int idx = ((ii + 1) * kNY + (w + 1)) * kNZ + (lane + 1);
+        const uint32_t key = nkey[idx];
+        int verdict = 2, pos = -1;
+        if (int(key >> (kSlotBits + 1)) <= min(ntx[ii], nthr_yz)) {    // proven (an empty node holds n = 2^19 - 1 > every threshold)
+          verdict = int(key & 1u);
+          const uint32_t t = (key >> 1) & kSlotMax, r = slotrow[t];
+          pos = int(seg_s[r] + (sb + t - seg_off[r]));
+        }
+        emit(out, part, rs, node, verdict, pos);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Stage A for the bricks the sweep declined (clustered input: a few dense bricks hold most of the particles): node-centric, a
+// warp = 32 consecutive z nodes, the 2x2x2 window as 4 cell rows, straight from global memory.  Persistent CTAs take
+// (brick, x plane) items from a global cursor.
+__global__ void __launch_bounds__(256, 6) k_search_crowded(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
+                                                            Lattice L, float eps, SearchOut out, unsigned gx_b, unsigned gy_b) {
+  __shared__ unsigned long long item_s;
+  const unsigned long long nitems = out.stats->n_crowded * kBX;       // work item = one x plane of a brick (256 nodes)
+  const bool far = out.stats->n_far != 0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float hx = g.hxf, hy = g.hyf, hz = g.hzf;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) item_s = atomicAdd(&out.stats->crowded_cursor, 1ull);
+    __syncthreads();
+    const unsigned long long item = item_s;
+    if (item >= nitems) break;
+    const unsigned id = out.crowded[item / kBX];
+    const int ii = int(item % kBX);
+    const int k0 = int(id % gx_b) * kBZ, j0 = int((id / gx_b) % gy_b) * kBY, i0 = int(id / (gx_b * gy_b)) * kBX;
+    const int j = j0 + w, k = k0 + lane, gi = i0 + ii;
+    if (j >= L.ny || k >= L.nz || gi >= L.nx) continue;
+    const int wx = __ldg(L.wx + gi), wy = __ldg(L.wy + j), wz = __ldg(L.wz + k);
+    const size_t node = (size_t(gi) * L.ny + j) * L.nz + k;
     if (far && (touches_end(wx, wx + 1, g.gx) || touches_end(wy, wy + 1, g.gy) || touches_end(wz, wz + 1, g.gz))) {
       out.list_c[atomicAdd(&out.stats->n_wide, 1ull)] = uint32_t(node);
-    } else {
-      const float qx = __ldg(L.rx + i) + float(ii) * hx;
-      Cand c;
-      c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
-      scan_smem(sp, s0, e0, qx, qy, qz, c);
-      scan_smem(sp, s1, e1, qx, qy, qz, c);
-      scan_smem(sp, s2, e2, qx, qy, qz, c);
-      scan_smem(sp, s3, e3, qx, qy, qz, c);
-      const int verdict = judge(c, eps, fminf(__ldg(L.mx + i), fminf(my, mz)));
-      emit(out, part, rs, node, verdict, c.bi >= 0 ? __float_as_int(sp[c.bi].w) : -1);
+      continue;
     }
-    s0 = s2; e0 = e2; s1 = s3; e1 = e3;
+    const float rx = __ldg(L.rx + gi), ry = __ldg(L.ry + j), rz = __ldg(L.rz + k);
+    Cand c;
+    c.b1 = INFINITY; c.b2 = INFINITY; c.bi = -1;
+    for (int a = 0; a < 2; ++a)
+      for (int bb = 0; bb < 2; ++bb) {
+        const int X = wx + a, Y = wy + bb;
+        if (X >= g.gx || Y >= g.gy) continue;
+        scan_zcells(part, rs, start, (size_t(X) * g.gy + Y) * g.gz, wz, min(wz + 1, g.gz - 1), wz, rx - float(a) * hx,
+                    ry - float(bb) * hy, rz, hz, c);
+      }
+    emit(out, part, rs, node, judge(c, eps, fminf(__ldg(L.mx + gi), fminf(__ldg(L.my + j), __ldg(L.mz + k)))), c.bi);
   }
 }
 
@@ -1049,7 +1164,7 @@ NNScratch nn_scratch(int64_t np, bool pay, uint64_t ncells, uint32_t nb, int64_t
   s.tab = vp_align256((ncells + 8) * 4);
   s.hist = 2 * vp_align256((size_t(nb) * kSub + 1) * 4);          // (bucket, sub-stream) histogram and cursors
   s.sums = vp_scan_scratch_bytes_local(int64_t(ncells) + 1);
-  const size_t b_lists = 2 * vp_align256(size_t(nnodes) * 4);
+  const size_t b_lists = 2 * vp_align256(size_t(nnodes) * 4) + vp_align256((size_t(nnodes) / 8 + 4096) * 4);   // + the crowded-brick list (>= the number of bricks of any lattice shape)
   s.tail = s.rec1 > b_lists ? s.rec1 : b_lists;   // the bucketed records are dead once placed; the two node lists reuse them
   s.total = s.tail + s.spos + s.tab + s.hist + s.sums + 4096;
   return s;
@@ -1086,7 +1201,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   // ---- lattice tables (host -> pinned -> device)
   const size_t nt = size_t(nx) + ny + nz;
   const size_t off_w = vp_align256(nt * 8), off_r = off_w + vp_align256(nt * 4), off_m = off_r + vp_align256(nt * 4);
-  const size_t tab_bytes = off_m + vp_align256(nt * 4);
+  const size_t off_t = off_m + vp_align256(nt * 4);
+  const size_t tab_bytes = off_t + vp_align256(nt * 4);
   if (ctx->pinned_cap < tab_bytes || ctx->small_cap < tab_bytes) {
     VP_CUDA(cudaStreamSynchronize(st));
     if (ctx->pinned_cap < tab_bytes) {
@@ -1141,10 +1257,48 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   fill_axis(qy, ny, nx, g.oy, g.hy, g.ihy, gy, false, false);
   fill_axis(qz, nz, nx + ny, g.oz, g.hz, g.ihz, gz, false, false);
   // brick kernel: consecutive windows on every axis, z windows starting on a 32-cell boundary, node inside its window
-  bool brick = consecutive && (hw[nx + ny] % 32 == 0) && gx >= 2 && gy >= 2 && gz >= 2 && getenv("VP_SEARCH_BRICK");   // measured slower than k_search_rows
+  bool brick = consecutive && (hw[nx + ny] % 32 == 0) && gx >= 2 && gy >= 2 && gz >= 2 && !getenv("VP_SEARCH_ROWS");   // (VP_SEARCH_ROWS: the node-centric kernel, for A/B runs)
   for (size_t t = 0; t < nt && brick; ++t) {
     const double hh = t < size_t(nx) ? g.hx : (t < size_t(nx + ny) ? g.hy : g.hz);
     if (!(hr[t] >= -0.5f * float(hh) && hr[t] <= 2.5f * float(hh))) brick = false;   // keeps the f32 error bound of the brick frame
+  }
+  // brick kernel: quantisation of d^2 and the per-axis proof thresholds on the quantised value (see k_search_brick)
+  const float hmax = float(fmax(fmax(g.hx, g.hy), g.hz));
+  const float eps = 2e-5f * hmax;
+  BrickQ bq;
+  memset(&bq, 0, sizeof bq);
+  if (brick) {
+    int* ht = reinterpret_cast<int*>(hb + off_t);
+    float mmax = 0.f;
+    for (size_t t = 0; t < nt; ++t)
+      if (hm[t] != INFINITY && hm[t] > mmax) mmax = hm[t];
+    const double e = double(eps);
+    auto tol = [&](double b) { return 8.0 * sqrt(b) * e + 8.0 * e * e + 1e-6 * b; };     // judge()'s bound, in f64
+    const double m2max = mmax > 0.f ? double(mmax) * double(mmax) : 27.0 * double(hmax) * double(hmax);
+    const double dclamp = 1.05 * m2max + 4.0 * tol(2.0 * m2max);
+    bq.S = float(double(kQ) / dclamp);
+    bq.invS = float(1.0 / double(bq.S));
+    const double S = double(bq.S), q = 1.6 / S;       // three roundings of 0.5 + the f32 roundings of the scaled squares
+    bq.q2 = float(2.0 * q * (1.0 + 1e-6));
+    bq.nt = uint32_t(ceil((2.0 * tol(dclamp) + 2.0 * q) * S * (1.0 + 1e-5))) + 2u;
+    for (size_t t = 0; t < nt; ++t) {
+      int thr = -1;
+      if (hm[t] == INFINITY) thr = int(kQ) - 1;
+      else {
+        const double m2 = double(hm[t]) * double(hm[t]);
+        if (m2 > 8.0 * e * e) {
+          // largest b with b + tol(b) < m2:  (1 + 1e-6) r^2 + 8 e r + 8 e^2 - m2 = 0,  b = r^2
+          const double a2 = 1.0 + 1e-6, r = (-8.0 * e + sqrt(64.0 * e * e + 4.0 * a2 * (m2 - 8.0 * e * e))) / (2.0 * a2);
+          const double bsafe = r * r * (1.0 - 1e-6);
+          const double nn_ = floor(bsafe * S - 1.6) - 1.0;
+          thr = nn_ < 0.0 ? -1 : (nn_ > double(kQ) - 1.0 ? int(kQ) - 1 : int(nn_));
+          while (thr >= 0 && !((double(thr) + 1.6) / S + tol((double(thr) + 1.6) / S) < m2)) --thr;   // (belt and braces)
+        }
+      }
+      ht[t] = thr;
+    }
+    const char* dbt = reinterpret_cast<const char*>(ctx->small_d) + off_t;
+    bq.tx = reinterpret_cast<const int*>(dbt); bq.ty = bq.tx + nx; bq.tz = bq.ty + ny;
   }
   VP_CUDA(cudaMemcpyAsync(ctx->small_d, ctx->pinned_h, tab_bytes, cudaMemcpyHostToDevice, st));
   VP_CUDA(cudaEventRecord(ctx->ev_tables, st));
@@ -1170,6 +1324,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   uint32_t* cursor = hist + vp_align256((size_t(g.nb) * kSub + 1) * 4) / 4;
   uint32_t* node_list = static_cast<uint32_t*>(rec1);                                           // -> exact kernel
   uint32_t* list_b = node_list + vp_align256(size_t(nnodes) * 4) / 4;                            // -> wider stage
+  uint32_t* crowded = list_b + vp_align256(size_t(nnodes) * 4) / 4;                              // -> node-centric stage A of dense bricks
   const int rs = has_pay ? 2 : 1;     // float4 stride of the sorted records
 
   VP_CUDA(cudaMemsetAsync(ctx->nn_stats_d, 0, sizeof(vp_nn_stats_dev), st));
@@ -1239,7 +1394,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       vp_stage stage(ctx, "k1b_bin_scatter", st, 1, double(np) * (has_pay ? (3 + 3 + (pay->rho ? 1 : 0)) * es + 32.0 : 3 * es + 16.0));
       launch_scatter(pos, has_pay ? pay->vel : nullptr, has_pay ? pay->rho : nullptr, np, 0);
     }
-    const unsigned nbk = unsigned((np + 255) / 256);
+    const unsigned nbk = unsigned((np + 256 * kIlp - 1) / (256 * kIlp));
     {
       // the cell index of every record read (one sector), one counter bumped
       vp_stage stage(ctx, "k1c_cell_count", st, 1, double(np) * (has_pay ? 32.0 : 16.0) + double(ncells) * 4.0);
@@ -1261,10 +1416,8 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   }
   const uint32_t* start = xtab + 3;
   int32_t* nn_pos = has_pay ? pay->nn_pos_out : nullptr;
-  const float hmax = float(fmax(fmax(g.hx, g.hy), g.hz));
-  const float eps = 2e-5f * hmax;
   SearchOut so;
-  so.nn = nn; so.nn_pos = nn_pos; so.list_b = list_b; so.list_c = node_list; so.stats = ctx->nn_stats_d;
+  so.nn = nn; so.nn_pos = nn_pos; so.list_b = list_b; so.list_c = node_list; so.crowded = crowded; so.stats = ctx->nn_stats_d;
   so.f = has_pay ? pay->fo : FieldOut{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   {
     // sorted records read once + cell starts read once + one index written per node
@@ -1278,7 +1431,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         VP_CUDA(cudaFuncSetAttribute(k_search_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBrickSmem)));
         brick_attr = true;
       }
-      k_search_brick<<<grid, 256, kBrickSmem, st>>>(srec, rs, start, g, L, eps, so);
+      k_search_brick<<<grid, kBThreads, kBrickSmem, st>>>(srec, rs, start, g, L, eps, bq, so);
+      k_search_crowded<<<ctx->sm_count * 6, 256, 0, st>>>(srec, rs, start, g, L, eps, so, grid.x, grid.y);
+      ctx->n_launch += 1;
     } else {
       // block = (z nodes, y rows), one x plane per blockIdx.z: no integer division in the kernel
       // A warp = 32 consecutive z nodes; the 8 warps of a CTA take 8 consecutive y rows, so that the cell rows two

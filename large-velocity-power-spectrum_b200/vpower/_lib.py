@@ -76,6 +76,8 @@ SIGNATURES = {
     "vp_fft_unpack_half": (_I, [_P, _P, _P, _P]),
     "vp_power_bin_full": (_I, [_P, _P, _P, _P, _P]),
     "vp_power_cube": (_I, [_P, C.POINTER(_P), _I, _P, _P]),
+    "vp_fold_field": (_I, [_P, C.POINTER(_P), _I, _I, _I, C.POINTER(_I), _P, _P]),
+    "vp_fold_power": (_I, [_P, _P, _I, _I, _P, _P]),
     "vp_k_magnitude": (_I, [_P, _dp, _dp, _dp, _I, _P, _P]),
     "vp_hist_weighted": (_I, [_P, _P, _P, _L, _dp, _I, _P, _P, _P]),
     "vp_sort_pairs": (_I, [_P, _P, _P, _L, _I, _P]),
@@ -558,6 +560,34 @@ class PkPlan:
         half = torch.empty((self.N, self.N, self.N // 2 + 1, 2), dtype=torch.float32, device=cube.device)
         _check(load_library().vp_fft_unpack_half(self._h, _P(cube.data_ptr()), _P(half.data_ptr()), stream_ptr()))
         return torch.view_as_complex(half)
+
+
+def fold_field(cubes, m, beta):
+    """BoxField.fold on the device: cubes = 1..3 float32 CUDA tensors [N,N,N] (read only) ->
+    complex128 CUDA tensor [N/m, N/m, N/m, ncomp] = fold_field(v * phase_beta, m) / m**1.5."""
+    torch = _torch()
+    N = int(cubes[0].shape[0])
+    for c in cubes:
+        assert c.is_cuda and c.dtype == torch.float32 and c.is_contiguous() and tuple(c.shape) == (N,) * 3
+    if N % m:
+        raise VPowerError(f"fold: Nsize={N} is not a multiple of the folding factor m={m}")
+    n = N // m
+    out = torch.empty((n, n, n, len(cubes), 2), dtype=torch.float64, device=cubes[0].device)
+    ptrs = (_P * len(cubes))(*[c.data_ptr() for c in cubes])
+    b = (_I * 3)(*[int(t) for t in beta])
+    _check(load_library().vp_fold_field(ctx(), ptrs, len(cubes), N, int(m), b, _P(out.data_ptr()), stream_ptr()))
+    return torch.view_as_complex(out)
+
+
+def fold_power(folded_t):
+    """sum_c |FFT_n(folded_c)|^2 of a complex128 CUDA tensor [n,n,n,ncomp] (or [n,n,n]) -> f64 CUDA tensor [n,n,n]."""
+    torch = _torch()
+    f = folded_t if folded_t.dim() == 4 else folded_t[..., None]
+    f = torch.view_as_real(f.to(torch.complex128).contiguous())
+    n, ncomp = int(f.shape[0]), int(f.shape[3])
+    P = torch.empty((n, n, n), dtype=torch.float64, device=f.device)
+    _check(load_library().vp_fold_power(ctx(), _P(f.data_ptr()), ncomp, n, _P(P.data_ptr()), stream_ptr()))
+    return P
 
 
 def k_magnitude(kx, ky, kz):

@@ -6,7 +6,7 @@ libvpower_b200.so (include/vpower_b200.h), reached through `_lib` (ctypes).  The
 fallback: without the shared library or a CUDA device the compute calls raise `VPowerError`.
 
 Reference line numbers (vpower/interp.py) are cited per function.  Out of scope here: the Voxelize
-path, the ANN command-line path, folding (`fold*`, `FoldedBox`, `BrickInventory`) and plotting.
+path, the ANN command-line path, the brick inventory on disk (`BrickInventory`, `interp_to_brick`) and plotting.
 """
 from __future__ import annotations
 
@@ -15,8 +15,9 @@ import numpy as np
 from . import _lib
 from .spctrm import PowerSpectrum
 
-__all__ = ["load_snapshot", "GasParticles", "BoxField", "ann_interpolate", "make_grid_coords", "deposit_to_grid",
-           "check_conservation", "_vector_power", "_scalar_power", "_pair_power", "_hist_sample"]
+__all__ = ["load_snapshot", "GasParticles", "BoxField", "FoldedBox", "ann_interpolate", "make_grid_coords", "deposit_to_grid",
+           "check_conservation", "_vector_power", "_scalar_power", "_pair_power", "_hist_sample", "_get_phase", "_apply_phase",
+           "fold_field"]
 
 
 # ------------------------------------------------------------------------------------------ snapshot
@@ -313,6 +314,15 @@ class BoxField:
         """interp.py:544-557."""
         return self._power_grid("energy")
 
+    def fold(self, m, beta, quantity="velocity"):
+        """Folded velocity field for the residue class `beta` of the folding factor `m` (interp.py:598-609):
+        phase multiply, sum of the m^3 sub-blocks, / m^1.5 -- one kernel; the result stays on the device until `.f` is read."""
+        if quantity != "velocity":
+            raise Exception("""Unsupported physical quantity name.""")
+        planes, _ = self._planes("velocity")
+        phi = _lib.fold_field(planes, int(m), [int(b) for b in beta])
+        return FoldedBox(phi, m, beta, self.Lbox / m, self.Nsize // m)
+
     def spctrm(self, quantity="velocity", kmin=None, kmax=None, kres=None) -> PowerSpectrum:
         """Shell-averaged spectrum of `quantity` ('velocity' | 'momentum' | 'energy').  interp.py:560-595.
         FFT, |F|^2 and the k-shell histogram run fused on the device (no power cube is formed)."""
@@ -339,7 +349,102 @@ class BoxField:
         return PowerSpectrum(Pkk)
 
 
+class FoldedBox:
+    """A folded (complex) field and the sub-spectrum it yields.  interp.py:740-800.
+    `f` is a numpy complex128 array [n,n,n,3] (vector) or [n,n,n] (scalar), or the CUDA tensor BoxField.fold produced --
+    reading the attribute `f` returns numpy either way."""
+
+    def __init__(self, f, m, beta, Lbox, Nsize) -> None:
+        self._f = f
+        self.Lbox = Lbox
+        self.Nsize = Nsize
+        self.Lcell = Lbox / Nsize
+        self.m = m
+        self.beta = beta
+        self.totalLbox = Lbox * m
+
+    @property
+    def f(self):
+        if not isinstance(self._f, np.ndarray):
+            self._f = self._f.cpu().numpy()
+        return self._f
+
+    @f.setter
+    def f(self, value):
+        self._f = value
+
+    def fold_spctrm(self, fft_object=None, beta=np.array([0, 0, 0]), kmin=None, kmax=None, kres=None) -> PowerSpectrum:
+        """Sub-spectrum of this residue class (interp.py:755-791): c2c transform of the folded field, 1/2 sum |a F|^2, |k|
+        pairing shifted by 2 pi beta / totalLbox, shell histogram -- all on the device.  `fft_object` (a pyFFTW plan in the
+        reference) is ignored.  Unlike the reference, `f` is not overwritten by the power grid."""
+        torch = _lib._torch()
+        if kmin is None:
+            kmin = 2 * np.pi / self.totalLbox
+        if kmax is None:
+            kmax = np.pi / self.Lcell
+        if kres is None:
+            kres = kmin
+        f = self._f
+        if isinstance(f, np.ndarray):
+            if f.ndim not in (3, 4):
+                raise Exception("""Unrecognized field shape.
+        Supported: (N, N, N, 3), (N, N, N).""")
+            f = _lib.to_device(np.ascontiguousarray(f, dtype=np.complex128))
+        n = int(self.Nsize)
+        a = (self.Lbox / (2 * np.pi)) ** 1.5 / n ** 3                      # interp.py:1398
+        P = _lib.fold_power(f) * (0.5 * a * a)
+        ks = _k_axis(self.Lbox, n)
+        shift = 2 * np.pi * np.asarray(beta) / self.totalLbox              # interp.py:780
+        axes = [ks + shift[c] if shift[c] > 0 else ks for c in range(3)]   # interp.py:1453-1458
+        k = _lib.k_magnitude(*axes)
+        centres, edges = _edges_lib(kmin, kmax, kres)
+        Psum, ns = _lib.hist_weighted(k, P.reshape(-1), edges)
+        Nsample = ns.astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Pm = Psum / Nsample
+        Pm[Nsample == 0] = 0
+        Pkk = np.column_stack((centres, Pm, Psum, Nsample))
+        Pkk[:, 1] *= 4 * np.pi * Pkk[:, 0] ** 2
+        return PowerSpectrum(Pkk, m=self.m, beta=beta)
+
+    def save(self, run_output_dir) -> None:
+        """Pickle under `run_output_dir` as folded_field_b{beta}.pkl (interp.py:793-800)."""
+        import os
+        import pickle
+        _ = self.f                                                          # materialise on the host before pickling
+        with open(os.path.join(run_output_dir, "folded_field_b{}{}{}.pkl".format(*self.beta)), "wb") as file:
+            pickle.dump(self, file)
+
+
 # ------------------------------------------------------------------------------------------ functions
+def _get_phase(beta, totalNsize, Nphase, x0, y0, z0) -> np.ndarray:
+    """exp(-i (2 pi / totalNsize) beta.x) on the brick [x0, x0+Nphase) x ..., complex128.  interp.py:1215-1225 (host helper;
+    BoxField.fold evaluates the phase inside its kernel)."""
+    x, y, z = (np.arange(o, o + Nphase) for o in (x0, y0, z0))
+    xxx, yyy, zzz = np.meshgrid(x, y, z, indexing="ij")
+    return np.exp(-1j * (2 * np.pi / totalNsize) * (beta[0] * xxx + beta[1] * yyy + beta[2] * zzz))
+
+
+def _apply_phase(f, phase) -> np.ndarray:
+    """complex128 copy of f times the phase (every vector component).  interp.py:1195-1212."""
+    phi = np.array(f, dtype=np.complex128)
+    phi *= phase if phi.shape == phase.shape else phase[..., None]
+    return phi
+
+
+def fold_field(f, m):
+    """Sum of the m^3 sub-blocks of size N/m, in (i, j, k) order.  interp.py:1228-1252."""
+    if m == 1:
+        return f
+    n1, n2, n3 = f.shape[0] // m, f.shape[1] // m, f.shape[2] // m
+    r = 0.0
+    for i in range(m):
+        for j in range(m):
+            for k in range(m):
+                r = r + f[i * n1:(i + 1) * n1, j * n2:(j + 1) * n2, k * n3:(k + 1) * n3, ...]
+    return r
+
+
 def _lattice_axis(Lbox, Nsize):
     Lcell = Lbox / Nsize
     return np.linspace(Lcell / 2, Lbox + Lcell / 2, Nsize)       # interp.py:1062-1063

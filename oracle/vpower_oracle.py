@@ -308,6 +308,65 @@ def shell_counts(Lbox, Nsize, edges):
 
 
 # --------------------------------------------------------------------------
+# f3  folding (outer stage): BoxField.fold -> FoldedBox.fold_spctrm
+#     pinned by tests/golden/reference_golden_fold.npz (tests/golden/make_golden_fold.py)
+# --------------------------------------------------------------------------
+
+def fold_phase(beta, Nsize):
+    """interp.py:1215-1225 (_get_phase with x0=y0=z0=0, Nphase=totalNsize=Nsize):
+    exp(-i (2 pi / N) (beta . x)) on the [N,N,N] lattice, complex128."""
+    n = np.arange(Nsize)
+    xxx, yyy, zzz = np.meshgrid(n, n, n, indexing="ij")
+    return np.exp(-1j * (2 * np.pi / Nsize) * (beta[0] * xxx + beta[1] * yyy + beta[2] * zzz))
+
+
+def fold_field(f, m):
+    """interp.py:1228-1252: sum of the m^3 sub-blocks of size N/m, added in (i, j, k) order."""
+    if m == 1:
+        return f
+    n1, n2, n3 = f.shape[0] // m, f.shape[1] // m, f.shape[2] // m
+    r = 0.0
+    for i in range(m):
+        for j in range(m):
+            for k in range(m):
+                r = r + f[i * n1:(i + 1) * n1, j * n2:(j + 1) * n2, k * n3:(k + 1) * n3]
+    return r
+
+
+def fold_velocity(v_grid, m, beta):
+    """BoxField.fold, interp.py:598-609 (+ _apply_phase :1195-1212): complex128 [N/m,N/m,N/m,3] = fold(v * phase) / m^1.5."""
+    N = v_grid.shape[0]
+    phi = np.array(v_grid, dtype=np.complex128) * fold_phase(beta, N)[..., None]
+    return fold_field(phi, m) / m ** 1.5
+
+
+def fold_spctrm(folded, m, beta, totalLbox, kmin=None, kmax=None, kres=None):
+    """FoldedBox.fold_spctrm, interp.py:755-791 -> [nbins,4] (k, P*4 pi k^2, Psum, Nsample).
+    folded: [n,n,n,3] (vector) or [n,n,n] (scalar) complex; Lbox = totalLbox/m, Lcell = Lbox/n."""
+    n = folded.shape[0]
+    Lbox = totalLbox / m
+    Lcell = Lbox / n
+    if kmin is None:
+        kmin = 2 * np.pi / totalLbox
+    if kmax is None:
+        kmax = np.pi / Lcell
+    if kres is None:
+        kres = kmin
+    a = (Lbox / (2 * np.pi)) ** 1.5 / n ** 3                                   # :1398
+    fk = scipy.fft.fftn(folded, axes=(0, 1, 2), workers=-1) * a
+    P = 0.5 * np.sum(np.abs(fk) ** 2, axis=3) if folded.ndim == 4 else 0.5 * np.abs(fk) ** 2
+    ks = k_axis(Lbox, n)
+    shift = 2 * np.pi * np.asarray(beta) / totalLbox                           # :780
+    ax = [ks + shift[c] if shift[c] > 0 else ks for c in range(3)]             # :1453-1458
+    kx, ky, kz = np.meshgrid(ax[0], ax[1], ax[2], indexing="ij")
+    k = np.ravel(np.sqrt(kx * kx + ky * ky + kz * kz))
+    c, e = edges_lib(kmin, kmax, kres)
+    Pkk = hist_sample(k, P, c, e, empty_to_zero=True)
+    Pkk[:, 1] *= 4 * np.pi * Pkk[:, 0] ** 2
+    return Pkk
+
+
+# --------------------------------------------------------------------------
 # whole path, library flavour and script flavour
 # --------------------------------------------------------------------------
 

@@ -23,3 +23,20 @@ def golden():
 def orc():
     import vpower_oracle
     return vpower_oracle
+
+
+@pytest.fixture(scope="session")
+def golden_fold():
+    """Reference outputs of the folding stage (tests/golden/make_golden_fold.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_fold.npz"))
+
+
+def fold_case_field(seed, N):
+    """The velocity / mass arrays of a fold golden case, from its seed (same recipe as make_golden_fold.py)."""
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=(N, N, N, 3)).astype(np.float32)
+    x = (np.arange(N) + 0.5) / N
+    v[..., 0] += (2.0 * np.sin(2 * np.pi * 3 * x)[:, None, None]).astype(np.float32)
+    v[..., 2] += (1.5 * np.cos(2 * np.pi * 5 * x)[None, :, None]).astype(np.float32)
+    mass = (1.0 + rng.random((N, N, N))).astype(np.float32)
+    return v, mass

@@ -832,3 +832,49 @@ def test_fft_binning_N1000_reference_default(lib, orc):
     pw, nw = plan.fields([wave])
     j0 = int(np.floor(np.sqrt(9 + 25 + 49) + 0.5)) - 1
     assert abs(pw[j0] / (float(N) ** 6 / 2) - 1) < 1e-5 and np.delete(pw, j0).sum() < 1e-6 * float(N) ** 6 / 2
+
+
+# ------------------------------------------------------------------------------------------ folding (outer stage)
+@pytest.mark.parametrize("name,seed,N,L,m", [("fold16_m2", 31, 16, 1.0, 2), ("fold24_m3", 32, 24, 2.5, 3), ("fold128_m2", 33, 128, 1.0, 2)])
+def test_fold_vs_reference(vp, golden_fold, name, seed, N, L, m):
+    """BoxField.fold(m, beta) and FoldedBox.fold_spctrm on the device against the unmodified reference (interp.py:598-609,
+    755-791): folded field to 1e-12, mode counts bit-exact, Psum to 1e-9 where the folded transform runs in f64 (n = 8) and
+    1e-5 where it runs through the f32 line FFT (n = 64)."""
+    import vpower.interp as vi
+    from conftest import fold_case_field
+    g = golden_fold
+    v, mass = fold_case_field(seed, N)
+    bf = vi.BoxField(v, mass, L / N)
+    for tag in sorted(k.split("_b")[-1] for k in g.files if k.startswith(f"{name}/spctrm_b")):
+        beta = np.array([int(t) for t in tag])
+        fb = bf.fold(m, beta)
+        assert fb.Nsize == N // m and fb.m == m and abs(fb.totalLbox - L) < 1e-15
+        sp = fb.fold_spctrm(None, beta=beta)
+        f = fb.f
+        assert f.dtype == np.complex128 and f.shape == (N // m,) * 3 + (3,)
+        if f"{name}/folded_b{tag}" in g.files:
+            assert np.abs(f - g[f"{name}/folded_b{tag}"]).max() < 1e-12
+        else:
+            assert np.abs(f[::8, ::8, ::8, :] - g[f"{name}/folded_b{tag}_sample"]).max() < 1e-12
+        ref = g[f"{name}/spctrm_b{tag}"]
+        got = sp.data()
+        assert sp.m == m and tuple(sp.beta) == tuple(beta)
+        assert np.array_equal(got[:, 0], ref[:, 0])
+        assert np.array_equal(got[:, 3], ref[:, 3])                                   # mode counts bit-exact
+        ok = ref[:, 3] > 0
+        rel = np.abs(got[ok, 2] - ref[ok, 2]) / ref[ok, 2]
+        assert rel.max() < (1e-9 if N // m < 64 else 1e-5), (name, tag, rel.max())
+        assert np.allclose(got[ok, 1], ref[ok, 1], rtol=1e-5 if N // m >= 64 else 1e-9)
+
+
+def test_fold_from_numpy_folded_box(vp, golden_fold):
+    """A FoldedBox built by hand from a numpy array (as reference-produced pickles are) goes through the same device path."""
+    import vpower.interp as vi
+    g = golden_fold
+    f = g["fold16_m2/folded_b100"]
+    fb = vi.FoldedBox(f.copy(), 2, np.array([1, 0, 0]), 0.5, 8)
+    got = fb.fold_spctrm(None, beta=np.array([1, 0, 0])).data()
+    ref = g["fold16_m2/spctrm_b100"]
+    assert np.array_equal(got[:, 3], ref[:, 3])
+    ok = ref[:, 3] > 0
+    assert (np.abs(got[ok, 2] - ref[ok, 2]) / ref[ok, 2]).max() < 1e-9

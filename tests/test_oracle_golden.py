@@ -107,3 +107,42 @@ def test_script_path(golden, orc, name):
     assert np.array_equal(got[:, 3], ref[:, 3])
     assert np.allclose(got[:, 2], ref[:, 2], rtol=2e-5)
     assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ folding (outer stage)
+FOLD_CASES = [("fold16_m2", 31, 16, 1.0, 2), ("fold24_m3", 32, 24, 2.5, 3), ("fold128_m2", 33, 128, 1.0, 2)]
+
+
+@pytest.mark.parametrize("name,seed,N,L,m", FOLD_CASES)
+def test_fold_oracle_vs_reference(golden_fold, orc, name, seed, N, L, m):
+    """oracle fold_velocity / fold_spctrm == BoxField.fold / FoldedBox.fold_spctrm of the unmodified reference."""
+    from conftest import fold_case_field
+    g = golden_fold
+    v, _ = fold_case_field(seed, N)
+    if f"{name}/v" in g.files:
+        assert np.array_equal(v, g[f"{name}/v"])
+    tags = sorted(k.split("_b")[-1] for k in g.files if k.startswith(f"{name}/spctrm_b"))
+    assert tags
+    for tag in tags:
+        beta = [int(t) for t in tag]
+        f = orc.fold_velocity(v, m, beta)
+        if f"{name}/folded_b{tag}" in g.files:
+            assert np.abs(f - g[f"{name}/folded_b{tag}"]).max() < 1e-13
+        else:
+            assert np.abs(f[::8, ::8, ::8, :] - g[f"{name}/folded_b{tag}_sample"]).max() < 1e-13
+            assert abs(f.sum() - g[f"{name}/folded_b{tag}_sum"][0]) < 1e-9 * max(1.0, abs(f.sum()))
+        sp = orc.fold_spctrm(f, m, beta, L)
+        ref = g[f"{name}/spctrm_b{tag}"]
+        assert np.array_equal(sp[:, 0], ref[:, 0]) and np.array_equal(sp[:, 3], ref[:, 3])
+        ok = ref[:, 3] > 0
+        assert np.abs(sp[ok, 2] - ref[ok, 2]).max() <= 1e-12 * np.abs(ref[ok, 2]).max()
+
+
+def test_fold_subspectra_partition_the_full_spectrum(golden_fold):
+    """The reference's own identity behind folding: over all m^3 residue classes the sub-spectra hold every mode exactly once
+    (checked here on the classes the golden file carries: their mode counts never exceed the full spectrum's)."""
+    g = golden_fold
+    full = g["fold16_m2/spctrm_full"]
+    total = sum(g[k][:, 3].sum() for k in g.files if k.startswith("fold16_m2/spctrm_b"))
+    assert total <= full[:, 3].sum() + 16 ** 3       # shells of the shifted lattices overlap the unshifted ones only partly
+    assert total > 0
