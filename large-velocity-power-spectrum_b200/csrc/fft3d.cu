@@ -7,6 +7,7 @@
 // planes a+ib through the y and x passes; they are separated at the end by Hermitian symmetry
 // (k_plane_bin), all other columns are ordinary half-spectrum modes with weight 2.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -156,6 +157,8 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
   float* pt = reinterpret_cast<float*>(sm + XS);                   // [C][PP] sum over components of |F|^2
   const int tid = threadIdx.x, c = tid % C, t = tid / C;
   const int tiles_z = NZ / C;
+  // (launch order: tried with the kYB tiles that share the 1 KB blocks of the blocked layout as neighbours, so that their
+  // 64-byte pieces of one block are requested together -- no difference, 13.7 vs 13.5 ms at cfg4)
   const int ky = blockIdx.x / tiles_z, zt = blockIdx.x % tiles_z;
   // element (x, ky, zt, c): row-major  x*L*NZ + ky*NZ + zt*C + c;  blocked  ((((ky/16)*L + x)*tiles_z + zt)*16 + ky%16)*C + c
   const size_t xstride = fs.blocked ? size_t(tiles_z) * (kYB * C) : size_t(L) * NZ;
@@ -727,6 +730,9 @@ extern "C" int vp_pk_fields(vp_pk_plan* pl, float* const* field_d, int ncomp, do
   fs.n = ncomp;
   fs.blocked = 1;
   for (int c = 0; c < 3; ++c) fs.f[c] = nullptr;
+  // (Alternating the z and y passes over groups of 8-32 x planes, so that a group's z-pass output is still in L2 when its y
+  // pass reads it, was measured and lost: 26.9 / 23.7 / 33.0 ms for groups of 16 / 32 / 8 planes against 19.1 ms for whole-cube
+  // passes at cfg4 -- the short launches do not fill the machine.)
   for (int c = 0; c < ncomp; ++c) {
     VP_REQUIRE(field_d[c], "vp_pk_fields: null field %d", c);
     VP_TRY(run_z(field_d[c], N, N, pl, st));

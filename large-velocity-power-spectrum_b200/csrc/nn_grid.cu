@@ -185,24 +185,24 @@ struct PayloadIn {
 // particles are ranked per bucket with shared-memory atomics, every touched bucket claims ONE contiguous run of slots from
 // its sub-stream cursor, and the records go straight from registers to their slots: all records of a run are written
 // within the same few microseconds, and temporally adjacent tiles append adjacent runs, so L2 assembles whole lines.
-template <typename T, bool PAY>
-__global__ void __launch_bounds__(1024, 2) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
-                                                          uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
+template <typename T, bool PAY, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
+                                                                        uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
   // pos / pin.vel / pin.rho point at particle i0 (a chunk); the stored index is global (i0 + local).
   // 32 registers per thread = two CTAs per SM, so that one tile's loads overlap the other's stores: only the search half
   // of the record is carried across the two barriers, the payload is loaded right before the store.  (Persistent CTAs with
   // all position loads hoisted in front were slower: 31.0 vs 25.4 ms at 2^30 particles.)
   extern __shared__ uint32_t sh_cnt[];          // [nb] particles of this tile per bucket, then the first slot of its run
-  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) sh_cnt[b] = 0u;
+  for (uint32_t b = threadIdx.x; b < g.nb; b += THREADS) sh_cnt[b] = 0u;
   __syncthreads();
-  constexpr int kItems = kBinTile / 1024;
-  const uint32_t sub = ((tile0 + blockIdx.x) / kClu) % kSub;
-  const int64_t base = int64_t(blockIdx.x) * kBinTile;
+  constexpr int kItems = 4, kTile = THREADS * kItems;     // (kTile divides kBinTile: the sub-stream is that of the histogram's tile)
+  const uint32_t sub = ((tile0 + uint32_t((int64_t(blockIdx.x) * kTile) / kBinTile)) / kClu) % kSub;
+  const int64_t base = int64_t(blockIdx.x) * kTile;
   uint32_t ra[kItems][3], slot[kItems];          // fixed-point offsets (2 words), linear cell; bucket-local rank, later the slot
   bool farv[kItems];
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
-    const int64_t i = base + r * 1024 + threadIdx.x;
+    const int64_t i = base + r * THREADS + threadIdx.x;
     slot[r] = 0xffffffffu;
     farv[r] = false;
     double x, y, z;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(1024, 2) k_bin_scatter(const T* __restrict__ p
     farv[r] = far;
   }
   __syncthreads();
-  for (uint32_t b = threadIdx.x; b < g.nb; b += 1024) {
+  for (uint32_t b = threadIdx.x; b < g.nb; b += THREADS) {
     const uint32_t c = sh_cnt[b];
     if (c) sh_cnt[b] = atomicAdd(cursor + b * kSub + sub, c);
   }
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(1024, 2) k_bin_scatter(const T* __restrict__ p
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     if (slot[r] == 0xffffffffu) continue;
-    const int64_t i = base + r * 1024 + threadIdx.x;
+    const int64_t i = base + r * THREADS + threadIdx.x;
     const uint32_t dst = sh_cnt[ra[r][2] >> g.bshift] + slot[r];
     const uint32_t idx = uint32_t(i0 + i) | (farv[r] ? kFarBit : 0u);
     if (PAY) {
@@ -653,6 +653,18 @@ constexpr size_t kBrickOffNq = kBrickOffSeg + (3 * size_t(kBRows) + 4) * 4;
 constexpr size_t kBrickSmem = kBrickOffNq + size_t(kNX + kNY + kNZ + 2) * 4 + size_t(kBX) * 4;
 
 __host__ __device__ constexpr int brick_off(int q) { return (q >> 2) * (kNY * kNZ) + ((q >> 1) & 1) * kNZ + (q & 1); }
+// h = word at [base + OFF words] (shared-memory address); if key < h the atomicMin is issued and h becomes what it returned.
+// Predicated, so that the common path carries no branch bookkeeping (BSSY / BRA / BSYNC around an `if`).
+template <int OFF>
+__device__ __forceinline__ uint32_t brick_try_min(uint32_t base, uint32_t key) {
+  uint32_t h;
+  asm volatile(
+      "{\n .reg .pred p;\n ld.shared.u32 %0, [%1+%3];\n setp.lt.u32 p, %2, %0;\n @p atom.shared.min.u32 %0, [%1+%3], %2;\n}"
+      : "=&r"(h)
+      : "r"(base), "r"(key), "n"(OFF * 4)
+      : "memory");
+  return h;
+}
 
 __global__ void __launch_bounds__(kBThreads, 5) k_search_brick(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start,
                                                                 Grid g, Lattice L, float eps, BrickQ bq, SearchOut out) {
@@ -725,6 +737,7 @@ __global__ void __launch_bounds__(kBThreads, 5) k_search_brick(const rec_t* __re
   }
   const int nthr_yz = (j < L.ny && k < L.nz) ? min(__ldg(bq.ty + j), __ldg(bq.tz + k)) : -1;
   const float ihz = float(g.ihz);
+  const uint32_t nt = bq.nt;
   for (int xa = 0; xa < kBX; xa += planes) {
     const int r0 = xa * (kBY + 1), nrows = (planes + 1) * (kBY + 1);
     const uint32_t sb = seg_off[r0], count = seg_off[r0 + nrows] - sb;
@@ -761,18 +774,23 @@ __global__ void __launch_bounds__(kBThreads, 5) k_search_brick(const rec_t* __re
       const uint32_t uz0 = quant(nqz[cz] - pz) - 0xE1000000u, uz1 = quant(nqz[cz + 1] - pz) - 0xE1000000u;
       const uint32_t t2 = t << 1;
       uint32_t* m = nkey + (cx * kNY + cy) * kNZ + uint32_t(cz);
-#pragma unroll
-      for (int qd = 0; qd < 8; ++qd) {
-        const uint32_t n = ((qd & 4) ? ux1 : ux0) + ((qd & 2) ? uy1 : uy0) + ((qd & 1) ? uz1 : uz0);
-        const uint32_t key = (n << (kSlotBits + 1)) + t2;
-        uint32_t h = m[brick_off(qd)];
-        if (key < h) h = atomicMin(m + brick_off(qd), key);
-        const uint32_t nh = h >> (kSlotBits + 1);
-        if (n - nh + bq.nt <= 2u * bq.nt && n < kQ - bq.nt) {          // rare: neither clearly better nor clearly worse
-          const float dc = float(n) * bq.invS, M = float(nh) * bq.invS, dm = fmaxf(dc, M);
-          if (fabsf(dc - M) <= 2.f * (8.f * sqrtf(dm) * eps + 8.f * eps * eps + 1e-6f * dm) + bq.q2) atomicOr(m + brick_off(qd), 1u);
-        }
+      const uint32_t msh = uint32_t(__cvta_generic_to_shared(m));
+      // corner qd = 4a + 2b + c (x, y, z offsets): key, predicated atomicMin, rare ambiguity path
+#define VP_BRICK_CORNER(QD)                                                                                                \
+      {                                                                                                                     \
+        const uint32_t n = ((QD & 4) ? ux1 : ux0) + ((QD & 2) ? uy1 : uy0) + ((QD & 1) ? uz1 : uz0);                        \
+        const uint32_t key = (n << (kSlotBits + 1)) + t2;                                                                   \
+        const uint32_t h = brick_try_min<brick_off(QD)>(msh, key);                                                          \
+        const uint32_t nh = h >> (kSlotBits + 1);                                                                           \
+        if (n - nh + nt <= 2u * nt && n < kQ - nt) { /* rare: neither clearly better nor clearly worse */                   \
+          const float dc = float(n) * bq.invS, M = float(nh) * bq.invS, dm = fmaxf(dc, M);                                  \
+          if (fabsf(dc - M) <= 2.f * (8.f * sqrtf(dm) * eps + 8.f * eps * eps + 1e-6f * dm) + bq.q2)                        \
+            atomicOr(m + brick_off(QD), 1u);                                                                                \
+        }                                                                                                                   \
       }
+      VP_BRICK_CORNER(0) VP_BRICK_CORNER(1) VP_BRICK_CORNER(2) VP_BRICK_CORNER(3)
+      VP_BRICK_CORNER(4) VP_BRICK_CORNER(5) VP_BRICK_CORNER(6) VP_BRICK_CORNER(7)
+#undef VP_BRICK_CORNER
     }
     __syncthreads();
     // ---- pass 3: one thread per node (k = lane: plane stores are coalesced)
@@ -1361,8 +1379,10 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         if (has_pay) k_bin_scatter_clu<T, true><<<nbc, 1024, 2 * ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
         else k_bin_scatter_clu<T, false><<<nbc, 1024, 2 * ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
       } else {
-        if (has_pay) k_bin_scatter<T, true><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
-        else k_bin_scatter<T, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+        // (512-thread CTAs on 2048-particle tiles, four per SM instead of two: 25.1 vs 24.7 ms at cfg4 -- the phases of a tile
+        // are not what limits this kernel)
+        if (has_pay) k_bin_scatter<T, true, 1024><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+        else k_bin_scatter<T, false, 1024><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
       }
     };
     if (host_pos) {

@@ -12,11 +12,16 @@ import re
 import sys
 from collections import defaultdict
 
-STAGE_OF = [  # kernel name prefix -> stage label used by vp_stage (csrc/*.cu)
-    ("k_keygen_pack", "k1a_keygen_pack"), ("k_tile_hist", "k1b_radix_sort"), ("k_scan_", "k1b_radix_sort"),
+STAGE_OF = [  # kernel name prefix -> stage label used by vp_stage (csrc/*.cu); round-2 kernels first, round-1 names kept
+    ("k_bin_hist", "k1a_bin_hist"), ("k_bin_offsets", "k1a_bin_hist"), ("k_bin_scatter", "k1b_bin_scatter"),
+    ("k_cell_count", "k1c_cell_count"), ("k_scan_", "k1d_cell_scan"), ("k_cell_place", "k1e_cell_place"),
+    ("k_search_brick", "k1f_search_brick"), ("k_search_crowded", "k1f_search_brick"), ("k_search_rows", "k1f_search_rows"),
+    ("k_search_block4", "k1g_search_block4"), ("k_search_exact", "k1h_search_exact"),
+    ("k_fft_x_pow", "k4c_fft_x_pow"), ("k_bin_tiles", "k5_bin_tiles"),
+    ("k_keygen_pack", "k1a_keygen_pack"), ("k_tile_hist", "k1b_radix_sort"),
     ("k_scatter", "k1b_radix_sort"), ("k_row_starts", "k1d_row_starts"), ("k_group_rows", "k1c_group_rows"),
-    ("k_permute", "k1c_permute"), ("k_search_block2", "k1e_search_block2"), ("k_search_block4", "k1e_search_block4"),
-    ("k_search_exact", "k1f_search_exact"), ("k_fields_sorted", "k3_fields_sorted"), ("k_fft_z", "k4a_fft_z"),
+    ("k_permute", "k1c_permute"), ("k_search_block2", "k1e_search_block2"),
+    ("k_fields_sorted", "k3_fields_sorted"), ("k_fft_z", "k4a_fft_z"),
     ("k_fft_y", "k4b_fft_y"), ("k_fft_x_bin", "k4c_fft_x_bin"), ("k_plane_bin", "k5_plane_bin"),
 ]
 

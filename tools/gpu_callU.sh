@@ -1,0 +1,15 @@
+set -x
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+python __graft_entry__.py 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "nn or golden or library or cfg or slab or spot or script" > gpurun_out/r2u_pytest.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/r2u_pytest.log
+for v in 20 21 19; do
+VP_BUCKET_LOG2=$v timeout 900 python bench.py --workload cfg4 --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/r2u_bench_b$v.json 2> gpurun_out/r2u_bench_b$v.err; echo "bench rc=$?"
+python - <<P
+import json
+d=json.loads(open('gpurun_out/r2u_bench_b$v.json').read().strip().splitlines()[-1])
+print($v, d['ms_per_step'], d['nn_stats'], d['result']['nsample_crc32'])
+for k,v in d['stages'].items():
+    if k.startswith('k1'): print(k, v['ms_per_step'])
+P
+done
