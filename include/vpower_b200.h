@@ -213,8 +213,10 @@ int vp_pk_dist_p2p_close(vp_pk_plan* plan);
 
 /* Sharded particle input for the slab decomposition: every particle of this rank's subset is copied into the block of
  * each destination rank d whose kept range lo_h[d] <= x <= hi_h[d] contains it (use -/+ infinity for open ends).
- *   rows_d   [cap_rows, 7 (6 without rho)] of dtype: x y z vx vy vz rho, blocks in rank order;  counts_h[d] = rows for rank d.
- * One counting pass, one scatter pass, one global atomic per block and destination.  Syncs (the split sizes of the
+ *   rows_d   [cap_rows, 8] of dtype: x y z vx vy vz rho 0 (rho = 0 when rho_d is NULL; the pad makes a row one or two whole
+ *            32-byte sectors and every run 16-byte aligned), blocks in rank order;  counts_h[d] = rows for rank d.
+ * One counting pass, one scatter pass (rows grouped in shared memory, one global atomic and ONE bulk copy shared -> global
+ * -- cp.async.bulk, the TMA engine -- per tile and destination).  Syncs (the split sizes of the
  * all-to-all are needed on the host).  nranks <= 16. */
 int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void* rho_d, int dtype, int64_t np,
                    const double* lo_h, const double* hi_h, int nranks, void* rows_d, int64_t cap_rows, int64_t* counts_h,
@@ -222,8 +224,8 @@ int vp_slab_bucket(vp_ctx* ctx, const void* pos_d, const void* vel_d, const void
 
 /* The same exchange FUSED into the bucketing kernel: each rank owns a receive buffer (allocated here, exported with CUDA
  * IPC, mapped by every peer); after vp_slab_count and an exchange of the counts (any transport) every rank knows the
- * first row it may write in each destination's buffer, and vp_slab_scatter_p2p stores the rows there directly (own HBM
- * or NVLink peer stores).  The caller separates "all ranks have stored" from "this rank reads" with a stream-ordered
+ * first row it may write in each destination's buffer, and vp_slab_scatter_p2p stores the rows (8 elements each, as above)
+ * there directly: bulk copies from shared memory into own HBM or, over NVLink, into the peers' buffers.  The caller separates "all ranks have stored" from "this rank reads" with a stream-ordered
  * barrier across ranks.  Rows of one destination arrive grouped by source rank, in rank order. */
 /* Lifetime of the shared buffers (CUDA leaves freeing an exported allocation that a peer still maps undefined): to grow or
  * drop them, EVERY rank calls vp_slab_p2p_close (unmaps the peers; syncs the device), the caller runs a barrier across the

@@ -18,6 +18,7 @@
 // deciding arithmetic is f64 with the reference's association ((dx*dx+dy*dy)+dz*dz) and no FMA
 // contraction (explicit __dmul_rn/__dadd_rn); ties go to the lowest particle index.
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 
 #include <cooperative_groups.h>
@@ -1368,7 +1369,10 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       attr_done = true;
     }
     auto launch_hist = [&](const T* p, int64_t n_c, int64_t i0) {
-      const int64_t nt = (n_c + kBinTile - 1) / kBinTile, cap = int64_t(ctx->sm_count) * 4;
+      // persistent CTAs: as many as the shared-memory histograms allow per SM (ncu: the kernel waits on its position loads --
+      // 68 % long-scoreboard stalls at 4 CTAs/SM)
+      const int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (size_t(220) << 10) / (hsmem + 1024))));
+      const int64_t nt = (n_c + kBinTile - 1) / kBinTile, cap = int64_t(ctx->sm_count) * per_sm;
       k_bin_hist<T><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
     };
     auto launch_scatter = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
@@ -1526,25 +1530,37 @@ __global__ void __launch_bounds__(256) k_bucket_count(const T* __restrict__ pos,
   if (threadIdx.x < R.n && sc[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
 }
 
-// rows = [x y z vx vy vz (rho)] ; cursors[d] starts at the first row this rank may write in destination d's buffer
-// (exclusive prefix of counts for the single local buffer; with peer stores, the rows of lower ranks for d).
+// rows = [x y z vx vy vz rho 0]: kSlabW = 8 elements (32 bytes in f32, 64 in f64; rho = 0 when absent) -- a padded row is one
+// or two whole sectors and every run of rows is 16-byte aligned, which is what the bulk store below needs.
+// cursors[d] starts at the first row this rank may write in destination d's buffer (exclusive prefix of counts for the
+// single local buffer; with peer stores, the rows of lower ranks for d).
 struct SlabDest {
   void* base[16];   // all equal for the local form; peer-mapped receive buffers for the fused exchange
 };
+constexpr int kSlabW = 8;
 // Tiles of 512 x ITEMS particles per CTA (2048 for f32).  Pass 1: which destinations take each particle (one ballot per
 // destination and item; only the per-warp counts are kept).  Then ONE contiguous row range is claimed per destination
 // (one global atomic each) and the same ballots are formed again to place every row in shared memory, grouped by
-// destination; each group leaves as one coalesced run -- 128-byte store instructions whether the destination is local
-// HBM or a peer's buffer over NVLink.  Rows that do not fit the staging area (very wide halos) are stored directly.
+// destination (vector stores).  Each group then leaves as ONE bulk copy shared -> global issued by a single thread
+// (cp.async.bulk, the TMA engine; SASS UBLKCP): whole lines whether the destination is local HBM or a peer's buffer over
+// NVLink, and no thread spends issue slots on the copy.  Rows that do not fit the staging area (very wide halos) are
+// stored directly.
 template <typename T> struct SlabTile { static constexpr int items = sizeof(T) == 4 ? 4 : 2; };
-template <typename T, int W>
+__device__ __forceinline__ void slab_store_row(float* o, const float (&r)[kSlabW]) {
+  reinterpret_cast<float4*>(o)[0] = make_float4(r[0], r[1], r[2], r[3]);
+  reinterpret_cast<float4*>(o)[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+__device__ __forceinline__ void slab_store_row(double* o, const double (&r)[kSlabW]) {
+#pragma unroll
+  for (int c = 0; c < kSlabW; c += 2) reinterpret_cast<double2*>(o)[c / 2] = make_double2(r[c], r[c + 1]);
+}
+template <typename T>
 __global__ void __launch_bounds__(512) k_bucket_scatter(const T* __restrict__ pos, const T* __restrict__ vel, const T* __restrict__ rho,
                                                          int64_t np, SlabRanges R, unsigned long long* __restrict__ cursors,
                                                          SlabDest D, int cap_rows) {
   constexpr int ITEMS = SlabTile<T>::items;
-  constexpr int w = W;
-  extern __shared__ __align__(16) unsigned char slab_smem[];
-  T* stage = reinterpret_cast<T*>(slab_smem);            // [cap_rows][w]
+  extern __shared__ __align__(128) unsigned char slab_smem[];
+  T* stage = reinterpret_cast<T*>(slab_smem);            // [cap_rows][kSlabW]
   __shared__ unsigned wcnt[ITEMS][16][16];                 // [item][warp][destination]: count, then first staged row
   __shared__ unsigned pre[17];                             // exclusive prefix of the rows per destination
   __shared__ unsigned long long sbase[16];
@@ -1584,11 +1600,12 @@ __global__ void __launch_bounds__(512) k_bucket_scatter(const T* __restrict__ po
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const int64_t i = i0 + r * 512 + tid;
-    T row[7];
+    T row[kSlabW];
     if (okv[r]) {
       row[0] = pos[3 * i]; row[1] = pos[3 * i + 1]; row[2] = pos[3 * i + 2];
       row[3] = vel[3 * i]; row[4] = vel[3 * i + 1]; row[5] = vel[3 * i + 2];
       row[6] = rho ? rho[i] : T(0);
+      row[7] = T(0);
     }
     for (int d = 0; d < R.n; ++d) {
       const bool in = okv[r] && x[r] >= R.lo[d] && x[r] <= R.hi[d];
@@ -1596,24 +1613,25 @@ __global__ void __launch_bounds__(512) k_bucket_scatter(const T* __restrict__ po
       if (in) {
         const unsigned rank = wcnt[r][wp][d] + __popc(m & ((1u << lane) - 1u));
         const unsigned p = pre[d] + rank;
-        if (p < unsigned(cap_rows)) {
-#pragma unroll
-          for (int c = 0; c < W; ++c) stage[p * W + c] = row[c];
-        } else {   // staging area full: store directly
-          T* o = static_cast<T*>(D.base[d]) + (sbase[d] + rank) * size_t(w);
-#pragma unroll
-          for (int c = 0; c < W; ++c) o[c] = row[c];
-        }
+        if (p < unsigned(cap_rows)) slab_store_row(stage + size_t(p) * kSlabW, row);
+        else slab_store_row(static_cast<T*>(D.base[d]) + (sbase[d] + rank) * size_t(kSlabW), row);   // staging area full
       }
     }
   }
+  // the staged rows were written through the generic proxy; the bulk copy reads them through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  for (int d = 0; d < R.n; ++d) {
+  if (tid < R.n) {
+    const int d = tid;
     const unsigned r0 = min(pre[d], unsigned(cap_rows)), r1 = min(pre[d + 1], unsigned(cap_rows));
-    const T* src = stage + size_t(r0) * w;
-    T* dst = static_cast<T*>(D.base[d]) + (sbase[d] + (r0 - pre[d])) * size_t(w);
-    const unsigned nel = (r1 - r0) * unsigned(w);
-    for (unsigned e = tid; e < nel; e += 512) dst[e] = src[e];
+    if (r1 > r0) {
+      const uint32_t src = uint32_t(__cvta_generic_to_shared(stage + size_t(r0) * kSlabW));
+      T* dst = static_cast<T*>(D.base[d]) + (sbase[d] + (r0 - pre[d])) * size_t(kSlabW);
+      const uint32_t bytes = (r1 - r0) * uint32_t(kSlabW * sizeof(T));
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // complete (not only read) before the CTA retires
+    }
   }
 }
 
@@ -1634,7 +1652,7 @@ int slab_bucket_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int
   unsigned long long* cur = cnt + 16;
   VP_CUDA(cudaMemsetAsync(cnt, 0, 512, st));
   const unsigned nb = unsigned((np + 255) / 256);
-  const int w = rho ? 7 : 6;
+  const int w = kSlabW;
   if (np > 0) {
     vp_stage stage(ctx, "k0_slab_bucket_count", st, 1, double(np) * 3.0 * sizeof(T));
     k_bucket_count<T><<<nb, 256, 0, st>>>(pos, np, R, cnt);
@@ -1652,15 +1670,13 @@ int slab_bucket_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho, int
     for (int d = 0; d < 16; ++d) D.base[d] = rows;
     constexpr int kTile = 512 * SlabTile<T>::items;
     const int cap_rows = kTile + kTile / 4;                 // a particle inside a halo goes to two ranks
-    const size_t smem = size_t(cap_rows) * 7 * sizeof(T);
+    const size_t smem = size_t(cap_rows) * kSlabW * sizeof(T);
     static bool attr = false;
     if (!attr) {
-      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       attr = true;
     }
-    if (w == 7) k_bucket_scatter<T, 7><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
-    else k_bucket_scatter<T, 6><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
+    k_bucket_scatter<T><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
   }
   VP_CHECK_LAUNCH();
   VP_CUDA(cudaStreamSynchronize(st));   // cnt/cur live in the scope released on return
@@ -1695,22 +1711,20 @@ int slab_scatter_p2p_typed(vp_ctx* ctx, const T* pos, const T* vel, const T* rho
   unsigned long long h[16];
   for (int d = 0; d < 16; ++d) h[d] = d < R.n ? (unsigned long long)first_row_h[d] : 0ull;
   VP_CUDA(cudaMemcpyAsync(cur, h, sizeof h, cudaMemcpyHostToDevice, st));
-  const int w = rho ? 7 : 6;
+  const int w = kSlabW;
   if (np > 0) {
     vp_stage stage(ctx, "k0_slab_bucket_scatter", st, 1, double(np) * 2.0 * w * sizeof(T));
     SlabDest D;
     for (int d = 0; d < 16; ++d) D.base[d] = d < R.n ? ctx->slab_peer[d] : nullptr;
     constexpr int kTile = 512 * SlabTile<T>::items;
     const int cap_rows = kTile + kTile / 4;                 // a particle inside a halo goes to two ranks
-    const size_t smem = size_t(cap_rows) * 7 * sizeof(T);
+    const size_t smem = size_t(cap_rows) * kSlabW * sizeof(T);
     static bool attr = false;
     if (!attr) {
-      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      VP_CUDA(cudaFuncSetAttribute(k_bucket_scatter<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       attr = true;
     }
-    if (w == 7) k_bucket_scatter<T, 7><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
-    else k_bucket_scatter<T, 6><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
+    k_bucket_scatter<T><<<unsigned((np + kTile - 1) / kTile), 512, smem, st>>>(pos, vel, rho, np, R, cur, D, cap_rows);
     VP_CHECK_LAUNCH();
   }
   VP_CUDA(cudaStreamSynchronize(st));   // cur lives in the scope released on return

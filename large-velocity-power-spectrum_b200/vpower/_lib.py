@@ -202,11 +202,12 @@ def nn_grid(pos_t, qx, qy, qz, opts: NNOpts | None = None):
 
 
 def slab_bucket(pos_t, vel_t, rho_t, lo, hi):
-    """Sharded input -> rows [n,7|6] grouped by destination rank + counts per rank (see vp_slab_bucket)."""
+    """Sharded input -> rows [n,8] = [x y z vx vy vz rho 0] grouped by destination rank + counts per rank (see vp_slab_bucket;
+    rho = 0 when absent)."""
     torch = _torch()
     P = len(lo)
     n = pos_t.shape[0]
-    w = 7 if rho_t is not None else 6
+    w = SLAB_ROW
     lo_a, lop = _as_dp(lo)
     hi_a, hip = _as_dp(hi)
     cap = n + n // 2 + 1024          # halo duplicates; if that is too small the call reports the exact need in `counts`
@@ -224,6 +225,9 @@ def slab_bucket(pos_t, vel_t, rho_t, lo, hi):
         cap = need                               # wide halos can send a particle to every rank: up to P * n rows
     counts = [int(c) for c in counts]
     return rows[:sum(counts)], counts
+
+
+SLAB_ROW = 8          # elements per exchanged particle row (padded: whole 32-byte sectors, 16-byte aligned runs)
 
 
 class _RawCuda:
@@ -259,7 +263,7 @@ class SlabExchangeP2P:
         self.cap_bytes = cap
 
     def exchange(self, pos_t, vel_t, rho_t, lo, hi):
-        """-> torch tensor [rows, 7|6] ALIASING this rank's receive buffer (all particles of its slab + halo).  It is valid
+        """-> torch tensor [rows, 8] ALIASING this rank's receive buffer (all particles of its slab + halo).  It is valid
         until the next exchange() on this object (which overwrites, and may re-allocate, the buffer): clone it to keep it."""
         torch = _torch()
         import torch.distributed as dist
@@ -267,7 +271,7 @@ class SlabExchangeP2P:
         lo_a, lop = _as_dp(lo)
         hi_a, hip = _as_dp(hi)
         n = pos_t.shape[0]
-        w = 7 if rho_t is not None else 6
+        w = SLAB_ROW
         es = pos_t.element_size()
         counts = (_L * P)()
         _check(load_library().vp_slab_count(ctx(), _P(pos_t.data_ptr()), _dtype_code(pos_t), n, lop, hip, P, counts, stream_ptr()))
@@ -278,6 +282,7 @@ class SlabExchangeP2P:
         need = int(M.sum(axis=0).max()) * w * es                       # the fullest receive buffer, same on every rank
         self._ensure(need)
         first = (_L * P)(*[int(M[:self.rank, d].sum()) for d in range(P)])
+        self.last_peer_bytes = int((M[self.rank].sum() - M[self.rank, self.rank]) * w * es)    # rows this rank stores into peers
         # barrier: every rank has finished reading its receive buffer from the previous exchange (stream ordered)
         tok = torch.zeros(1, device=pos_t.device)
         dist.all_reduce(tok, group=self.group)

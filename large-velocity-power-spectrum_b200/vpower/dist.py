@@ -218,6 +218,13 @@ def particles_to_pk_dist(pos, vel, rho, ax, lcell3, norm, k_axis, edges, quantit
         halo = min(2 * halo, max_halo_cells)
     if timings is not None:
         timings["halo_cells"] = halo
+        # bytes this rank stores into the other ranks' buffers (exact, from the exchange tables): the particle rows, and per
+        # transformed component the kz columns of its x slab that other ranks own
+        sx = getattr(backend, "slab_x", None)
+        ncomp_total = sum(3 if (q == "velocity" or (q == "momentum" and not momentum_strict)) else 1 for q in quantities)
+        timings["nvlink_bytes"] = {
+            "particle_exchange": int(getattr(sx, "last_peer_bytes", 0)) if (sharded and sx is not None) else 0,
+            "transpose": int(ncomp_total * (x1 - x0) * N * (N // 2) * 8 * (nranks - 1) // nranks) if getattr(backend, "p2p", False) else 0}
 
     out = {}
     ns_total = None

@@ -496,11 +496,13 @@ def test_slab_bucket_kernel(lib):
         assert counts[d] == int(m.sum())
         blk = got[at:at + counts[d]]
         at += counts[d]
+        assert blk.shape[1] == 8 and not blk[:, 7].any()                 # padded rows: whole 32-byte sectors
+        blk = blk[:, :7]
         a = blk[np.lexsort(blk.T[::-1])]
         b = ref[m][np.lexsort(ref[m].T[::-1])]
         assert np.array_equal(a, b)
     rows6, counts6 = lib.slab_bucket(pos, vel, None, lo, hi)
-    assert counts6 == counts and rows6.shape[1] == 6
+    assert counts6 == counts and rows6.shape[1] == 8 and not rows6[:sum(counts6), 6:].any().item()
 
 
 def test_fft_2048_single_mode_and_low_shells(lib, orc):
