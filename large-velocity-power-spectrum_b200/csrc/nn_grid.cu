@@ -869,7 +869,8 @@ __global__ void __launch_bounds__(256, 6) k_search_crowded(const rec_t* __restri
 // Stage B: the nodes stage A could not prove, one thread per listed node, the 32-cell union of the three 4x2x2 bars
 // through the window (proves sqrt(2) h with corner-aligned nodes), same f32 prefilter and verdict.  What is still
 // unproven or ambiguous goes to the exact kernel.
-__global__ void __launch_bounds__(256) k_search_block4(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_search_block4(const rec_t* __restrict__ part, int rs, const uint32_t* __restrict__ start, Grid g,
                                                         Lattice L, float eps, SearchOut out) {
   const unsigned long long nb = out.stats->n_b;
   const bool far = out.stats->n_far != 0;
@@ -1484,7 +1485,11 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   }
   {
     vp_stage stage(ctx, "k1g_search_block4", st, 1);
-    k_search_block4<<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
+    // latency bound (ncu: 92 % long-scoreboard stalls): more resident warps beat a few spilled registers -- 4 / 5 / 6 CTAs per SM
+    static const int b4occ = getenv("VP_B4_OCC") ? atoi(getenv("VP_B4_OCC")) : 6;
+    if (b4occ <= 4) k_search_block4<4><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
+    else if (b4occ == 5) k_search_block4<5><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
+    else k_search_block4<6><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
   }
   {
     vp_stage stage(ctx, "k1h_search_exact", st, 1);

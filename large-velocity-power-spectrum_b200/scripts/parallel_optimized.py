@@ -198,12 +198,14 @@ def main(argv=None):
         out, ns = _lib.particles_to_pk(pos32, vel32, None, ax, ax, ax, NTOT_, LCELL ** 3, 0.5 * const * const, kax, edges,
                                        quantities=("velocity",))
     if rank == 0:
-        Psum = out["velocity"].astype(np.float32).astype(np.float64)                 # :436-438 float32 on the wire
-        Nsample = ns.astype(np.float32).astype(np.float64)
+        # :436-461 -- the reference holds the table as float32 and forms P in float32 from the float32-rounded k
+        Pkk = np.empty((len(centres), 4), dtype=np.float32)
+        Pkk[:, 0] = centres
+        Pkk[:, 2] = out["velocity"]
+        Pkk[:, 3] = ns
         with warnings.catch_warnings(), np.errstate(invalid="ignore", divide="ignore"):
             warnings.simplefilter("ignore")
-            P = Psum / Nsample * (4 * np.pi * centres ** 2)                          # :434, 461
-        Pkk = np.column_stack((centres.astype(np.float32).astype(np.float64), P, Psum, Nsample))
+            Pkk[:, 1] = Pkk[:, 2] / Pkk[:, 3] * (4 * np.pi * Pkk[:, 0] ** 2)
         np.savetxt(outputfile, Pkk)                                                  # :473
         print(f"[{datetime.datetime.now()}] Saved: {outputfile}", flush=True)
     if world > 1:
