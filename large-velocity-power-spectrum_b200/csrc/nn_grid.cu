@@ -1485,8 +1485,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
   }
   {
     vp_stage stage(ctx, "k1g_search_block4", st, 1);
-    // latency bound (ncu: 92 % long-scoreboard stalls): more resident warps beat a few spilled registers -- 4 / 5 / 6 CTAs per SM
-    static const int b4occ = getenv("VP_B4_OCC") ? atoi(getenv("VP_B4_OCC")) : 6;
+    // latency bound (ncu: 92 % long-scoreboard stalls), yet more resident warps lose: 10.4 / 11.0 / 12.7 ms at 4 / 5 / 6 CTAs per
+    // SM (60 / 48 / 40 registers) -- the spills and the extra DRAM pressure cost more than the occupancy gives
+    static const int b4occ = getenv("VP_B4_OCC") ? atoi(getenv("VP_B4_OCC")) : 4;
     if (b4occ <= 4) k_search_block4<4><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
     else if (b4occ == 5) k_search_block4<5><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
     else k_search_block4<6><<<ctx->sm_count * 8, 256, 0, st>>>(srec, rs, start, g, L, eps, so);
