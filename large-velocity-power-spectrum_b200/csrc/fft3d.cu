@@ -6,6 +6,7 @@
 // so the whole transform is in place with a power-of-two pitch.  The kz=0 column therefore carries two real
 // planes a+ib through the y and x passes; they are separated at the end by Hermitian symmetry
 // (k_plane_bin), all other columns are ordinary half-spectrum modes with weight 2.
+#include <cuda.h>   // CUtensorMap and its enums (types only: the encoder is looked up through the runtime, no -lcuda)
 #include <math.h>
 #include <stdlib.h>
 
@@ -192,6 +193,142 @@ __global__ void __launch_bounds__(R2* R3* C, (R2 * R3 * C <= 512 ? 2 : 1)) k_fft
       float q = pt[cc * PP + r];
       if (r > 0 && r < L / 2) q += pt[cc * PP + L - r];
       out[i] = q;
+    }
+  }
+}
+
+// ---- the same x pass fed by the TMA engine (blocked layout only) ------------------------------------------------------------
+// One persistent CTA per shared-memory slot of the SM walks its tiles; the components of its tiles form one stream of "items".
+// An item (one component of one (ky, kz-tile)) is L x C complex values that lie in the blocked half spectrum as L pieces of
+// C*8 bytes, one per x plane: as a 5-D tensor  [ky block][x][kz tile][ky in block][c]  that is NBOX boxes of  BX x 1 x 1 x 1 x C
+// elements, which ONE thread requests with cp.async.bulk.tensor (SASS UTMALDG) into a ring of NST item buffers; the
+// boxes of an item complete on the item's mbarrier (complete_tx).  While the CTA transforms item m out of its registers, the
+// TMA engine fills the buffers of items m+1 .. m+NST -- the loads the old kernel issued per thread (sixteen strided 8-byte
+// LDGs, nothing in flight during the butterflies) are off the instruction stream altogether.  The sum over components of
+// |F|^2 stays in registers (same thread, same slots for every component) and goes through the exchange area once per tile.
+struct XMaps {
+  CUtensorMap m[3];
+};
+template <int L>
+__host__ __device__ constexpr int xbox_of() { return L <= 256 ? L : (L % 256 == 0 ? 256 : 250); }   // x planes per box (<= 256, divides L)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_box_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <int R1, int R2, int R3, int C>
+struct XTma {
+  using F = LineFFT<R1, R2, R3, C>;
+  static constexpr int L = F::L, T = F::T, NT = T * C, BX = xbox_of<L>(), NBOX = L / BX;
+  static constexpr int BOXB = BX * C * 8, BOXP = (BOXB + 127) / 128 * 128;        // bytes of a box; its slot (TMA wants 128-byte aligned destinations)
+  static constexpr int ITEMB = NBOX * BOXP;
+  static constexpr int XSB = (xsize<L, C>() * 8 + 127) / 128 * 128;                // exchange area (also holds the [C][L+4] power tile)
+  static constexpr int NST = (2 * ITEMB + XSB + 64 <= 227 * 1024) ? 2 : 1;         // item buffers in the ring
+  static constexpr int SMEM = NST * ITEMB + XSB + 64;
+  static constexpr bool ok = (C * 8) % 16 == 0 && (ITEMB + XSB + 64 <= 227 * 1024) && NT <= 1024;
+};
+
+template <int R1, int R2, int R3, int C>
+__global__ void __launch_bounds__(R2* R3* C) k_fft_x_pow_tma(const __grid_constant__ XMaps maps, int ncomp, int NZ,
+                                                              const float2* __restrict__ tw, float2* __restrict__ plane0, int kz_offset,
+                                                              float* __restrict__ P, int ntiles) {
+  using X = XTma<R1, R2, R3, C>;
+  using F = typename X::F;
+  constexpr int L = F::L, T = F::T, NT = X::NT, PP = L + 4, NR = L / 2 + 1, NRP = nrp_of<L>(), kYB = yb_of<L>(), BX = X::BX, NST = X::NST;
+  extern __shared__ __align__(128) unsigned char xsm[];
+  unsigned char* ring = xsm;                                                  // [NST][NBOX][BOXP]
+  float2* sm = reinterpret_cast<float2*>(xsm + NST * X::ITEMB);                // exchange area
+  float* pt = reinterpret_cast<float*>(sm);                                    // power tile: the same memory, between two barriers
+  const uint32_t bar0 = smem_u32(xsm + NST * X::ITEMB + X::XSB);               // NST mbarriers
+  const int tid = threadIdx.x, c = tid % C, t = tid / C;
+  const int tiles_z = NZ / C;
+  const int my_tiles = (ntiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int nitems = my_tiles * ncomp;
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // item m of this CTA = component m % ncomp of tile blockIdx.x + (m / ncomp) * gridDim.x; requested by thread 0 only
+  auto request = [&](int tile, int comp, int slot) {
+    const int ky = tile / tiles_z, zt = tile - ky * tiles_z;
+    const uint32_t bar = bar0 + 8 * slot, dst = smem_u32(ring + slot * X::ITEMB);
+    const CUtensorMap* mp = comp == 0 ? &maps.m[0] : (comp == 1 ? &maps.m[1] : &maps.m[2]);
+    mbar_expect_tx(bar, uint32_t(X::NBOX * X::BOXB));
+#pragma unroll
+    for (int q = 0; q < X::NBOX; ++q) tma_box_5d(dst + q * X::BOXP, mp, bar, 0, ky % kYB, zt, q * BX, ky / kYB);
+  };
+  int rq_tile = blockIdx.x, rq_comp = 0, rq_m = 0;                             // next item to request (thread 0)
+  if (tid == 0) {
+    for (; rq_m < NST && rq_m < nitems; ++rq_m) {
+      request(rq_tile, rq_comp, rq_m % NST);
+      if (++rq_comp == ncomp) { rq_comp = 0; rq_tile += gridDim.x; }
+    }
+  }
+  float acc[F::P];
+  int tile = blockIdx.x, comp = 0;
+  for (int m = 0; m < nitems; ++m) {
+    const int slot = m % NST;
+    mbar_wait(bar0 + 8 * slot, uint32_t(m / NST) & 1u);
+    const unsigned char* it = ring + slot * X::ITEMB;
+    float2 v[F::P];
+#pragma unroll
+    for (int j = 0; j < F::P; ++j) {
+      const int x = j * T + t;
+      v[j] = *reinterpret_cast<const float2*>(it + (x / BX) * X::BOXP + ((x % BX) * C + c) * 8);
+    }
+    __syncthreads();   // the item buffer is free again; the previous item's last exchange reads / power-tile reads are done
+    if (tid == 0 && rq_m < nitems) {
+      request(rq_tile, rq_comp, slot);
+      ++rq_m;
+      if (++rq_comp == ncomp) { rq_comp = 0; rq_tile += gridDim.x; }
+    }
+    F::run(v, t, sm + c, tw);
+    const int ky = tile / tiles_z, zt = tile - ky * tiles_z;
+    if (kz_offset + zt * C + c == 0) {
+      float2* pl = plane0 + (size_t(comp) * L + ky) * L;
+#pragma unroll
+      for (int j = 0; j < F::P; ++j) pl[F::kout(j, t)] = v[j];
+    }
+    if (comp == 0) {
+#pragma unroll
+      for (int j = 0; j < F::P; ++j) acc[j] = v[j].x * v[j].x + v[j].y * v[j].y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < F::P; ++j) acc[j] += v[j].x * v[j].x + v[j].y * v[j].y;
+    }
+    if (++comp == ncomp) {
+      __syncthreads();   // the last exchange reads are done: the area becomes the power tile [C][PP]
+      float* col = pt + c * PP;
+#pragma unroll
+      for (int j = 0; j < F::P; ++j) col[F::kout(j, t)] = acc[j];
+      __syncthreads();
+      float* out = P + size_t(tile) * (C * NRP);
+      for (int i = tid; i < C * NRP; i += NT) {
+        const int cc = i / NRP, r = i - cc * NRP;
+        if (r < NR) {
+          float q = pt[cc * PP + r];
+          if (r > 0 && r < L / 2) q += pt[cc * PP + L - r];
+          out[i] = q;
+        }
+      }
+      comp = 0;
+      tile += gridDim.x;
     }
   }
 }
@@ -389,6 +526,33 @@ __global__ void k_expand_power(const float2* __restrict__ packed, int N, double*
 }
 
 // ------------------------------------------------------------------ launch helpers
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library does not link libcuda)
+typedef CUresult (*vp_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes,
+                      const cuuint32_t* box) {
+  static vp_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    VP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    VP_REQUIRE(p && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<vp_encode_tiled_fn>(p);
+  }
+  static const int promo = getenv("VP_X_L2PROMO") ? atoi(getenv("VP_X_L2PROMO")) : 1;   // 0 none, 1 128 B, 2 256 B
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<void*>(base), gdim, gstride_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vp_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, base %p)", int(r), rank, base);
+    return VP_ERR_CUDA;
+  }
+  return VP_OK;
+}
+
 template <int R1, int R2, int R3>
 int launch_z(float* data, int N, int nx, const vp_pk_plan* pl, cudaStream_t st) {
   using F = LineFFT<R1, R2, R3, 1>;
@@ -433,7 +597,36 @@ int launch_x_pow(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, doub
   const size_t smem = size_t(xsize<F::L, C>()) * sizeof(float2) + size_t(C) * (F::L + 4) * sizeof(float);
   static bool attr = false;
   if (!attr) { VP_CUDA(cudaFuncSetAttribute(k_fft_x_pow<R1, R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
-  {
+  using X = XTma<R1, R2, R3, C>;
+  static const bool tma_on = !(getenv("VP_X_TMA") && atoi(getenv("VP_X_TMA")) == 0);
+  const bool use_tma = X::ok && fs.blocked && tma_on;
+  if constexpr (X::ok) if (use_tma) {
+    // blocked half spectrum as a 5-D tensor of f32 (innermost first): [2C][kYB][tiles_z][N (x)][N/kYB]; one box = BX x planes of
+    // one (ky, kz tile): 2C x 1 x 1 x BX x 1
+    constexpr int kYB = yb_of<F::L>();
+    XMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int c = 0; c < fs.n; ++c) {
+      const cuuint64_t gdim[5] = {cuuint64_t(2 * C), cuuint64_t(kYB), cuuint64_t(tiles_z), cuuint64_t(N), cuuint64_t(N / kYB)};
+      const cuuint64_t row = cuuint64_t(C) * 8;
+      const cuuint64_t gstr[4] = {row, row * kYB, row * kYB * tiles_z, row * kYB * tiles_z * N};
+      const cuuint32_t box[5] = {cuuint32_t(2 * C), 1u, 1u, cuuint32_t(X::BX), 1u};
+      VP_TRY(encode_tensor_map(&maps.m[c], fs.f[c], 5, gdim, gstr, box));
+    }
+    static int occ = 0;
+    if (!occ) {
+      VP_CUDA(cudaFuncSetAttribute(k_fft_x_pow_tma<R1, R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM));
+      VP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fft_x_pow_tma<R1, R2, R3, C>, NT, X::SMEM));
+      VP_REQUIRE(occ >= 1, "fft x pass: the TMA kernel for N=%d does not fit an SM", N);
+    }
+    const int grid = ntiles < ctx->sm_count * occ ? ntiles : ctx->sm_count * occ;
+    vp_stage stage(ctx, "k4c_fft_x_pow", st, 1, 8.0 * double(N) * N * NZ * fs.n + 4.0 * double(N) * NZ * (N / 2 + 1));
+    k_fft_x_pow_tma<R1, R2, R3, C><<<grid, NT, X::SMEM, st>>>(maps, fs.n, NZ, pl->tw_full, pl->plane0, kz_offset, P, ntiles);
+    VP_CHECK_LAUNCH();
+  }
+  if (!use_tma) {
+    // row-major input (NCCL exchange), N = 250 (40-byte pieces) and N = 2048 (an item does not fit beside its exchange area):
+    // per-thread loads
     // 8 B/mode read per component, the folded power tile written (4 B per pair of modes)
     vp_stage stage(ctx, "k4c_fft_x_pow", st, 1, 8.0 * double(N) * N * NZ * fs.n + 4.0 * double(N) * NZ * (N / 2 + 1));
     k_fft_x_pow<R1, R2, R3, C><<<ntiles, NT, smem, st>>>(fs, NZ, pl->tw_full, pl->plane0, kz_offset, P);
