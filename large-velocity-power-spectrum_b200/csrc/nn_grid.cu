@@ -94,6 +94,29 @@ __device__ __forceinline__ bool load_pos(const T* __restrict__ pos, const Grid& 
   return !(g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi))));
 }
 
+// N consecutive values (N * sizeof(T) bytes, W-byte aligned) with W-byte loads: a thread that owns FOUR CONSECUTIVE particles
+// fetches their 12 position components with three 16-byte loads instead of twelve 4-byte loads 12 bytes apart (the bucket
+// kernels are bound by the load/store and shared-memory pipe, not by DRAM: ncu MIO-throttle + short-scoreboard 25 %)
+template <int W, typename T, int N>
+__device__ __forceinline__ void load_run(const T* __restrict__ p, T (&out)[N]) {
+  static_assert((N * sizeof(T)) % W == 0 && (W == 8 || W == 16), "load_run: whole vectors only");
+  constexpr int NV = int(N * sizeof(T)) / W;
+  if (W == 16) {
+    uint4 tmp[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tmp[k] = reinterpret_cast<const uint4*>(p)[k];
+    memcpy(out, tmp, sizeof(out));
+  } else {
+    uint2 tmp[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tmp[k] = reinterpret_cast<const uint2*>(p)[k];
+    memcpy(out, tmp, sizeof(out));
+  }
+}
+__device__ __forceinline__ bool keep_x(const Grid& g, double x) {
+  return !(g.use_keep && ((g.closed_xlo && !(x >= g.keep_lo)) || (g.closed_xhi && !(x <= g.keep_hi))));
+}
+
 // Bucket pass.  Particles are taken in TILES of kBinTile consecutive particles; tile t appends to SUB-STREAM t % kSub of each
 // bucket (kSub independent append cursors per bucket keep the per-address atomic rate low; the sub-streams of a bucket are
 // laid out one after the other, so downstream a bucket is still one contiguous run of records).
@@ -101,7 +124,7 @@ __device__ __forceinline__ bool load_pos(const T* __restrict__ pos, const Grid& 
 constexpr int kBinTile = 4096;
 constexpr int kSub = 8;
 constexpr int kClu = 8;      // tiles per thread-block cluster of the scatter kernel: they claim their runs together
-template <typename T>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ hist_g,
                                                    uint32_t tile0) {
   extern __shared__ uint32_t sh_hist[];         // [nb][kSub]
@@ -112,6 +135,26 @@ __global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t sub = uint32_t(((tile0 + tile) / kClu) % kSub);   // all tiles of a cluster append to the same sub-stream
     const int64_t base = tile * kBinTile;
+    if constexpr (VEC) if (base + kBinTile <= np) {
+      // compact, 16-byte aligned positions: four consecutive particles per thread and step
+#pragma unroll 2
+      for (int r = 0; r < kBinTile / 1024; ++r) {
+        T pv[12];
+        load_run<16>(pos + 3 * (base + (r * 256 + threadIdx.x) * 4), pv);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double x = pv[3 * u], y = pv[3 * u + 1], z = pv[3 * u + 2];
+          if (!keep_x(g, x)) continue;
+          uint32_t fx, fy, fz;
+          bool far = false;
+          const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+                    cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+          const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+          atomicAdd(&sh_hist[(lin >> g.bshift) * kSub + sub], 1u);
+        }
+      }
+      continue;
+    }
 #pragma unroll 4
     for (int r = 0; r < kBinTile / 256; ++r) {
       const int64_t i = base + r * 256 + threadIdx.x;
@@ -186,7 +229,7 @@ struct PayloadIn {
 // particles are ranked per bucket with shared-memory atomics, every touched bucket claims ONE contiguous run of slots from
 // its sub-stream cursor, and the records go straight from registers to their slots: all records of a run are written
 // within the same few microseconds, and temporally adjacent tiles append adjacent runs, so L2 assembles whole lines.
-template <typename T, bool PAY, int THREADS>
+template <typename T, bool PAY, int THREADS, bool VEC>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_bin_scatter(const T* __restrict__ pos, PayloadIn<T> pin, int64_t np, int64_t i0, Grid g,
                                                                         uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
   // pos / pin.vel / pin.rho point at particle i0 (a chunk); the stored index is global (i0 + local).
@@ -201,13 +244,22 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_bin_scatter(const T
   const int64_t base = int64_t(blockIdx.x) * kTile;
   uint32_t ra[kItems][3], slot[kItems];          // fixed-point offsets (2 words), linear cell; bucket-local rank, later the slot
   bool farv[kItems];
+  // VEC (compact 16-byte aligned arrays; the host launches it on whole tiles only): thread t owns particles 4t .. 4t+3 of the
+  // tile and fetches them with 16-byte loads; otherwise particle r*THREADS + t, element by element
+  constexpr bool vec = VEC;
+  static_assert(!VEC || kItems == 4, "the vector path takes four consecutive particles per thread");
+  T pv[VEC ? 12 : 1];
+  if constexpr (VEC) { if (vec) load_run<16>(pos + 3 * (base + 4 * int64_t(threadIdx.x)), pv); }
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
-    const int64_t i = base + r * THREADS + threadIdx.x;
+    const int64_t i = vec ? base + 4 * int64_t(threadIdx.x) + r : base + r * THREADS + threadIdx.x;
     slot[r] = 0xffffffffu;
     farv[r] = false;
     double x, y, z;
-    if (i >= np || !load_pos(pos, g, i, x, y, z)) continue;
+    if (VEC && vec) {
+      x = pv[3 * r]; y = pv[3 * r + 1]; z = pv[3 * r + 2];
+      if (!keep_x(g, x)) continue;
+    } else if (i >= np || !load_pos(pos, g, i, x, y, z)) continue;
     uint32_t fx, fy, fz;
     bool far = false;
     const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
@@ -224,17 +276,29 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_bin_scatter(const T
     if (c) sh_cnt[b] = atomicAdd(cursor + b * kSub + sub, c);
   }
   __syncthreads();
+  T vpair[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, rpair[2] = {T(1), T(1)};
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
+    // payload of two consecutive particles at a time on the vector path (8-byte loads for f32, 16-byte loads for f64)
+    T vv[(VEC && PAY) ? 6 : 1], rv[(VEC && PAY) ? 2 : 1];
+    if constexpr (VEC && PAY) if (vec && (r & 1) == 0) {
+      const int64_t i2 = base + 4 * int64_t(threadIdx.x) + r;
+      load_run<sizeof(T) == 4 ? 8 : 16>(pin.vel + 3 * i2, vv);
+      if (pin.rho) load_run<sizeof(T) == 4 ? 8 : 16>(pin.rho + i2, rv);
+      vpair[0] = vv[0]; vpair[1] = vv[1]; vpair[2] = vv[2]; vpair[3] = vv[3]; vpair[4] = vv[4]; vpair[5] = vv[5];
+      rpair[0] = rv[0]; rpair[1] = rv[1];
+    }
     if (slot[r] == 0xffffffffu) continue;
-    const int64_t i = base + r * THREADS + threadIdx.x;
+    const int64_t i = vec ? base + 4 * int64_t(threadIdx.x) + r : base + r * THREADS + threadIdx.x;
     const uint32_t dst = sh_cnt[ra[r][2] >> g.bshift] + slot[r];
     const uint32_t idx = uint32_t(i0 + i) | (farv[r] ? kFarBit : 0u);
     if (PAY) {
-      T vx = pin.vel[size_t(g.vs) * i], vy = pin.vel[size_t(g.vs) * i + 1], vz = pin.vel[size_t(g.vs) * i + 2];
+      T vx, vy, vz;
+      if (VEC && vec) { vx = vpair[3 * (r & 1)]; vy = vpair[3 * (r & 1) + 1]; vz = vpair[3 * (r & 1) + 2]; }
+      else { vx = pin.vel[size_t(g.vs) * i]; vy = pin.vel[size_t(g.vs) * i + 1]; vz = pin.vel[size_t(g.vs) * i + 2]; }
       T m = pin.lcell3;
       if (pin.rho) {
-        const T rr = pin.rho[size_t(g.rs) * i];
+        const T rr = (VEC && vec) ? rpair[r & 1] : pin.rho[size_t(g.rs) * i];
         vx = (vx * rr) / rr;
         vy = (vy * rr) / rr;
         vz = (vz * rr) / rr;
@@ -1363,10 +1427,13 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     // thread-block clusters claiming one run per bucket together: measured 55 ms against 26 ms without (four cluster-wide
     // barriers per tile with one 1024-thread CTA per SM), kept behind a switch
     const bool use_clusters = getenv("VP_SCATTER_CLUSTERS") != nullptr;
+    static const bool vec_on = !(getenv("VP_BIN_VEC") && atoi(getenv("VP_BIN_VEC")) == 0);
     static bool attr_done = false;
     if (!attr_done) {
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
       attr_done = true;
     }
     auto launch_hist = [&](const T* p, int64_t n_c, int64_t i0) {
@@ -1374,7 +1441,9 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       // 68 % long-scoreboard stalls at 4 CTAs/SM)
       const int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (size_t(220) << 10) / (hsmem + 1024))));
       const int64_t nt = (n_c + kBinTile - 1) / kBinTile, cap = int64_t(ctx->sm_count) * per_sm;
-      k_bin_hist<T><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
+      const bool vec = vec_on && g.ps == 3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+      if (vec) k_bin_hist<T, true><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
+      else k_bin_hist<T, false><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
     };
     auto launch_scatter = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
@@ -1390,8 +1459,28 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       } else {
         // (512-thread CTAs on 2048-particle tiles, four per SM instead of two: 25.1 vs 24.7 ms at cfg4 -- the phases of a tile
         // are not what limits this kernel)
-        if (has_pay) k_bin_scatter<T, true, 1024><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
-        else k_bin_scatter<T, false, 1024><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+        const bool vec = vec_on && g.ps == 3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 &&
+                         (!has_pay || (g.vs == 3 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (!r || (g.rs == 1 && (reinterpret_cast<uintptr_t>(r) & 15) == 0))));
+        if (vec) {
+          // whole tiles with vector loads, the last partial tile element by element
+          const unsigned nfull = unsigned(n_c / kBinTile);
+          if (nfull) {
+            if (has_pay) k_bin_scatter<T, true, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+            else k_bin_scatter<T, false, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+          }
+          if (nfull < nbk) {
+            const int64_t done = int64_t(nfull) * kBinTile;
+            PayloadIn<T> pt = pin;
+            if (pt.vel) pt.vel += 3 * done;
+            if (pt.rho) pt.rho += done;
+            const uint32_t t1 = uint32_t(((i0 + done) / kBinTile) % (kSub * kClu));
+            if (has_pay) k_bin_scatter<T, true, 1024, false><<<1, 1024, ssmem, st>>>(p + 3 * done, pt, n_c - done, i0 + done, g, cursor, t1, rec1);
+            else k_bin_scatter<T, false, 1024, false><<<1, 1024, ssmem, st>>>(p + 3 * done, pt, n_c - done, i0 + done, g, cursor, t1, rec1);
+          }
+        } else {
+          if (has_pay) k_bin_scatter<T, true, 1024, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+          else k_bin_scatter<T, false, 1024, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
+        }
       }
     };
     if (host_pos) {
