@@ -312,6 +312,126 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_bin_scatter(const T
   }
 }
 
+// Part 2, write-combining form (whole tiles of compact, 16-byte aligned arrays -- the usual case; everything else takes
+// k_bin_scatter above).  What the plain kernel pays for is not DRAM but the store instruction itself: a warp whose 32 lanes write
+// 32 unrelated sectors is served one sector at a time by the load/store unit (tools/ubench/bin_scatter.cu: 17 of its 25 ms at
+// 2^30 particles are the stores; with the stores removed the kernel takes 8 ms).  Here the tile's records are first put in BUCKET
+// ORDER in shared memory -- position = exclusive prefix of the tile's bucket counts + rank inside the bucket, half a tile (kWin
+// records, 64 KB) at a time so that two CTAs fit an SM -- and then written out by consecutive lanes: a warp covers ~8 runs of
+// consecutive destinations instead of 32 sectors.  Same records, same runs, same cursors as the plain kernel.
+constexpr int kWin = 2048;
+constexpr uint32_t kWcBuckets = 2048;      // = kMaxBuckets: fixed shared-memory layout (compile-time offsets, two registers less)
+template <typename T, bool PAY>
+__global__ void __launch_bounds__(1024, 2) k_bin_scatter_wc(const T* __restrict__ pos, PayloadIn<T> pin, int64_t i0, Grid g,
+                                                           uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
+  static_assert(kBinTile == 4096, "four consecutive particles per thread, 1024 threads");
+  extern __shared__ __align__(16) unsigned char wsm[];
+  uint4* sA = reinterpret_cast<uint4*>(wsm);                               // [kWin] search half of the staged records
+  uint4* sB = sA + kWin;                                                   // [kWin] payload half (PAY only)
+  uint32_t* sh_cnt = reinterpret_cast<uint32_t*>(sA + (PAY ? 2 : 1) * kWin);   // [nb] counts, then the tile-local exclusive prefix
+  uint32_t* sh_delta = sh_cnt + kWcBuckets;                                // [nb] first slot of the claimed run - tile-local prefix
+  uint32_t* sh_w = sh_delta + kWcBuckets;                                      // [33] warp totals of the scan
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  for (uint32_t b = tid; b < g.nb; b += 1024) sh_cnt[b] = 0u;
+  __syncthreads();
+  const uint32_t sub = ((tile0 + blockIdx.x) / kClu) % kSub;
+  const int64_t base = int64_t(blockIdx.x) * kBinTile + 4 * int64_t(tid);  // this thread's four particles: base .. base + 3
+  const uint32_t idx0 = uint32_t(i0 + base);
+  const T* __restrict__ velp = PAY ? pin.vel + 3 * base : nullptr;      // this thread's four particles
+  const T* __restrict__ rhop = (PAY && pin.rho) ? pin.rho + base : nullptr;
+  uint32_t ra[4][3], slot[4];       // slot: rank inside the tile's bucket (< 4096) | far flag in bit 30; all ones = not taking part
+  constexpr int kHalves = sizeof(T) == 4 ? 1 : 2, kPer = 4 / kHalves;      // f64: two particles (48 bytes) per batch of loads
+#pragma unroll
+  for (int h = 0; h < kHalves; ++h) {
+    T pv[3 * kPer];
+    load_run<16>(pos + 3 * (base + h * kPer), pv);
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int r = h * kPer + u;
+      slot[r] = 0xffffffffu;
+      const double x = pv[3 * u], y = pv[3 * u + 1], z = pv[3 * u + 2];
+      if (!keep_x(g, x)) continue;
+      uint32_t fx, fy, fz;
+      bool far = false;
+      const int cx = cell_fix(x, g.ox, g.ihx, g.gx, fx, far), cy = cell_fix(y, g.oy, g.ihy, g.gy, fy, far),
+                cz = cell_fix(z, g.oz, g.ihz, g.gz, fz, far);
+      const uint32_t lin = (uint32_t(cx) * uint32_t(g.gy) + uint32_t(cy)) * uint32_t(g.gz) + uint32_t(cz);
+      const uint32_t rk = atomicAdd(&sh_cnt[lin >> g.bshift], 1u);
+      const unsigned long long w = (unsigned long long)fx | ((unsigned long long)fy << kFixBits) | ((unsigned long long)fz << (2 * kFixBits));
+      ra[r][0] = uint32_t(w); ra[r][1] = uint32_t(w >> 32); ra[r][2] = lin;
+      slot[r] = rk | (far ? 0x40000000u : 0u);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the bucket counts in bucket order (thread t owns buckets 2t, 2t+1: nb <= 2048), one run claimed per bucket
+  const uint32_t b0 = 2u * tid, b1 = b0 + 1u;
+  const uint32_t c0 = b0 < g.nb ? sh_cnt[b0] : 0u, c1 = b1 < g.nb ? sh_cnt[b1] : 0u;
+  uint32_t incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh_w[wp] = incl;
+  __syncthreads();
+  if (wp == 0) {
+    const uint32_t v = sh_w[lane];
+    uint32_t is = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, is, o);
+      if (lane >= o) is += t;
+    }
+    sh_w[lane] = is - v;
+    if (lane == 31) sh_w[32] = is;
+  }
+  __syncthreads();
+  const uint32_t tp0 = sh_w[wp] + incl - (c0 + c1), tp1 = tp0 + c0;
+  const uint32_t gb0 = c0 ? atomicAdd(cursor + b0 * kSub + sub, c0) : 0u;     // (both claims in flight before either is used)
+  const uint32_t gb1 = c1 ? atomicAdd(cursor + b1 * kSub + sub, c1) : 0u;
+  if (b0 < g.nb) { sh_cnt[b0] = tp0; sh_delta[b0] = gb0 - tp0; }
+  if (b1 < g.nb) { sh_cnt[b1] = tp1; sh_delta[b1] = gb1 - tp1; }
+  const uint32_t nv = sh_w[32];      // particles of the tile that take part
+  __syncthreads();
+  for (uint32_t w0 = 0; w0 < nv; w0 += kWin) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (slot[r] == 0xffffffffu) continue;
+      const uint32_t p = sh_cnt[ra[r][2] >> g.bshift] + (slot[r] & 0xffffu) - w0;
+      if (p >= uint32_t(kWin)) continue;
+      sA[p] = make_uint4(ra[r][0], ra[r][1], ra[r][2], (idx0 + r) | ((slot[r] & 0x40000000u) ? kFarBit : 0u));
+      if (PAY) {
+        T vx = velp[3 * r], vy = velp[3 * r + 1], vz = velp[3 * r + 2];
+        T m = pin.lcell3;
+        if (rhop) {
+          const T rr = rhop[r];
+          vx = (vx * rr) / rr;
+          vy = (vy * rr) / rr;
+          vz = (vz * rr) / rr;
+          m = rr * pin.lcell3;
+        }
+        sB[p] = make_uint4(__float_as_uint(float(vx)), __float_as_uint(float(vy)), __float_as_uint(float(vz)), __float_as_uint(float(m)));
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kWin / 1024; ++k) {
+      const uint32_t q = uint32_t(tid) + k * 1024;
+      if (w0 + q < nv) {
+        const uint4 a = sA[q];
+        const uint32_t dst = sh_delta[a.z >> g.bshift] + w0 + q;
+        if (PAY) {
+          const uint4 b = sB[q];
+          st256(static_cast<Rec32*>(rec1) + dst, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+        } else {
+          static_cast<uint4*>(rec1)[dst] = a;
+        }
+      }
+    }
+    if (w0 + kWin < nv) __syncthreads();
+  }
+}
+
 // The same with thread-block clusters (sm_90+/sm_100): the kClu CTAs of a cluster rank their tiles independently, add up
 // their per-bucket counts through distributed shared memory, claim ONE run per bucket for the whole cluster (kClu times
 // longer: ~1 KB instead of ~128 B at 1024 buckets) and write into it side by side -- DRAM sees the long runs it needs
@@ -1165,6 +1285,7 @@ AxisPlan plan_axis(const double* q, int n, int g, double lo_ext, double hi_ext, 
   return a;
 }
 
+static_assert(kWcBuckets == 2048, "k_bin_scatter_wc lays its tables out for kMaxBuckets buckets");
 constexpr uint32_t kMaxBuckets = 2048;    // 8 KB of shared-memory counters / cursors per CTA of the bucket pass
 
 Grid plan_grid(int64_t np, const double* qx, int nx, const double* qy, int ny, const double* qz, int nz,
@@ -1428,12 +1549,18 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     // barriers per tile with one 1024-thread CTA per SM), kept behind a switch
     const bool use_clusters = getenv("VP_SCATTER_CLUSTERS") != nullptr;
     static const bool vec_on = !(getenv("VP_BIN_VEC") && atoi(getenv("VP_BIN_VEC")) == 0);
+    static const bool wc_on = !(getenv("VP_BIN_WC") && atoi(getenv("VP_BIN_WC")) == 0);
     static bool attr_done = false;
     if (!attr_done) {
       VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
       VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
       VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
       VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      const int wmax = int(2 * kWin * 16 + 2 * kMaxBuckets * 4 + 33 * 4);
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
       attr_done = true;
     }
     auto launch_hist = [&](const T* p, int64_t n_c, int64_t i0) {
@@ -1464,7 +1591,11 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         if (vec) {
           // whole tiles with vector loads, the last partial tile element by element
           const unsigned nfull = unsigned(n_c / kBinTile);
-          if (nfull) {
+          if (nfull && wc_on) {
+            const size_t wsmem = size_t(has_pay ? 2 : 1) * kWin * 16 + 2 * size_t(kWcBuckets) * 4 + 33 * 4;
+            if (has_pay) k_bin_scatter_wc<T, true><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
+            else k_bin_scatter_wc<T, false><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
+          } else if (nfull) {
             if (has_pay) k_bin_scatter<T, true, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
             else k_bin_scatter<T, false, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
           }
