@@ -124,7 +124,7 @@ __device__ __forceinline__ bool keep_x(const Grid& g, double x) {
 constexpr int kBinTile = 4096;
 constexpr int kSub = 8;
 constexpr int kClu = 8;      // tiles per thread-block cluster of the scatter kernel: they claim their runs together
-template <typename T, bool VEC>
+template <typename T, int VEC>   // 0: element by element; 1: compact [np,3], 16-byte loads; 2: 32-byte rows (x y z vx | vy vz rho -), f32
 __global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int64_t np, Grid g, uint32_t* __restrict__ hist_g,
                                                    uint32_t tile0) {
   extern __shared__ uint32_t sh_hist[];         // [nb][kSub]
@@ -135,12 +135,21 @@ __global__ void __launch_bounds__(256) k_bin_hist(const T* __restrict__ pos, int
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t sub = uint32_t(((tile0 + tile) / kClu) % kSub);   // all tiles of a cluster append to the same sub-stream
     const int64_t base = tile * kBinTile;
-    if constexpr (VEC) if (base + kBinTile <= np) {
+    if constexpr (VEC != 0) if (base + kBinTile <= np) {
       // compact, 16-byte aligned positions: four consecutive particles per thread and step
 #pragma unroll 2
       for (int r = 0; r < kBinTile / 1024; ++r) {
         T pv[12];
-        load_run<16>(pos + 3 * (base + (r * 256 + threadIdx.x) * 4), pv);
+        if constexpr (VEC == 2) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            // (consecutive lanes take consecutive rows: a warp load covers 1 KB, not 32 separate lines)
+            const uint4 q = *reinterpret_cast<const uint4*>(pos + 8 * (base + (r * 4 + u) * 256 + threadIdx.x));
+            pv[3 * u] = T(__uint_as_float(q.x)); pv[3 * u + 1] = T(__uint_as_float(q.y)); pv[3 * u + 2] = T(__uint_as_float(q.z));
+          }
+        } else {
+          load_run<16>(pos + 3 * (base + (r * 256 + threadIdx.x) * 4), pv);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const double x = pv[3 * u], y = pv[3 * u + 1], z = pv[3 * u + 2];
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_bin_scatter(const T
 // consecutive destinations instead of 32 sectors.  Same records, same runs, same cursors as the plain kernel.
 constexpr int kWin = 2048;
 constexpr uint32_t kWcBuckets = 2048;      // = kMaxBuckets: fixed shared-memory layout (compile-time offsets, two registers less)
-template <typename T, bool PAY>
+template <typename T, bool PAY, bool ROWS>   // ROWS: pos/vel/rho are columns 0-2 / 3-5 / 6 of one [np,8] f32 row array (the slab exchange's rows)
 __global__ void __launch_bounds__(1024, 2) k_bin_scatter_wc(const T* __restrict__ pos, PayloadIn<T> pin, int64_t i0, Grid g,
                                                            uint32_t* __restrict__ cursor, uint32_t tile0, void* __restrict__ rec1) {
   static_assert(kBinTile == 4096, "four consecutive particles per thread, 1024 threads");
@@ -335,16 +344,27 @@ __global__ void __launch_bounds__(1024, 2) k_bin_scatter_wc(const T* __restrict_
   for (uint32_t b = tid; b < g.nb; b += 1024) sh_cnt[b] = 0u;
   __syncthreads();
   const uint32_t sub = ((tile0 + blockIdx.x) / kClu) % kSub;
-  const int64_t base = int64_t(blockIdx.x) * kBinTile + 4 * int64_t(tid);  // this thread's four particles: base .. base + 3
+  // this thread's four particles: base + r*kStep -- four consecutive ones of compact arrays (one batch of 16-byte loads), or
+  // particles 1024 apart of a row array (consecutive lanes then read consecutive 32-byte rows)
+  constexpr int kStep = ROWS ? 1024 : 1;
+  const int64_t base = int64_t(blockIdx.x) * kBinTile + (ROWS ? 1 : 4) * int64_t(tid);
   const uint32_t idx0 = uint32_t(i0 + base);
-  const T* __restrict__ velp = PAY ? pin.vel + 3 * base : nullptr;      // this thread's four particles
-  const T* __restrict__ rhop = (PAY && pin.rho) ? pin.rho + base : nullptr;
+  const T* __restrict__ velp = (PAY && !ROWS) ? pin.vel + 3 * base : nullptr;      // this thread's four particles
+  const T* __restrict__ rhop = (PAY && pin.rho) ? (ROWS ? pin.rho : pin.rho + base) : nullptr;   // (ROWS: only its presence matters)
   uint32_t ra[4][3], slot[4];       // slot: rank inside the tile's bucket (< 4096) | far flag in bit 30; all ones = not taking part
   constexpr int kHalves = sizeof(T) == 4 ? 1 : 2, kPer = 4 / kHalves;      // f64: two particles (48 bytes) per batch of loads
 #pragma unroll
   for (int h = 0; h < kHalves; ++h) {
     T pv[3 * kPer];
-    load_run<16>(pos + 3 * (base + h * kPer), pv);
+    if constexpr (ROWS) {
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const uint4 q = *reinterpret_cast<const uint4*>(pos + 8 * (base + (h * kPer + u) * kStep));
+        pv[3 * u] = T(__uint_as_float(q.x)); pv[3 * u + 1] = T(__uint_as_float(q.y)); pv[3 * u + 2] = T(__uint_as_float(q.z));
+      }
+    } else {
+      load_run<16>(pos + 3 * (base + h * kPer), pv);
+    }
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
       const int r = h * kPer + u;
@@ -399,12 +419,19 @@ __global__ void __launch_bounds__(1024, 2) k_bin_scatter_wc(const T* __restrict_
       if (slot[r] == 0xffffffffu) continue;
       const uint32_t p = sh_cnt[ra[r][2] >> g.bshift] + (slot[r] & 0xffffu) - w0;
       if (p >= uint32_t(kWin)) continue;
-      sA[p] = make_uint4(ra[r][0], ra[r][1], ra[r][2], (idx0 + r) | ((slot[r] & 0x40000000u) ? kFarBit : 0u));
+      sA[p] = make_uint4(ra[r][0], ra[r][1], ra[r][2], (idx0 + r * kStep) | ((slot[r] & 0x40000000u) ? kFarBit : 0u));
       if (PAY) {
-        T vx = velp[3 * r], vy = velp[3 * r + 1], vz = velp[3 * r + 2];
+        T vx, vy, vz, rrow = T(1);
+        if constexpr (ROWS) {
+          const T* row = pos + 8 * (base + r * kStep);
+          const uint4 hi = *reinterpret_cast<const uint4*>(row + 4);
+          vx = row[3]; vy = T(__uint_as_float(hi.x)); vz = T(__uint_as_float(hi.y)); rrow = T(__uint_as_float(hi.z));
+        } else {
+          vx = velp[3 * r]; vy = velp[3 * r + 1]; vz = velp[3 * r + 2];
+        }
         T m = pin.lcell3;
         if (rhop) {
-          const T rr = rhop[r];
+          const T rr = ROWS ? rrow : rhop[r];
           vx = (vx * rr) / rr;
           vy = (vy * rr) / rr;
           vz = (vz * rr) / rr;
@@ -1552,15 +1579,19 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
     static const bool wc_on = !(getenv("VP_BIN_WC") && atoi(getenv("VP_BIN_WC")) == 0);
     static bool attr_done = false;
     if (!attr_done) {
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_hist<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxBuckets * kSub * 4)));
       const int wmax = int(2 * kWin * 16 + 2 * kMaxBuckets * 4 + 33 * 4);
-      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
-      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
+      VP_CUDA(cudaFuncSetAttribute(k_bin_scatter_wc<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wmax));
       attr_done = true;
     }
     auto launch_hist = [&](const T* p, int64_t n_c, int64_t i0) {
@@ -1569,8 +1600,10 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
       const int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (size_t(220) << 10) / (hsmem + 1024))));
       const int64_t nt = (n_c + kBinTile - 1) / kBinTile, cap = int64_t(ctx->sm_count) * per_sm;
       const bool vec = vec_on && g.ps == 3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-      if (vec) k_bin_hist<T, true><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
-      else k_bin_hist<T, false><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
+      const bool rows = vec_on && sizeof(T) == 4 && g.ps == 8 && (reinterpret_cast<uintptr_t>(p) & 31) == 0;
+      if (rows) k_bin_hist<T, 2><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
+      else if (vec) k_bin_hist<T, 1><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
+      else k_bin_hist<T, 0><<<unsigned(nt < cap ? nt : cap), 256, hsmem, st>>>(p, n_c, g, hist, uint32_t((i0 / kBinTile) % (kSub * kClu)));
     };
     auto launch_scatter = [&](const T* p, const T* v, const T* r, int64_t n_c, int64_t i0) {
       PayloadIn<T> pin;
@@ -1588,13 +1621,22 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
         // are not what limits this kernel)
         const bool vec = vec_on && g.ps == 3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 &&
                          (!has_pay || (g.vs == 3 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (!r || (g.rs == 1 && (reinterpret_cast<uintptr_t>(r) & 15) == 0))));
-        if (vec) {
+        // interleaved 32-byte rows (the slab exchange's output): x y z vx | vy vz rho -, read in place by the write-combining kernel
+        const bool rows = vec_on && wc_on && sizeof(T) == 4 && g.ps == 8 && (reinterpret_cast<uintptr_t>(p) & 31) == 0 &&
+                          (!has_pay || (g.vs == 8 && v == p + 3 && (!r || (g.rs == 8 && r == p + 6))));
+        if (vec || rows) {
           // whole tiles with vector loads, the last partial tile element by element
           const unsigned nfull = unsigned(n_c / kBinTile);
-          if (nfull && wc_on) {
+          if (nfull && rows) {
             const size_t wsmem = size_t(has_pay ? 2 : 1) * kWin * 16 + 2 * size_t(kWcBuckets) * 4 + 33 * 4;
-            if (has_pay) k_bin_scatter_wc<T, true><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
-            else k_bin_scatter_wc<T, false><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
+            if constexpr (sizeof(T) == 4) {
+              if (has_pay) k_bin_scatter_wc<T, true, true><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
+              else k_bin_scatter_wc<T, false, true><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
+            }
+          } else if (nfull && wc_on) {
+            const size_t wsmem = size_t(has_pay ? 2 : 1) * kWin * 16 + 2 * size_t(kWcBuckets) * 4 + 33 * 4;
+            if (has_pay) k_bin_scatter_wc<T, true, false><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
+            else k_bin_scatter_wc<T, false, false><<<nfull, 1024, wsmem, st>>>(p, pin, i0, g, cursor, t0, rec1);
           } else if (nfull) {
             if (has_pay) k_bin_scatter<T, true, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
             else k_bin_scatter<T, false, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
@@ -1602,11 +1644,11 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
           if (nfull < nbk) {
             const int64_t done = int64_t(nfull) * kBinTile;
             PayloadIn<T> pt = pin;
-            if (pt.vel) pt.vel += 3 * done;
-            if (pt.rho) pt.rho += done;
+            if (pt.vel) pt.vel += size_t(g.vs) * done;
+            if (pt.rho) pt.rho += size_t(g.rs) * done;
             const uint32_t t1 = uint32_t(((i0 + done) / kBinTile) % (kSub * kClu));
-            if (has_pay) k_bin_scatter<T, true, 1024, false><<<1, 1024, ssmem, st>>>(p + 3 * done, pt, n_c - done, i0 + done, g, cursor, t1, rec1);
-            else k_bin_scatter<T, false, 1024, false><<<1, 1024, ssmem, st>>>(p + 3 * done, pt, n_c - done, i0 + done, g, cursor, t1, rec1);
+            if (has_pay) k_bin_scatter<T, true, 1024, false><<<1, 1024, ssmem, st>>>(p + size_t(g.ps) * done, pt, n_c - done, i0 + done, g, cursor, t1, rec1);
+            else k_bin_scatter<T, false, 1024, false><<<1, 1024, ssmem, st>>>(p + size_t(g.ps) * done, pt, n_c - done, i0 + done, g, cursor, t1, rec1);
           }
         } else {
           if (has_pay) k_bin_scatter<T, true, 1024, false><<<nbk, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);

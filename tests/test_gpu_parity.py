@@ -880,3 +880,26 @@ def test_fold_from_numpy_folded_box(vp, golden_fold):
     assert np.array_equal(got[:, 3], ref[:, 3])
     ok = ref[:, 3] > 0
     assert (np.abs(got[ok, 2] - ref[ok, 2]) / ref[ok, 2]).max() < 1e-9
+
+
+@pytest.mark.parametrize("Np,N,with_rho", [(1 << 18, 64, True), ((1 << 17) + 4099, 48, True), (3 * 4096, 32, False)])
+def test_interleaved_rows_equal_compact(lib, orc, Np, N, with_rho):
+    """vp_nn_opts.row_stride = 8: positions, velocities and densities read in place from the 32-byte rows the slab exchange
+    delivers (x y z vx | vy vz rho -) -- the row forms of the bucket kernels -- give the planes and indices of the compact
+    arrays, bit for bit (whole tiles and a ragged last tile)."""
+    import torch
+    pos, vel, dens, _ = orc.synth_particles(9, Np, 1.0)
+    ax = orc.lattice_axis_lib(1.0, N)
+    lc3 = (1.0 / N) ** 3
+    dp, dv, dr = lib.to_device(pos), lib.to_device(vel), lib.to_device(dens)
+    rows = torch.zeros((Np, 8), dtype=torch.float32, device="cuda")
+    rows[:, 0:3], rows[:, 3:6], rows[:, 6] = dp, dv, dr
+    o = lib.NNOpts()
+    o.row_stride = 8
+    kw = dict(want_v=True, want_p=(True, False, False), want_e=True, want_m=True, want_idx=True)
+    f1, nn1 = lib.nn_grid_fields(dp, dv, dr if with_rho else None, ax, ax, ax, lc3, **kw)
+    f2, nn2 = lib.nn_grid_fields(rows[:, 0:3], rows[:, 3:6], rows[:, 6] if with_rho else None, ax, ax, ax, lc3, opts=o, **kw)
+    assert np.array_equal(nn1.cpu().numpy(), nn2.cpu().numpy())
+    assert np.array_equal(nn1.cpu().numpy(), orc.nn_exact_lattice(pos.astype(np.float64), ax, ax, ax))
+    for k in f1:
+        assert np.array_equal(f1[k].cpu().numpy(), f2[k].cpu().numpy()), k
