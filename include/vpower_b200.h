@@ -251,6 +251,15 @@ int vp_snapshot_preamble(vp_ctx* ctx, void* pos_d, void* vel_d, const void* mass
                          int do_bulk, double* min_h, double* bulk_h, void* stream);
 
 /* Test/diagnostic entry points */
+/* The blocked half-spectrum layout the y pass writes and the x pass reads, and the tensor map / shared-memory ring of the
+ * TMA-fed x pass for a lattice of N with kz_columns half-spectrum columns on this rank (N/2 on one GPU, N/2/nranks in a slab
+ * decomposition) -- host arithmetic only, no device, no ctx.  info_out[24] = { C (columns per tile), ky per block, kz tiles,
+ * x planes per box, boxes per item, 1 if the TMA kernel serves this N (else per-thread loads), tensor dims[5] (f32 elements,
+ * innermost first), strides[4] (bytes, dims 1..4), box[5], bytes of a box slot, items in the ring, dynamic shared memory of
+ * the kernel, threads per CTA }.  Element (x, ky, kz = zt*C + c) of the blocked cube is complex number
+ * ((((ky / kyb) * N + x) * tiles + zt) * kyb + ky % kyb) * C + c.  (No counterpart in the reference: pyFFTW owns its layout,
+ * scripts/parallel_optimized.py:124-141.) */
+int vp_fft_x_layout(int N, int kz_columns, int64_t* info_out);
 /* In-place 3-D r2c transform only.  Output layout: [N][N][N/2] complex64 where entry (x,y,0) packs
  * (Re F(x,y,0), Re F_zNyquist-line ...) -- see DESIGN.md "half-spectrum layout"; use
  * vp_fft_unpack_half to obtain the conventional [N][N][N/2+1] array. */

@@ -243,6 +243,24 @@ struct XTma {
   static constexpr bool ok = (C * 8) % 16 == 0 && (ITEMB + XSB + 64 <= 227 * 1024) && NT <= 1024;
 };
 
+// Tensor map of the blocked half spectrum [N (x)][N (ky)][NZ (kz)] of one rank (see YDest), as the x pass requests it: f32
+// elements, innermost dimension first.  Host arithmetic only; vp_fft_x_layout() reports it, launch_x_pow() encodes it.
+struct XGeom {
+  unsigned long long gdim[5];       // [2C][kYB][NZ/C][N][N/kYB]
+  unsigned long long gstride[4];    // bytes, dimensions 1..4
+  unsigned box[5];                  // 2C x 1 x 1 x BX x 1
+};
+template <int L, int C>
+XGeom x_geometry(int NZ) {
+  constexpr int kYB = yb_of<L>();
+  const unsigned long long tiles_z = (unsigned long long)(NZ / C), row = (unsigned long long)(C) * 8;
+  XGeom g;
+  g.gdim[0] = 2 * C; g.gdim[1] = kYB; g.gdim[2] = tiles_z; g.gdim[3] = L; g.gdim[4] = L / kYB;
+  g.gstride[0] = row; g.gstride[1] = row * kYB; g.gstride[2] = row * kYB * tiles_z; g.gstride[3] = row * kYB * tiles_z * L;
+  g.box[0] = 2 * C; g.box[1] = 1; g.box[2] = 1; g.box[3] = xbox_of<L>(); g.box[4] = 1;
+  return g;
+}
+
 template <int R1, int R2, int R3, int C>
 __global__ void __launch_bounds__(R2* R3* C) k_fft_x_pow_tma(const __grid_constant__ XMaps maps, int ncomp, int NZ,
                                                               const float2* __restrict__ tw, float2* __restrict__ plane0, int kz_offset,
@@ -603,16 +621,14 @@ int launch_x_pow(FieldSet fs, int N, int NZ, int kz_offset, vp_pk_plan* pl, doub
   if constexpr (X::ok) if (use_tma) {
     // blocked half spectrum as a 5-D tensor of f32 (innermost first): [2C][kYB][tiles_z][N (x)][N/kYB]; one box = BX x planes of
     // one (ky, kz tile): 2C x 1 x 1 x BX x 1
-    constexpr int kYB = yb_of<F::L>();
+    const XGeom xg = x_geometry<F::L, C>(NZ);
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5];
+    for (int i = 0; i < 5; ++i) { gdim[i] = xg.gdim[i]; box[i] = xg.box[i]; }
+    for (int i = 0; i < 4; ++i) gstr[i] = xg.gstride[i];
     XMaps maps;
     memset(&maps, 0, sizeof(maps));
-    for (int c = 0; c < fs.n; ++c) {
-      const cuuint64_t gdim[5] = {cuuint64_t(2 * C), cuuint64_t(kYB), cuuint64_t(tiles_z), cuuint64_t(N), cuuint64_t(N / kYB)};
-      const cuuint64_t row = cuuint64_t(C) * 8;
-      const cuuint64_t gstr[4] = {row, row * kYB, row * kYB * tiles_z, row * kYB * tiles_z * N};
-      const cuuint32_t box[5] = {cuuint32_t(2 * C), 1u, 1u, cuuint32_t(X::BX), 1u};
-      VP_TRY(encode_tensor_map(&maps.m[c], fs.f[c], 5, gdim, gstr, box));
-    }
+    for (int c = 0; c < fs.n; ++c) VP_TRY(encode_tensor_map(&maps.m[c], fs.f[c], 5, gdim, gstr, box));
     static int occ = 0;
     if (!occ) {
       VP_CUDA(cudaFuncSetAttribute(k_fft_x_pow_tma<R1, R2, R3, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM));
@@ -788,6 +804,39 @@ double sq_threshold(double e, bool strict) {
 }
 
 }  // namespace
+
+namespace {
+template <int R1, int R2, int R3, int C>
+int x_layout_report(int NZ, int64_t* o) {
+  using X = XTma<R1, R2, R3, C>;
+  constexpr int L = R1 * R2 * R3;
+  if (NZ <= 0 || NZ % C != 0) { vp_set_error("vp_fft_x_layout: %d columns is not a multiple of the tile width %d", NZ, C); return VP_ERR_ARG; }
+  const XGeom g = x_geometry<L, C>(NZ);
+  o[0] = C; o[1] = yb_of<L>(); o[2] = NZ / C; o[3] = X::BX; o[4] = X::NBOX; o[5] = X::ok ? 1 : 0;
+  for (int i = 0; i < 5; ++i) o[6 + i] = int64_t(g.gdim[i]);
+  for (int i = 0; i < 4; ++i) o[11 + i] = int64_t(g.gstride[i]);
+  for (int i = 0; i < 5; ++i) o[15 + i] = int64_t(g.box[i]);
+  o[20] = X::BOXP; o[21] = X::NST; o[22] = X::SMEM; o[23] = X::NT;
+  return VP_OK;
+}
+}  // namespace
+
+extern "C" int vp_fft_x_layout(int N, int kz_columns, int64_t* info_out) {
+  VP_REQUIRE(info_out, "vp_fft_x_layout: null argument");
+  switch (N) {
+    case 64: return x_layout_report<16, 4, 1, 32>(kz_columns, info_out);
+    case 128: return x_layout_report<16, 8, 1, 32>(kz_columns, info_out);
+    case 256: return x_layout_report<16, 16, 1, 16>(kz_columns, info_out);
+    case 512: return x_layout_report<16, 16, 2, 8>(kz_columns, info_out);
+    case 1024: return x_layout_report<16, 16, 4, 8>(kz_columns, info_out);
+    case 2048: return x_layout_report<16, 16, 8, 8>(kz_columns, info_out);
+    case 250: return x_layout_report<10, 5, 5, 5>(kz_columns, info_out);
+    case 500: return x_layout_report<10, 10, 5, 10>(kz_columns, info_out);
+    case 1000: return x_layout_report<10, 10, 10, 10>(kz_columns, info_out);
+  }
+  vp_set_error("vp_fft_x_layout: N=%d has no line-FFT path", N);
+  return VP_ERR_UNSUPPORTED;
+}
 
 extern "C" int vp_pk_plan_create(vp_ctx* ctx, int N, const double* k_h, const double* edges_h, int nbins, vp_pk_plan** out) {
   VP_REQUIRE(ctx && k_h && edges_h && out, "vp_pk_plan_create: null argument");

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vp_nn_grid_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L), _P]),
     "vp_nn_grid_stats_ex": (_I, [_P, C.POINTER(_L), _P]),
     "vp_nn_grid_plan": (_I, [_L, _dp, _I, _dp, _I, _dp, _I, C.POINTER(NNOpts), C.POINTER(_L)]),
+    "vp_fft_x_layout": (_I, [_I, _I, C.POINTER(_L)]),
     "vp_nn_grid_payload": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, _P, _P, _P, C.POINTER(NNOpts), _P]),
     "vp_nn_grid_fields": (_I, [_P, _P, _P, _P, _I, _L, _dp, _I, _dp, _I, _dp, _I, _D, C.POINTER(_P), C.POINTER(_P), _P, _P, _P,
                                C.POINTER(NNOpts), _P]),
@@ -383,6 +384,15 @@ def nn_grid_plan(np_particles, qx, qy, qz, opts: NNOpts | None = None):
                                           C.byref(opts) if opts is not None else None, out))
     names = ("cells_x", "cells_y", "cells_z", "bucket_shift", "n_buckets", "r5", "r6", "r7", "scratch_MiB", "corner_aligned")
     return dict(zip(names, (int(v) for v in out)))
+
+
+def fft_x_layout(N, kz_columns=None):
+    """Host-only view of the blocked half-spectrum layout and the x pass's tensor map (vp_fft_x_layout)."""
+    out = (_L * 24)()
+    _check(load_library().vp_fft_x_layout(int(N), int(N // 2 if kz_columns is None else kz_columns), out))
+    v = [int(x) for x in out]
+    return {"C": v[0], "kyb": v[1], "tiles": v[2], "box_x": v[3], "boxes": v[4], "tma": bool(v[5]), "dims": v[6:11],
+            "strides": v[11:15], "box": v[15:20], "box_slot_bytes": v[20], "ring_items": v[21], "smem_bytes": v[22], "threads": v[23]}
 
 
 def nn_grid_stats():

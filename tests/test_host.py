@@ -298,3 +298,43 @@ def test_bench_integer_shell_closed_form():
         assert np.array_equal(bench.integer_shell_counts(N), ref)
     assert bench.integer_shell_counts(16).tolist()[:8] == [18, 62, 98, 210, 350, 450, 602, 687]
     assert bench.integer_shell_counts(64).sum() == 143457 and bench.integer_shell_counts(256).sum() == 8886577
+
+
+@pytest.mark.parametrize("N,nranks", [(64, 1), (128, 2), (256, 1), (512, 4), (1024, 1), (1024, 2), (1024, 8), (500, 1), (1000, 1),
+                                      (2048, 8), (250, 1)])
+def test_x_pass_tensor_map_addresses_the_blocked_layout(built, N, nranks):
+    """The tensor map the TMA-fed x pass encodes (vp_fft_x_layout: host arithmetic, the same function the launcher uses) must
+    address exactly the blocked half spectrum the y pass stores (csrc/fft3d.cu YDest): for every (x, ky, kz) the box
+    coordinates the kernel issues -- (0, ky % kyb, zt, q*box_x, ky / kyb) -- plus the position inside the box reach complex
+    number ((((ky/kyb)*N + x)*tiles + zt)*kyb + ky%kyb)*C + c; the map obeys the TMA rules (16-byte strides and box rows,
+    box dims <= 256) and the ring fits the 227 KB of a CTA whenever the TMA kernel is selected."""
+    from vpower import _lib
+    kzc = N // 2 // nranks
+    g = _lib.fft_x_layout(N, kzc)
+    C, kyb, tiles, bx = g["C"], g["kyb"], g["tiles"], g["box_x"]
+    assert tiles * C == kzc and N % kyb == 0 and N % bx == 0 and g["boxes"] == N // bx
+    dims, strides, box = g["dims"], [4] + g["strides"], g["box"]
+    assert dims == [2 * C, kyb, tiles, N, N // kyb] and box == [2 * C, 1, 1, bx, 1]
+    assert np.prod(dims) * 4 == N * N * kzc * 8                      # the map covers the rank's cube exactly
+    expect_tma = N not in (250, 2048)
+    assert g["tma"] == expect_tma
+    if g["tma"]:
+        assert all(s % 16 == 0 for s in strides[1:]) and (box[0] * 4) % 16 == 0 and max(box) <= 256
+        assert g["smem_bytes"] <= 227 * 1024 and g["box_slot_bytes"] % 128 == 0 and g["box_slot_bytes"] >= bx * C * 8
+        assert g["ring_items"] in (1, 2) and g["threads"] <= 1024
+    rng = np.random.default_rng(N + nranks)
+    n = 4000
+    x, ky, zt, c = rng.integers(0, N, n), rng.integers(0, N, n), rng.integers(0, tiles, n), rng.integers(0, C, n)
+    blocked = ((((ky // kyb) * N + x) * tiles + zt) * kyb + ky % kyb) * C + c          # complex index, YDest / k_fft_x_pow
+    q, xin = x // bx, x % bx                                                           # box of the item, row inside the box
+    coord = np.stack([2 * c, ky % kyb, zt, q * bx + xin, ky // kyb], axis=1).astype(np.int64)
+    byte = (coord * np.asarray(strides, dtype=np.int64)).sum(axis=1)
+    assert np.array_equal(byte, blocked * 8)
+    # shared-memory side: box q lands at q*slot, dense [box_x][C] complex -- what the kernel's register loads index
+    smem = q * g["box_slot_bytes"] + (xin * C + c) * 8
+    assert np.all(smem + 8 <= g["boxes"] * g["box_slot_bytes"])
+    # corner cases of the index range
+    for (xx, kk, zz, cc) in ((0, 0, 0, 0), (N - 1, N - 1, tiles - 1, C - 1)):
+        b = ((((kk // kyb) * N + xx) * tiles + zz) * kyb + kk % kyb) * C + cc
+        co = np.array([2 * cc, kk % kyb, zz, xx, kk // kyb], dtype=np.int64)
+        assert int((co * np.asarray(strides, dtype=np.int64)).sum()) == b * 8 and b < N * N * kzc
