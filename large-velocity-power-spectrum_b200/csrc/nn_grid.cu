@@ -1642,6 +1642,7 @@ int nn_grid_typed(vp_ctx* ctx, const T* pos, int64_t np, const double* qx, int n
             else k_bin_scatter<T, false, 1024, true><<<nfull, 1024, ssmem, st>>>(p, pin, n_c, i0, g, cursor, t0, rec1);
           }
           if (nfull < nbk) {
+            if (nfull) ctx->n_launch += 1;      // (the stage counts one launch; the ragged last tile is a second one)
             const int64_t done = int64_t(nfull) * kBinTile;
             PayloadIn<T> pt = pin;
             if (pt.vel) pt.vel += size_t(g.vs) * done;
