@@ -142,6 +142,7 @@ def install(engine="oracle"):
         def build(self, n_trees, n_jobs=-1):
             n = len(self.items)
             self.data = np.stack([self.items[i] for i in range(n)]).astype(np.float64)
+            self.tree = None
 
         def save(self, path):
             np.save(path + ".npy", self.data)
@@ -149,10 +150,14 @@ def install(engine="oracle"):
 
         def load(self, path):
             self.data = np.load(path + ".npy")
+            self.tree = None
 
         def get_nns_by_vector(self, q, n=1, search_k=-1, include_distances=False):
             qq = np.asarray(q, dtype=np.float32).astype(np.float64)[None, :]
-            return [int(orc.nn_exact_points(self.data, qq)[0])]
+            if self.tree is None:                 # one kd-tree per index, not one per query (the decision stays the oracle's)
+                from scipy.spatial import cKDTree
+                self.tree = cKDTree(self.data)
+            return [int(orc.nn_exact_points(self.data, qq, tree=self.tree)[0])]
 
     annoy.AnnoyIndex = AnnoyIndex
     sys.modules["annoy"] = annoy

@@ -82,7 +82,7 @@ def _d2(q, p):
     return (dx * dx + dy * dy) + dz * dz
 
 
-def nn_exact_points(data_pos, query_pos, kcand=4, return_ties=False):
+def nn_exact_points(data_pos, query_pos, kcand=4, return_ties=False, tree=None):
     """Index of the nearest data point for every query point.
 
     Contract (BASELINE.json north_star; reference call interp.py:1027-1037 with
@@ -98,8 +98,9 @@ def nn_exact_points(data_pos, query_pos, kcand=4, return_ties=False):
     qry = np.ascontiguousarray(query_pos, dtype=np.float64)
     n = data.shape[0]
     k = int(min(kcand, n))
-    tree = cKDTree(data)
-    _, cand = tree.query(qry, k=k, workers=-1)
+    if tree is None:                                           # (callers that ask query by query pass their tree of `data`)
+        tree = cKDTree(data)
+    _, cand = tree.query(qry, k=k, workers=-1 if len(qry) > 64 else 1)
     if k == 1:
         cand = cand[:, None]
     d2 = _d2(qry[:, None, :], data[cand])                      # [Nq, k]
