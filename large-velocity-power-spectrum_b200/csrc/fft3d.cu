@@ -6,6 +6,8 @@
 // so the whole transform is in place with a power-of-two pitch.  The kz=0 column therefore carries two real
 // planes a+ib through the y and x passes; they are separated at the end by Hermitian symmetry
 // (k_plane_bin), all other columns are ordinary half-spectrum modes with weight 2.
+// The x pass reads the (blocked) half spectrum through the TMA engine: k_fft_x_pow_tma, tensor-map boxes into a shared-memory
+// ring with mbarrier completion; k_fft_x_pow (per-thread loads) serves the row-major layout, N = 250 and N = 2048.
 #include <cuda.h>   // CUtensorMap and its enums (types only: the encoder is looked up through the runtime, no -lcuda)
 #include <math.h>
 #include <stdlib.h>

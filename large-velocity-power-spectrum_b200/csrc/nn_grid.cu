@@ -4,8 +4,10 @@
 // this are in profiles/r2_ubench_scatter_gather.jsonl: a random scatter of whole 32-byte sectors inside a <= 32 MB
 // window runs at the copy rate, a random gather over the whole array at a quarter of it):
 //   1. k_bin_hist     particles per BUCKET (a bucket = 2^bshift consecutive cells of the linear cell order)
-//   2. k_bin_scatter  every particle's packed 32-byte record is appended to its bucket (one cursor atomic per particle;
-//                        the append frontiers of all buckets together are a few hundred KB, so L2 merges the sectors)
+//   2. k_bin_scatter_wc  every particle's packed 32-byte record is appended to its bucket: a tile of 4096 particles claims one
+//                        run per touched bucket, is put in bucket order in shared memory and written out by consecutive lanes
+//                        (the append frontiers of all buckets together are a few hundred KB, so L2 merges the sectors);
+//                        k_bin_scatter (records stored straight from registers) serves ragged tiles and strided input
 //   3. k_cell_count      records are now grouped by bucket: per-cell counts with L2-resident atomics
 //   4. exclusive scan    -> the cell-start table
 //   5. k_cell_place      counting-sort placement inside the bucket's window; the record is rewritten in search format
