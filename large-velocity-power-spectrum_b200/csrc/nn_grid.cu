@@ -621,11 +621,6 @@ __global__ void __launch_bounds__(256) k_cell_place(const void* __restrict__ rec
   if (nfar) atomicAdd(&stats->n_far, (unsigned long long)nfar);
 }
 
-__global__ void k_fill_u32(uint32_t* a, int64_t n, uint32_t v) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = v;
-}
-
 struct Best {
   double d2;
   int idx;
